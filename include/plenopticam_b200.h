@@ -1,0 +1,146 @@
+/*
+ * plenopticam_b200 — C-ABI of the B200-native light-field hot path (libpcb200.so).
+ *
+ * Drop-in boundary for hahnec/plenopticam's data-parallel path.  The reference has no FFI of its own
+ * (it is pure Python); each entry point below replaces the numpy/scipy body of one reference method and
+ * is what a ctypes binding inside that method would call.  Citations are
+ * file:line in /root/reference/plenopticam/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *   - no allocation, no synchronisation inside: work is enqueued on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream) and the call returns immediately;
+ *   - images are dense, row-major, channel-interleaved (H, W, C) exactly like the reference's ndarrays;
+ *     the 4-D light field is (M, M, S, T, C) = vp_img_arr[j, i, s, t, c];
+ *   - return value: PCB_OK or an error code; pcb_last_error() gives the text (thread-local).
+ */
+#ifndef PLENOPTICAM_B200_H
+#define PLENOPTICAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCB_OK               0
+#define PCB_ERR_INVALID      1   /* bad argument (null pointer, non-positive size, unsupported dtype)  */
+#define PCB_ERR_CUDA         2   /* a CUDA runtime call / launch failed                                  */
+#define PCB_ERR_UNSUPPORTED  3   /* valid in the reference but not offered by this library              */
+
+/* element types of image buffers */
+#define PCB_U16 0
+#define PCB_F32 1
+#define PCB_U8  2
+
+/* micro-lens arrangement: cfg.calibs['pat_type'] */
+#define PCB_REC 0
+#define PCB_HEX 1
+
+/* One calibrated micro-lens, prepared on the host in float64 so that `rint` (round-half-even,
+ * misc/type_checks.py:57-58) is bit-exact:  for centroid (my, mx), ry = rint(my), fy = my - ry,
+ *   oy = ry - M/2 + floor(fy)   first raw row read for patch row v = 0
+ *   wy = fy - floor(fy)         bilinear weight of row oy+v+1                     (same for x)
+ * A lens whose (M+2)^2 window leaves the image (lfp_local_resampler.py:50,58-60 -> zero patch) has
+ * oy = PCB_LENS_INVALID. */
+#define PCB_LENS_INVALID INT32_MIN
+typedef struct { int32_t oy, ox; float wy, wx; } pcb_lens_t;
+
+/* One output lens column k of the hex->rectilinear stretch (lfp_local_resampler.py:129-136):
+ * out = P[x0] + (P[x1] - P[x0]) * w.  Two tables of Xs entries: row parity (ly + hex_odd) % 2 = 0, 1.
+ * For PCB_REC pass NULL (identity). */
+typedef struct { int32_t x0, x1; float w; int32_t reserved; } pcb_hexcol_t;
+
+/* Order-preserving uint32 keys of the running float min / max (keys[0] = min, keys[1] = max). */
+typedef struct { uint32_t kmin, kmax; } pcb_minmax_t;
+
+int         pcb_version(void);
+const char *pcb_last_error(void);
+float       pcb_key_to_float(uint32_t key);         /* host helper: decode a pcb_minmax_t key           */
+
+/* Reset a pcb_minmax_t to (+inf, -inf). */
+int pcb_minmax_reset(pcb_minmax_t *mm, void *stream);
+/* Fold n float32 values into *mm (atomic). */
+int pcb_minmax_f32(const float *data, int64_t n, pcb_minmax_t *mm, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (a) Micro-image resampling — replaces LfpLocalResampler.resample_rec / resample_hex / _patch_align
+ *     (lfp_aligner/lfp_local_resampler.py:44-148, method 'linear') and, for the _u16 form, the
+ *     quantisation in LfpResampler._write_lfp_align (lfp_aligner/lfp_resampler.py:60,
+ *     misc/normalizer.py:33-46,69-78).
+ *   raw (H,W,C) of raw_dtype;  lens[LY*LX];  hexcol[2*Xs] or NULL;  Xs = LX for PCB_REC.
+ *   Output aligned image: (LY*M, Xs*M, C).
+ *   pcb_resample_minmax : no image output, folds min/max of the float32 aligned values into *mm
+ *   pcb_resample_f32    : float32 aligned image (and min/max if mm != NULL)
+ *   pcb_resample_u16    : recomputes and writes uint16(round_half_even(clip((x-min)/(max-min))*65535))
+ *                         using *mm read on the device (no host round trip between the two passes)
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_resample_minmax(const void *raw, int raw_dtype, int H, int W, int C,
+                        const pcb_lens_t *lens, int LY, int LX, int M,
+                        int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,
+                        pcb_minmax_t *mm, void *stream);
+int pcb_resample_f32(const void *raw, int raw_dtype, int H, int W, int C,
+                     const pcb_lens_t *lens, int LY, int LX, int M,
+                     int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,
+                     float *aligned, pcb_minmax_t *mm, void *stream);
+int pcb_resample_u16(const void *raw, int raw_dtype, int H, int W, int C,
+                     const pcb_lens_t *lens, int LY, int LX, int M,
+                     int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,
+                     const pcb_minmax_t *mm, uint16_t *aligned, void *stream);
+/* Normalizer.uint16_norm on an existing float32 buffer (misc/normalizer.py:43-46). */
+int pcb_quantize_u16(const float *in, int64_t n, const pcb_minmax_t *mm, uint16_t *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (a') Rotation — replaces LfpRotator._rotate_img (lfp_aligner/lfp_rotator.py:129-145):
+ *     scipy.ndimage.rotate(img, deg, reshape=False, order=3, mode='constant', cval=0).
+ *   pcb_spline_prefilter : cubic B-spline coefficients (mirror boundary), separable, float32;
+ *                          `tmp` and `coef` are (H,W,C) float32 scratch/outputs.
+ *   pcb_rotate_sample    : out[y,x] = sum 4x4 B-spline taps of coef at R(y,x), 0 outside [0,H-1]x[0,W-1]
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_spline_prefilter(const void *img, int dtype, int H, int W, int C, float *tmp, float *coef, void *stream);
+int pcb_rotate_sample(const float *coef, int H, int W, int C, double rad, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (b) Viewpoint gather — replaces LfpRearranger.compose_viewpoints / decompose_viewpoints
+ *     (lfp_extractor/lfp_rearranger.py:79-137) with LfpCropper.crop_micro_image
+ *     (lfp_extractor/lfp_cropper.py:58-62) folded into the index math.
+ *   aligned (rows, cols, C) with micro images of M_in px; vp (M_out, M_out, rows/M_in, cols/M_in, C);
+ *   crop margin k = (M_in - M_out)/2.  dtype preserved (bit-exact copy).
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_viewpoints(const void *aligned, int dtype, int rows, int cols, int C, int M_in, int M_out,
+                   void *vp, void *stream);
+int pcb_viewpoints_inverse(const void *vp, int dtype, int M, int S, int T, int C, void *aligned, void *stream);
+int pcb_crop_micro_images(const void *aligned, int dtype, int rows, int cols, int C, int M_in, int M_out,
+                          void *cropped, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (c) Shift-and-sum refocus — replaces LfpShiftAndSum.refo_from_vp without refinement
+ *     (lfp_refocuser/lfp_shiftandsum.py:77-139) including circular_view_aperture
+ *     (lfp_extractor/lfp_viewpoints.py:229-250) and the /M scaling (:89):
+ *       out[n,y,x,c] = (1/M) * sum_{(j,i): !view_zeroed[j*M+i]} vp[j,i,clamp(y+a_n(c0-j)),clamp(x+a_n(c0-i)),c]
+ *   uint16 input is accumulated exactly in integers; out is float32 (N,S,T,C).  M must be odd.
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C,
+                    const int32_t *a_list, int N, const uint8_t *view_zeroed,
+                    float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Post-processing of the stack — replaces LfpContrast.auto_hist_align + GammaConverter.srgb_conv as used
+ * by LfpRefocuser.shift_and_sum (lfp_refocuser/top_level.py:68-70; lfp_extractor/lfp_contrast.py:249-263;
+ * misc/normalizer.py:53-78; misc/gamma_converter.py:32-44).
+ *   pcb_percentile_f32 : numpy-style linear-interpolated percentiles (exact order statistics by radix
+ *                        select).  luma != 0 -> values are BT.709 luma of C=3 pixels (rgb2gry), n pixels.
+ *                        `q_host` are percents in [0,100]; results (float64) go to `result` (device, nq).
+ *                        `scratch` >= pcb_percentile_scratch_bytes() bytes.
+ *   pcb_contrast_srgb  : y = clip((x-lo)/(hi-lo),0,1) evaluated in float64, cast to float32, then sRGB OETF.
+ *                        lo/hi are read from the device (`lohi` = 2 doubles).
+ * ------------------------------------------------------------------------------------------------ */
+int64_t pcb_percentile_scratch_bytes(void);
+int pcb_percentile_f32(const float *data, int64_t n, int luma, const double *q_host, int nq,
+                       double *result, void *scratch, void *stream);
+int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLENOPTICAM_B200_H */

@@ -1,0 +1,511 @@
+"""CPU oracle: a numpy restatement of PlenoptiCam's data-parallel light-field hot path.
+
+TEST INFRASTRUCTURE ONLY.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
+`--impl reference` legs may import this module, and only as the checker or as the reported CPU
+baseline.  The product package (`plenopticam_b200/`) never imports it and has no CPU fallback.
+
+Parity pinning: the reference's own test-suite holds NO golden vectors / known-answer tests for this
+path (its integration tests only assert `main()` is True).  The oracle is therefore
+pinned against OUTPUTS OF THE REFERENCE ITSELF, produced in the build container by importing the
+unmodified reference through `oracle/ref_shim.py` (see `oracle/gen_golden.py`; vectors are committed
+under `tests/golden/`).  One third-party function stays "parity unpinned": `color_space_converter.rgb2gry`
+(source absent; assumed BT.709 luma) which only feeds the lower contrast percentile.
+
+All file:line citations are relative to /root/reference/plenopticam/.
+All arithmetic is float64 unless the reference itself uses float32 (Normalizer).
+"""
+import numpy as np
+import scipy.ndimage
+from scipy.interpolate import make_interp_spline
+
+
+# ----------------------------------------------------------------------------------------------------
+# misc/type_checks.py:57-58  rint = int(round(val))  (Python round-half-even on float64)
+# ----------------------------------------------------------------------------------------------------
+def rint(val):
+    return int(round(float(val)))
+
+
+def rint_arr(a):
+    """Vectorised `rint`: np.rint is round-half-even like Python's round()."""
+    return np.rint(np.asarray(a, dtype=np.float64)).astype(np.int64)
+
+
+# ----------------------------------------------------------------------------------------------------
+# lfp_aligner/lfp_microlenses.py
+# ----------------------------------------------------------------------------------------------------
+def get_hex_direction(centroids):
+    """lfp_microlenses.py:221-245 — True if the lens row below the upper-left lens is shifted right."""
+    centroids = np.asarray(centroids, dtype=np.float64)
+    first_mic = centroids[(centroids[:, 2] == 0) & (centroids[:, 3] == 0), :][0, :2]
+    central_row_idx = int(centroids[:, 3].max() / 2)
+    mean_pitch = np.mean(np.diff(centroids[centroids[:, 3] == central_row_idx, 0]))
+    found = centroids[(centroids[:, 0] > first_mic[0] + mean_pitch / 2) &
+                      (centroids[:, 0] < first_mic[0] + 3 * mean_pitch / 2) &
+                      (centroids[:, 1] < first_mic[1]) &
+                      (centroids[:, 1] > first_mic[1] - 3 * mean_pitch / 4)]
+    return bool(found.size == 0)
+
+
+def centroid_avg_pitch(centroids):
+    """lfp_microlenses.py:159-174 — (mean_pitch_y, mean_pitch_x), ceil'ed ints."""
+    centroids = np.asarray(centroids, dtype=np.float64)
+    central_row_idx = int(max(centroids[:, 2]) / 2)
+    central_col_idx = int(max(centroids[:, 3]) / 2)
+    mean_pitch_x = int(np.ceil(np.mean(np.diff(centroids[centroids[:, 2] == central_row_idx, 1]))))
+    mean_pitch_y = int(np.ceil(np.mean(np.diff(centroids[centroids[:, 3] == central_col_idx, 0]))))
+    return np.array([mean_pitch_y, mean_pitch_x])
+
+
+def safe_pitch(cavg_pitch, user_pitch):
+    """lfp_microlenses.py:121-157 restricted to the case `limg_pitch == 0` (no previous alignment)."""
+    safe = 3
+    if safe <= user_pitch <= cavg_pitch + 2:
+        safe = user_pitch
+    elif user_pitch > cavg_pitch:
+        safe = cavg_pitch
+    elif user_pitch < safe < cavg_pitch:
+        safe = cavg_pitch
+    return int(safe)
+
+
+def dense_centroid_table(centroids):
+    """lfp_microlenses.py:49-53,113-119 — `get_coords_by_idx` for every (ly, lx) as one (LY,LX,2) array.
+
+    The reference takes the FIRST table row matching (ly, lx); a missing lenslet raises IndexError."""
+    c = np.asarray(centroids, dtype=np.float64)
+    LY = int(c[:, 2].max() + 1)
+    LX = int(c[:, 3].max() + 1)
+    tab = np.full((LY, LX, 2), np.nan)
+    # iterate backwards so that the first occurrence wins
+    ly = c[::-1, 2].astype(np.int64)
+    lx = c[::-1, 3].astype(np.int64)
+    ok = (c[::-1, 2] == ly) & (c[::-1, 3] == lx) & (ly >= 0) & (lx >= 0)
+    tab[ly[ok], lx[ok]] = c[::-1][ok, :2]
+    if np.isnan(tab).any():
+        raise IndexError("lenslet index missing from centroid table (lfp_microlenses.py:119)")
+    return tab
+
+
+# ----------------------------------------------------------------------------------------------------
+# lfp_aligner/lfp_local_resampler.py — K1 (patch), rec tiling, K2 (hex stretch)
+# ----------------------------------------------------------------------------------------------------
+def patches(raw, centroids, M, flip=False):
+    """lfp_local_resampler.py:44-65,91-95,122-127 — P[ly,lx,v,u,ch], method='linear'.
+
+    Window = raw[ry-c-1 : ry+c+2, rx-c-1 : rx+c+2]; FITPACK k=1 spline evaluated at
+    arange(M+2) + (m - rint(m)), cropped [1:-1, 1:-1].  For the surviving samples this is plain bilinear
+    interpolation at (ry-c+v+fy, rx-c+u+fx).  A window that leaves the image (or an even M, for which the
+    window is (M+3)^2) yields an all-zero patch (:50,:58-60)."""
+    raw = np.asarray(raw, dtype=np.float64)
+    if raw.ndim == 2:
+        raw = raw[..., None]
+    H, W, C = raw.shape
+    tab = dense_centroid_table(centroids)
+    LY, LX = tab.shape[:2]
+    c = M // 2
+    out = np.zeros((LY, LX, M, M, C))
+    if M % 2 == 0:
+        return out
+    ry = rint_arr(tab[..., 0])
+    rx = rint_arr(tab[..., 1])
+    fy = tab[..., 0] - ry
+    fx = tab[..., 1] - rx
+    valid = (ry - c - 1 >= 0) & (ry + c + 2 <= H) & (rx - c - 1 >= 0) & (rx + c + 2 <= W)
+    fly = np.floor(fy).astype(np.int64)   # -1 or 0
+    flx = np.floor(fx).astype(np.int64)
+    wy = fy - fly
+    wx = fx - flx
+    v = np.arange(M)
+    for ly in range(LY):
+        ok = valid[ly]
+        if not ok.any():
+            continue
+        y0 = (ry[ly, ok] - c + fly[ly, ok])[:, None] + v[None, :]            # (n, M)
+        x0 = (rx[ly, ok] - c + flx[ly, ok])[:, None] + v[None, :]            # (n, M)
+        Y0 = y0[:, :, None]
+        X0 = x0[:, None, :]
+        a00 = raw[Y0, X0]
+        a01 = raw[Y0, X0 + 1]
+        a10 = raw[Y0 + 1, X0]
+        a11 = raw[Y0 + 1, X0 + 1]
+        WX = wx[ly, ok][:, None, None, None]
+        WY = wy[ly, ok][:, None, None, None]
+        top = a00 + (a01 - a00) * WX
+        bot = a10 + (a11 - a10) * WX
+        out[ly, ok] = top + (bot - top) * WY
+    if flip:
+        out = out[:, :, ::-1, ::-1]
+    return out
+
+
+def hex_columns(LX, ly, hex_odd):
+    """lfp_local_resampler.py:110,134-136 — for output lens column k: source column x0 and lerp weight.
+
+    interp_coords = linspace(0, LX, Xs) + .5*mod(ly+hex_odd, 2); np.interp clamps to [0, LX-1]."""
+    Xs = int(np.round(2 * LX / np.sqrt(3)))
+    coords = np.linspace(0, LX, int(np.round(LX * 2 / np.sqrt(3)))) + .5 * np.mod(ly + hex_odd, 2)
+    xc = np.clip(coords, 0, LX - 1)
+    x0 = np.floor(xc).astype(np.int64)        # == LX-1 only where xc == LX-1 (then w == 0: np.interp's fp[-1])
+    w = xc - x0
+    return Xs, x0, w
+
+
+def resample_rec(raw, centroids, M, flip=False):
+    """lfp_local_resampler.py:76-104 — aligned[ly*M+v, lx*M+u] = P[ly,lx,v,u]."""
+    P = patches(raw, centroids, M, flip)
+    LY, LX, _, _, C = P.shape
+    return P.transpose(0, 2, 1, 3, 4).reshape(LY * M, LX * M, C)
+
+
+def resample_hex(raw, centroids, M, flip=False, hex_odd=None):
+    """lfp_local_resampler.py:106-148 — per lens row, np.interp along lx onto Xs = round(2*LX/sqrt(3))
+    columns, then tile."""
+    P = patches(raw, centroids, M, flip)
+    LY, LX, _, _, C = P.shape
+    if hex_odd is None:
+        hex_odd = get_hex_direction(centroids)
+    Xs = int(np.round(2 * LX / np.sqrt(3)))
+    out = np.zeros((LY * M, Xs * M, C))
+    for ly in range(LY):
+        _, x0, w = hex_columns(LX, ly, hex_odd)
+        p0 = P[ly, x0]                      # (Xs, M, M, C)
+        p1 = P[ly, np.minimum(x0 + 1, LX - 1)]
+        # np.interp arithmetic: slope*(x - xp[j]) + fp[j]
+        st = (p1 - p0) * w[:, None, None, None] + p0
+        out[ly * M:(ly + 1) * M] = st.transpose(1, 0, 2, 3).reshape(M, Xs * M, C)
+    return out
+
+
+def resample(raw, centroids, M, pat_type, flip=False):
+    """lfp_local_resampler.py:29-42 dispatch."""
+    if pat_type == 'rec':
+        return resample_rec(raw, centroids, M, flip)
+    if pat_type == 'hex':
+        return resample_hex(raw, centroids, M, flip)
+    raise ValueError(pat_type)
+
+
+# ----------------------------------------------------------------------------------------------------
+# misc/normalizer.py — float32 arithmetic
+# ----------------------------------------------------------------------------------------------------
+def norm_fun(data32, mn, mx):
+    """normalizer.py:69-78.  `data32` float32; mn/mx keep their own type (NumPy promotion applies:
+    a numpy float64 scalar promotes the expression to float64, a float32 scalar keeps float32)."""
+    if mx != mn and mx != 0:
+        norm = (data32 - mn) / (mx - mn)
+    else:
+        norm = data32.copy()
+    norm[norm < 0] = 0
+    norm[norm > 1] = 1
+    return norm
+
+
+def uint16_norm(aligned):
+    """lfp_resampler.py:60 + normalizer.py:33-46 — global min/max of the float32 cast, round-half-even."""
+    d = np.asarray(aligned, dtype='float32')
+    mn, mx = d.min(), d.max()
+    return np.asarray(np.round(norm_fun(d, mn, mx) * (2 ** 16 - 1)), dtype=np.uint16)
+
+
+# ----------------------------------------------------------------------------------------------------
+# lfp_aligner/lfp_rotator.py — K0
+# ----------------------------------------------------------------------------------------------------
+def estimate_rad(centroids):
+    """lfp_rotator.py:68-118 — OLS slopes of middle lens row / every-other lens of middle column."""
+    c = np.asarray(centroids, dtype=np.float64)
+    mid_row_idx = int(c[:, 2].max() / 2)
+    mid_col_idx = int(c[:, 3].max() / 2)
+    mid_row = c[c[:, 2] == mid_row_idx][:, :2]
+    mid_col = c[c[:, 3] == mid_col_idx][:, :2][0::2]
+    A = np.vstack([np.ones(len(mid_row)), mid_row[:, 1]]).T
+    slope_row = np.dot(np.linalg.pinv(A), mid_row[:, 0])[1]
+    A = np.vstack([np.ones(len(mid_col)), mid_col[:, 0]]).T
+    slope_col = np.dot(np.linalg.pinv(A), mid_col[:, 1])[1]
+    return (np.arctan(slope_row) + np.arctan(slope_col) * -1) / 2
+
+
+def rotate_img(img, rad):
+    """lfp_rotator.py:129-145 — scipy.ndimage.rotate(order=3, reshape=False); skipped if the angle is 0.
+    scipy is the reference's own third-party dependency and is installed, so it is called directly."""
+    deg = rad * 180 / np.pi
+    if deg != 0:
+        return scipy.ndimage.rotate(np.asarray(img), angle=deg, reshape=False, order=3)
+    return np.asarray(img)
+
+
+def rotate_img_closed_form(img, rad):
+    """Closed form of the call above, used to document what the CUDA kernel computes:
+    coef = spline_filter(order 3, mirror); out[y,x] = sum_{p,q} B(Y-floor(Y))[p] B(X-floor(X))[q] coef[...]
+    with (Y,X) = R (y,x - ctr) + ctr, zero outside [0,H-1]x[0,W-1]."""
+    img = np.asarray(img, dtype=np.float64)
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[..., None]
+    H, W, C = img.shape
+    cs, sn = np.cos(rad), np.sin(rad)
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing='ij')
+    cy, cx = (H - 1) / 2., (W - 1) / 2.
+    Y = cs * (yy - cy) + sn * (xx - cx) + cy
+    X = -sn * (yy - cy) + cs * (xx - cx) + cx
+    out = np.zeros_like(img)
+    for ch in range(C):
+        out[..., ch] = scipy.ndimage.map_coordinates(img[..., ch], [Y, X], order=3, mode='constant', cval=0.0)
+    return out[..., 0] if squeeze else out
+
+
+def rotate_centroids(centroids, rad, shape):
+    """lfp_rotator.py:147-172 — rotate (y,x) columns about (shape-1)/2."""
+    c = np.array(centroids, dtype=np.float64)
+    ctr = (np.asarray(shape[:2]) - 1) / 2.
+    c[:, :2] -= ctr
+    Rz = np.array([[np.cos(rad), -np.sin(rad)], [np.sin(rad), np.cos(rad)]])
+    c[:, :2] = np.dot(Rz, c[:, :2].T).T
+    c[:, :2] += ctr
+    return c
+
+
+# ----------------------------------------------------------------------------------------------------
+# lfp_extractor — K4, K5, K6
+# ----------------------------------------------------------------------------------------------------
+def crop_micro_images(aligned, M_in, M_out):
+    """lfp_cropper.py:34,46-62 — central crop of every micro image, margin k = (M_in - M_out)//2."""
+    aligned = np.asarray(aligned)
+    if M_out == M_in:
+        return aligned
+    k = (M_in - M_out) // 2
+    LY, LX = aligned.shape[0] // M_in, aligned.shape[1] // M_in
+    a = aligned[:LY * M_in, :LX * M_in].reshape(LY, M_in, LX, M_in, -1)
+    # reference slice: [k + l*M_in : (l+1)*M_in - k] assigned into an M_out-long slot (:60-62);
+    # shapes only agree when M_in - 2k == M_out, i.e. equal parity.
+    a = a[:, k:M_in - k, :, k:M_in - k]
+    return a.reshape(LY * M_out, LX * M_out, aligned.shape[2] if aligned.ndim == 3 else 1)
+
+
+def compose_viewpoints(aligned, M):
+    """lfp_rearranger.py:37-49,79-107 — vp[j,i] = aligned[j::M, i::M, :]; dtype preserved;
+    shape (M, M, int(m/M), int(n/M), p)."""
+    aligned = np.asarray(aligned)
+    if aligned.ndim == 2:
+        aligned = aligned[..., None]
+    m, n, p = aligned.shape
+    S, T = int(m / M), int(n / M)
+    vp = np.zeros([M, M, S, T, p], dtype=aligned.dtype)
+    for j in range(M):
+        for i in range(M):
+            vp[j, i] = aligned[j::M, i::M, :][:S, :T]
+    return vp
+
+
+def decompose_viewpoints(vp):
+    """lfp_rearranger.py:51-68,109-137 — inverse scatter."""
+    vp = np.asarray(vp)
+    if vp.ndim == 4:
+        vp = vp[..., None]
+    Mj, Mi, S, T, p = vp.shape
+    out = np.zeros([S * Mj, T * Mi, p], dtype=vp.dtype)
+    for j in range(Mj):
+        for i in range(Mi):
+            out[j::Mj, i::Mi, :] = vp[j, i]
+    return out
+
+
+def aperture_mask(M):
+    """lfp_viewpoints.py:229-250 — True where the view is ZEROED: int(np.round(sqrt(x^2+y^2))) > M//2."""
+    r = M // 2
+    mask = np.zeros([2 * r + 1, 2 * r + 1], dtype=bool)
+    for x in range(-r, r + 1):
+        for y in range(-r, r + 1):
+            if int(np.round(np.sqrt(x ** 2 + y ** 2))) > r:
+                mask[r + y][r + x] = True
+    return mask
+
+
+# ----------------------------------------------------------------------------------------------------
+# lfp_refocuser/lfp_shiftandsum.py — K7 (integer), K8 (refinement)
+# ----------------------------------------------------------------------------------------------------
+def _apply_aperture(vp, M):
+    vp = np.array(vp, dtype=np.float64)          # lfp_viewpoints.py:35 float64 cast (copy)
+    mask = aperture_mask(M)
+    r = M // 2
+    # the reference indexes vp[coords] with coords in a (2r+1)^2 mask: identical to (M,M) for odd M
+    for y in range(mask.shape[0]):
+        for x in range(mask.shape[1]):
+            if mask[y, x] and y < vp.shape[0] and x < vp.shape[1]:
+                vp[y, x] = 0
+    return vp
+
+
+def refocus_int_slice_padadd(vp64, a, M):
+    """Literal restatement of lfp_shiftandsum.py:94-124 for one `a` (np.pad 'edge' + add, then crop).
+    `vp64` already divided by M and aperture-masked.  Kept for small cases; see refocus_int()."""
+    S, T, C = vp64.shape[2:]
+    overlap = abs(a) * (M - 1)
+    img = np.zeros((S + overlap, T + overlap, 3))
+    for j in range(M):
+        for i in range(M):
+            tb = (abs(a) * j, abs(a) * (M - 1 - j))
+            lr = (abs(a) * i, abs(a) * (M - 1 - i))
+            pad = (tb, lr, (0, 0)) if a >= 0 else (tb[::-1], lr[::-1], (0, 0))
+            img = np.add(img, np.pad(vp64[j, i], pad, 'edge'))
+    crop = int(overlap / 2)
+    return img[crop:-crop, crop:-crop, :] if a != 0 else img
+
+
+def refocus_int_slice(vp64, a, M, skip_zero_views=True):
+    """Closed form of the above for odd M:
+    E_a[y,x] = sum_{j,i} vp[j,i, clamp(y + a(c-j)), clamp(x + a(c-i))], float64, j-major/i-minor order."""
+    S, T, C = vp64.shape[2:]
+    c = M // 2
+    ys = np.arange(S)
+    xs = np.arange(T)
+    out = np.zeros((S, T, C))
+    mask = aperture_mask(M)
+    for j in range(M):
+        yi = np.clip(ys + a * (c - j), 0, S - 1)
+        for i in range(M):
+            if skip_zero_views and mask[j, i]:
+                continue                      # adding an all-zero view is exact
+            xi = np.clip(xs + a * (c - i), 0, T - 1)
+            out += vp64[j, i][yi][:, xi]
+    return out
+
+
+def refocus_int(vp, ran_refo, M):
+    """lfp_shiftandsum.py:48-139 without refinement: aperture mask, /M, one slice per a in range(*ran_refo).
+    Returns float64 (N,S,T,C)."""
+    vp64 = _apply_aperture(vp, M)
+    vp64 /= M                                 # :89 (divisor is M, not M*M)
+    if M % 2 == 0:
+        return np.asarray([refocus_int_slice_padadd(vp64, a, M) for a in range(*ran_refo)])
+    return np.asarray([refocus_int_slice(vp64, a, M) for a in range(*ran_refo)])
+
+
+def spline_resize_matrix(n_in, n_out):
+    """misc/data_proc.py:57-92 — `interp2d(kind='cubic')` == FITPACK interpolating bicubic spline (s=0)
+    == separable not-a-knot cubic spline.  Returns the (n_out, n_in) matrix W such that
+    resized = W @ signal for samples at linspace(0, n_in-1, n_out)."""
+    x = np.arange(n_in, dtype=np.float64)
+    xn = np.linspace(0, n_in - 1, n_out)
+    k = 3 if n_in >= 4 else n_in - 1
+    spl = make_interp_spline(x, np.eye(n_in), k=k, axis=0)
+    return spl(xn)
+
+
+def img_resize(img, scale):
+    """misc/data_proc.py:57-92 with method=None ('cubic'), x_scale=y_scale=scale."""
+    img = np.asarray(img, dtype=np.float64)
+    n, m = img.shape[:2]
+    if scale == 1 or scale <= 0:
+        return img
+    y_len, x_len = int(round(n * scale)), int(round(m * scale))
+    Wy = spline_resize_matrix(n, y_len)
+    Wx = spline_resize_matrix(m, x_len)
+    return np.einsum('yn,nmc,xm->yxc', Wy, img, Wx, optimize=True)
+
+
+def refocus_refi(vp, ran_refo, M):
+    """lfp_shiftandsum.py:77-139 with opt_refi: every view upsampled xM (:102), shifts in upsampled
+    pixels a in range(M*r0, M*r1) (:93-94), summed, cropped (:123-124), downsampled x1/M (:135).
+    Materialises the upsampled views; use only at small sizes."""
+    vp64 = _apply_aperture(vp, M)
+    vp64 /= M
+    S, T, C = vp64.shape[2:]
+    mask = aperture_mask(M)
+    c = M // 2
+    ups = {}
+    for j in range(M):
+        for i in range(M):
+            if not mask[j, i]:
+                ups[(j, i)] = img_resize(vp64[j, i], M)
+    ys = np.arange(S * M)
+    xs = np.arange(T * M)
+    stack = []
+    for a in range(M * ran_refo[0], M * ran_refo[1]):
+        acc = np.zeros((S * M, T * M, C))
+        for j in range(M):
+            yi = np.clip(ys + a * (c - j), 0, S * M - 1)
+            for i in range(M):
+                if mask[j, i]:
+                    continue
+                xi = np.clip(xs + a * (c - i), 0, T * M - 1)
+                acc += ups[(j, i)][yi][:, xi]
+        stack.append(img_resize(acc, 1. / M))
+    return np.asarray(stack)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K9 + K10: lfp_refocuser/top_level.py:68-70
+# ----------------------------------------------------------------------------------------------------
+LUMA_BT709 = np.array([0.2126, 0.7152, 0.0722])
+
+
+def rgb2gry(img):
+    """color_space_converter.rgb2gry — third-party, source absent, unpinned (`>=0.1.4`): assumed BT.709."""
+    return (np.asarray(img)[..., :3] * LUMA_BT709).sum(-1, keepdims=True)
+
+
+def hist_percentiles(ref_img):
+    """lfp_contrast.py:252-255 (opt=True): lo = P0.005 of gray(ref), hi = P99.9 of ref (numpy linear)."""
+    return np.percentile(rgb2gry(ref_img), 0.005), np.percentile(ref_img, 99.9)
+
+
+def auto_hist_align(stack, ref_img):
+    """lfp_contrast.py:249-263 + normalizer.py:33-41,53-78 (float branch of type_norm)."""
+    lo, hi = hist_percentiles(ref_img)
+    d = np.asarray(stack, dtype='float32')
+    mn = d.min() if not lo else lo            # normalizer.py:40-41 (falsy min/max fall back to the data's)
+    mx = d.max() if not hi else hi
+    return np.asarray(norm_fun(d, mn, mx) * (1.0 - 0.0) + 0.0, dtype='float32')
+
+
+def srgb_conv(img):
+    """misc/gamma_converter.py:32-44 forward direction."""
+    new = np.zeros_like(img)
+    new[img >= 0.0031308] = 1.055 * img[img >= 0.0031308] ** (5 / 12) - 0.055
+    new[img < 0.0031308] = img[img < 0.0031308] * 12.92
+    return new
+
+
+def refocuser_postprocess(stack):
+    """lfp_refocuser/top_level.py:68-70."""
+    return srgb_conv(auto_hist_align(stack, stack[0]))
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic data (BASELINE.json configs)
+# ----------------------------------------------------------------------------------------------------
+def synth_centroids(LY, LX, pitch, pat_type='hex', hex_odd=True, jitter=0.15, rot_deg=0.0, origin=None, seed=0):
+    """Centroid table rows [y, x, ly, lx] for a rec / hex MLA with Gaussian jitter and optional rotation.
+    Same row layout as `GridFitter.grid_gen` (lfp_calibrator/grid_fitter.py:215-256)."""
+    rng = np.random.default_rng(seed)
+    py = pitch * (np.sqrt(3) / 2 if pat_type == 'hex' else 1.0)
+    oy, ox = origin if origin is not None else (pitch / 2 + 2.0, pitch / 2 + 2.0)
+    ly, lx = np.meshgrid(np.arange(LY), np.arange(LX), indexing='ij')
+    y = oy + ly * py
+    x = ox + lx * pitch
+    if pat_type == 'hex':
+        x = x + (pitch / 2) * np.mod(ly + (0 if hex_odd else 1), 2)
+    y = y + rng.normal(0, jitter, y.shape)
+    x = x + rng.normal(0, jitter, x.shape)
+    if rot_deg:
+        t = np.deg2rad(rot_deg)
+        cy, cx = y.mean(), x.mean()
+        y, x = (cy + np.cos(t) * (y - cy) + np.sin(t) * (x - cx),
+                cx - np.sin(t) * (y - cy) + np.cos(t) * (x - cx))
+    return np.stack([y.ravel(), x.ravel(), ly.ravel().astype(float), lx.ravel().astype(float)], axis=1)
+
+
+def synth_raw(H, W, C=3, seed=0, dtype=np.uint16):
+    """Low-frequency sinusoid mix + uniform noise, uint16 range (post-demosaic RGB is uint16,
+    lfp_aligner/cfa_processor.py:73)."""
+    rng = np.random.default_rng(seed)
+    yy = np.arange(H, dtype=np.float32)[:, None, None]
+    xx = np.arange(W, dtype=np.float32)[None, :, None]
+    ph = np.arange(C, dtype=np.float32)[None, None, :]
+    img = 0.5 + 0.2 * np.sin(yy / 37.0 + ph) * np.cos(xx / 53.0 - ph) + 0.15 * np.sin((xx + yy) / 11.0 + 2 * ph)
+    img = img + 0.1 * rng.random((H, W, C), dtype=np.float32)
+    img = np.clip(img, 0, 1)
+    if np.issubdtype(dtype, np.integer):
+        return np.round(img * 65535.0).astype(dtype)
+    return img.astype(dtype)

@@ -1,0 +1,137 @@
+"""ctypes binding of libpcb200.so (C-ABI declared in include/plenopticam_b200.h).
+
+There is no CPU fallback: if the library cannot be loaded, every operator raises.  `build()` compiles the
+library in-tree with nvcc for sm_100a (the built .so is git-ignored but travels with the snapshot).
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+import threading
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libpcb200.so")
+HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "plenopticam_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+PCB_U16, PCB_F32, PCB_U8 = 0, 1, 2
+PCB_REC, PCB_HEX = 0, 1
+PCB_LENS_INVALID = -2 ** 31
+
+# numpy mirrors of the C structs
+LENS_DTYPE = np.dtype([("oy", "<i4"), ("ox", "<i4"), ("wy", "<f4"), ("wx", "<f4")])
+HEXCOL_DTYPE = np.dtype([("x0", "<i4"), ("x1", "<i4"), ("w", "<f4"), ("reserved", "<i4")])
+
+_lock = threading.Lock()
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def _sources():
+    return sorted(os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh")))
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources() + [HEADER])
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/pcb200.cu -> libpcb200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise NativeLibraryError("nvcc not found; cannot build %s" % LIB_PATH)
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC_DIR, "pcb200.cu")]
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise NativeLibraryError("nvcc failed:\n" + res.stdout)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+_vp = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+
+_SIGNATURES = {
+    "pcb_version": (C.c_int, []),
+    "pcb_last_error": (C.c_char_p, []),
+    "pcb_key_to_float": (C.c_float, [C.c_uint32]),
+    "pcb_minmax_reset": (_i, [_vp, _vp]),
+    "pcb_minmax_f32": (_i, [_vp, _i64, _vp, _vp]),
+    "pcb_resample_minmax": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "pcb_resample_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "pcb_resample_u16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "pcb_quantize_u16": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "pcb_spline_prefilter": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pcb_rotate_sample": (_i, [_vp, _i, _i, _i, C.c_double, _vp, _vp]),
+    "pcb_viewpoints": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pcb_viewpoints_inverse": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pcb_crop_micro_images": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pcb_refocus_int": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "pcb_percentile_scratch_bytes": (_i64, []),
+    "pcb_percentile_f32": (_i, [_vp, _i64, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
+    "pcb_contrast_srgb": (_i, [_vp, _i64, _vp, _vp, _vp]),
+}
+
+
+def exported_symbols():
+    """Names the header declares and the binding expects."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load (building first if the sources are newer and nvcc is present) and return the CDLL."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _stale():
+            try:
+                build()
+            except NativeLibraryError:
+                if not os.path.exists(LIB_PATH):
+                    raise
+        try:
+            handle = C.CDLL(LIB_PATH)
+        except OSError as e:
+            raise NativeLibraryError("cannot load %s (%s); run `python -c 'import __graft_entry__ as g; g.build()'`"
+                                     % (LIB_PATH, e))
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                raise NativeLibraryError("%s does not export %s" % (LIB_PATH, name))
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().pcb_last_error().decode("utf-8", "replace")
+        if rc == 1:
+            raise ValueError(msg)
+        if rc == 3:
+            raise NotImplementedError(msg)
+        raise RuntimeError(msg)

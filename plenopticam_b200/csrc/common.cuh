@@ -1,0 +1,106 @@
+// Shared helpers for libpcb200.so (sm_100a).  No torch types anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/plenopticam_b200.h"
+
+namespace pcb {
+
+extern thread_local char g_err[512];
+
+inline int fail(int code, const char *fmt, const char *a = "", long long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define PCB_REQUIRE(cond, what)                                                                   \
+    do {                                                                                          \
+        if (!(cond)) return pcb::fail(PCB_ERR_INVALID, "%s: requirement failed: " what, __func__); \
+    } while (0)
+
+#define PCB_LAUNCH_OK()                                                                           \
+    do {                                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess) {                                                                 \
+            snprintf(pcb::g_err, sizeof(pcb::g_err), "%s: CUDA error: %s", __func__,              \
+                     cudaGetErrorString(e__));                                                    \
+            return PCB_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define PCB_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            snprintf(pcb::g_err, sizeof(pcb::g_err), "%s: %s failed: %s", __func__, #call,        \
+                     cudaGetErrorString(e__));                                                    \
+            return PCB_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+// ---- order-preserving float <-> uint32 keys (for atomic min/max and radix select) -----------------
+__host__ __device__ __forceinline__ uint32_t float_to_key(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key_to_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+// ---- typed read-only loads returning float -------------------------------------------------------
+template <typename T> __device__ __forceinline__ float ld_as_float(const T *p);
+template <> __device__ __forceinline__ float ld_as_float<uint16_t>(const uint16_t *p) { return (float)__ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<uint8_t>(const uint8_t *p) { return (float)__ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<float>(const float *p) { return __ldg(p); }
+
+// ---- block-wide min/max fold into a pcb_minmax_t ---------------------------------------------------
+__device__ __forceinline__ void block_minmax_commit(float mn, float mx, pcb_minmax_t *mm) {
+    __shared__ float s_mn[32], s_mx[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        mn = lane < nw ? s_mn[lane] : INFINITY;
+        mx = lane < nw ? s_mx[lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) {
+            atomicMin(&mm->kmin, float_to_key(mn));
+            atomicMax(&mm->kmax, float_to_key(mx));
+        }
+    }
+}
+
+// Normalizer.norm_fun + uint16_norm (misc/normalizer.py:43-46,69-78), float32 arithmetic, IEEE division.
+__device__ __forceinline__ uint16_t quantize_u16(float x, float mn, float mx, bool scale) {
+    float n = scale ? __fdiv_rn(__fsub_rn(x, mn), __fsub_rn(mx, mn)) : x;
+    n = n < 0.f ? 0.f : n;
+    n = n > 1.f ? 1.f : n;
+    return (uint16_t)__float2uint_rn(__fmul_rn(n, 65535.0f));   // round-half-even like np.round
+}
+
+}  // namespace pcb

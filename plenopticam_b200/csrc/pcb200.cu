@@ -1,0 +1,182 @@
+// libpcb200.so — C-ABI entry points (include/plenopticam_b200.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC
+#include "common.cuh"
+#include "post.cuh"
+#include "refocus.cuh"
+#include "resample.cuh"
+#include "rotate.cuh"
+#include "viewpoints.cuh"
+
+namespace pcb {
+thread_local char g_err[512] = "";
+}
+
+using namespace pcb;
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int grid_for(int64_t n, int per_block) {
+    int64_t b = (n + per_block - 1) / per_block;
+    const int64_t cap = 148 * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" {
+
+int pcb_version(void) { return 100; }
+
+const char *pcb_last_error(void) { return g_err; }
+
+float pcb_key_to_float(uint32_t key) { return key_to_float(key); }
+
+int pcb_minmax_reset(pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(mm != nullptr, "mm != NULL");
+    minmax_reset_kernel<<<1, 1, 0, as_stream(stream)>>>(mm);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+int pcb_minmax_f32(const float *data, int64_t n, pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(data != nullptr && mm != nullptr && n > 0, "data, mm, n > 0");
+    minmax_f32_kernel<<<grid_for(n, 256 * 8), 256, 0, as_stream(stream)>>>(data, n, mm);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+static int make_resample_args(ResampleArgs &a, const void *raw, int H, int W, int C, const pcb_lens_t *lens, int LY,
+                              int LX, int M, int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip) {
+    PCB_REQUIRE(raw != nullptr && lens != nullptr, "raw, lens");
+    PCB_REQUIRE(H > 0 && W > 0 && C > 0 && LY > 0 && LX > 0 && M > 0 && Xs > 0, "positive sizes");
+    PCB_REQUIRE(LY <= 65535, "LY <= 65535");
+    PCB_REQUIRE(pattern == PCB_REC || pattern == PCB_HEX, "pattern");
+    PCB_REQUIRE(pattern == PCB_HEX ? hexcol != nullptr : Xs == LX, "hexcol for hex / Xs == LX for rec");
+    PCB_REQUIRE((int64_t)LY * M * (int64_t)Xs * M * C < ((int64_t)1 << 40), "aligned size");
+    PCB_REQUIRE((int64_t)Xs * M * C < ((int64_t)1 << 31), "aligned row length");
+    a.raw = raw; a.H = H; a.W = W; a.C = C;
+    a.lens = lens; a.LY = LY; a.LX = LX; a.M = M;
+    a.hexcol = pattern == PCB_HEX ? hexcol : nullptr;
+    a.Xs = Xs; a.hex_odd = hex_odd ? 1 : 0; a.flip = flip ? 1 : 0;
+    a.ncols = Xs * M * C;
+    return PCB_OK;
+}
+
+int pcb_resample_minmax(const void *raw, int raw_dtype, int H, int W, int C, const pcb_lens_t *lens, int LY, int LX,
+                        int M, int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,
+                        pcb_minmax_t *mm, void *stream) {
+    ResampleArgs a;
+    int rc = make_resample_args(a, raw, H, W, C, lens, LY, LX, M, pattern, hexcol, Xs, hex_odd, flip);
+    if (rc) return rc;
+    PCB_REQUIRE(mm != nullptr, "mm");
+    return launch_resample<RS_MINMAX>(a, raw_dtype, nullptr, nullptr, mm, nullptr, as_stream(stream));
+}
+
+int pcb_resample_f32(const void *raw, int raw_dtype, int H, int W, int C, const pcb_lens_t *lens, int LY, int LX,
+                     int M, int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip, float *aligned,
+                     pcb_minmax_t *mm, void *stream) {
+    ResampleArgs a;
+    int rc = make_resample_args(a, raw, H, W, C, lens, LY, LX, M, pattern, hexcol, Xs, hex_odd, flip);
+    if (rc) return rc;
+    PCB_REQUIRE(aligned != nullptr, "aligned");
+    return launch_resample<RS_F32>(a, raw_dtype, aligned, nullptr, mm, nullptr, as_stream(stream));
+}
+
+int pcb_resample_u16(const void *raw, int raw_dtype, int H, int W, int C, const pcb_lens_t *lens, int LY, int LX,
+                     int M, int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,
+                     const pcb_minmax_t *mm, uint16_t *aligned, void *stream) {
+    ResampleArgs a;
+    int rc = make_resample_args(a, raw, H, W, C, lens, LY, LX, M, pattern, hexcol, Xs, hex_odd, flip);
+    if (rc) return rc;
+    PCB_REQUIRE(aligned != nullptr && mm != nullptr, "aligned, mm");
+    return launch_resample<RS_U16>(a, raw_dtype, nullptr, aligned, nullptr, mm, as_stream(stream));
+}
+
+int pcb_quantize_u16(const float *in, int64_t n, const pcb_minmax_t *mm, uint16_t *out, void *stream) {
+    PCB_REQUIRE(in != nullptr && out != nullptr && mm != nullptr && n > 0, "in, out, mm, n > 0");
+    quantize_u16_kernel<<<grid_for(n, 256 * 8), 256, 0, as_stream(stream)>>>(in, n, mm, out);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+int pcb_spline_prefilter(const void *img, int dtype, int H, int W, int C, float *tmp, float *coef, void *stream) {
+    PCB_REQUIRE(img != nullptr && tmp != nullptr && coef != nullptr, "img, tmp, coef");
+    PCB_REQUIRE(H > 0 && W > 0 && C > 0 && H <= 65535 * PF_ROWS, "sizes");
+    switch (dtype) {
+    case PCB_U16: return launch_prefilter<uint16_t>(img, H, W, C, tmp, coef, as_stream(stream));
+    case PCB_F32: return launch_prefilter<float>(img, H, W, C, tmp, coef, as_stream(stream));
+    case PCB_U8:  return launch_prefilter<uint8_t>(img, H, W, C, tmp, coef, as_stream(stream));
+    }
+    return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
+int pcb_rotate_sample(const float *coef, int H, int W, int C, double rad, float *out, void *stream) {
+    PCB_REQUIRE(coef != nullptr && out != nullptr && H > 0 && W > 0 && C > 0 && H <= 65535, "coef, out, sizes");
+    dim3 grid((W + 255) / 256, H), block(256);
+    rotate_sample_kernel<<<grid, block, 0, as_stream(stream)>>>(coef, out, H, W, C, cos(rad), sin(rad),
+                                                                (H - 1) / 2.0, (W - 1) / 2.0);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+#define PCB_DISPATCH_COPY_DTYPE(dtype, FN, ...)                                           \
+    switch (dtype) {                                                                      \
+    case PCB_U16: return FN<uint16_t>(__VA_ARGS__);                                       \
+    case PCB_F32: return FN<float>(__VA_ARGS__);                                          \
+    case PCB_U8:  return FN<uint8_t>(__VA_ARGS__);                                        \
+    default: return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype); \
+    }
+
+int pcb_viewpoints(const void *aligned, int dtype, int rows, int cols, int C, int M_in, int M_out, void *vp,
+                   void *stream) {
+    PCB_REQUIRE(aligned != nullptr && vp != nullptr, "aligned, vp");
+    PCB_REQUIRE(rows > 0 && cols > 0 && C > 0 && M_in > 0 && M_out > 0 && M_out <= M_in, "sizes, M_out <= M_in");
+    PCB_REQUIRE(rows / M_in > 0 && cols / M_in > 0, "at least one micro image");
+    PCB_REQUIRE((M_in - M_out) % 2 == 0, "M_in - M_out even (lfp_cropper.py:34,60-62)");
+    PCB_DISPATCH_COPY_DTYPE(dtype, launch_viewpoints, aligned, vp, rows, cols, C, M_in, M_out, as_stream(stream));
+}
+
+int pcb_viewpoints_inverse(const void *vp, int dtype, int M, int S, int T, int C, void *aligned, void *stream) {
+    PCB_REQUIRE(aligned != nullptr && vp != nullptr, "aligned, vp");
+    PCB_REQUIRE(M > 0 && S > 0 && T > 0 && C > 0 && M <= 65535, "sizes");
+    PCB_DISPATCH_COPY_DTYPE(dtype, launch_viewpoints_inverse, vp, aligned, M, S, T, C, as_stream(stream));
+}
+
+int pcb_crop_micro_images(const void *aligned, int dtype, int rows, int cols, int C, int M_in, int M_out,
+                          void *cropped, void *stream) {
+    PCB_REQUIRE(aligned != nullptr && cropped != nullptr, "aligned, cropped");
+    PCB_REQUIRE(rows > 0 && cols > 0 && C > 0 && M_in > 0 && M_out > 0 && M_out <= M_in, "sizes, M_out <= M_in");
+    PCB_REQUIRE((M_in - M_out) % 2 == 0, "M_in - M_out even (lfp_cropper.py:34,60-62)");
+    PCB_DISPATCH_COPY_DTYPE(dtype, launch_crop, aligned, cropped, rows, cols, C, M_in, M_out, as_stream(stream));
+}
+
+int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C, const int32_t *a_list, int N,
+                    const uint8_t *view_zeroed, float *out, void *stream) {
+    PCB_REQUIRE(vp != nullptr && a_list != nullptr && view_zeroed != nullptr && out != nullptr, "pointers");
+    PCB_REQUIRE(M > 0 && S > 0 && T > 0 && C > 0 && N > 0 && N <= 65535, "sizes");
+    PCB_REQUIRE(M % 2 == 1, "odd M (even M changes the slice shape, lfp_shiftandsum.py:123-124)");
+    PCB_REQUIRE(dtype != PCB_F32 || true, "");
+    switch (dtype) {
+    case PCB_U16: return launch_refocus_int<uint16_t>(vp, M, S, T, C, a_list, N, view_zeroed, out, as_stream(stream));
+    case PCB_F32: return launch_refocus_int<float>(vp, M, S, T, C, a_list, N, view_zeroed, out, as_stream(stream));
+    case PCB_U8:  return launch_refocus_int<uint8_t>(vp, M, S, T, C, a_list, N, view_zeroed, out, as_stream(stream));
+    }
+    return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
+int64_t pcb_percentile_scratch_bytes(void) { return (int64_t)sizeof(SelectState); }
+
+int pcb_percentile_f32(const float *data, int64_t n, int luma, const double *q_host, int nq, double *result,
+                       void *scratch, void *stream) {
+    PCB_REQUIRE(data != nullptr && q_host != nullptr && result != nullptr && scratch != nullptr, "pointers");
+    PCB_REQUIRE(n > 0 && nq > 0 && nq <= PS_MAXQ, "n > 0, 1 <= nq <= 4");
+    for (int k = 0; k < nq; ++k) PCB_REQUIRE(q_host[k] >= 0.0 && q_host[k] <= 100.0, "0 <= q <= 100");
+    return run_percentile(data, n, luma, q_host, nq, result, scratch, as_stream(stream));
+}
+
+int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, float *out, void *stream) {
+    PCB_REQUIRE(in != nullptr && out != nullptr && lohi != nullptr && n > 0, "in, out, lohi, n > 0");
+    contrast_srgb_kernel<<<grid_for(n, 256 * 8), 256, 0, as_stream(stream)>>>(in, n, lohi, out);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+// Reductions and element-wise epilogues of the hot path:
+//   min/max fold                       (misc/normalizer.py:40-41)
+//   Normalizer.uint16_norm             (misc/normalizer.py:43-46,69-78)
+//   numpy-style percentiles            (lfp_extractor/lfp_contrast.py:252-255) by exact 4x8-bit radix select
+//   auto_hist_align + sRGB             (lfp_contrast.py:261, normalizer.py:53-78, gamma_converter.py:41-42)
+#pragma once
+#include "common.cuh"
+
+namespace pcb {
+
+__global__ void minmax_reset_kernel(pcb_minmax_t *mm) {
+    mm->kmin = 0xffffffffu;
+    mm->kmax = 0u;
+}
+
+__global__ void __launch_bounds__(256)
+minmax_f32_kernel(const float *__restrict__ data, int64_t n, pcb_minmax_t *mm) {
+    float mn = INFINITY, mx = -INFINITY;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = __ldg(data + i);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    block_minmax_commit(mn, mx, mm);
+}
+
+__global__ void __launch_bounds__(256)
+quantize_u16_kernel(const float *__restrict__ in, int64_t n, const pcb_minmax_t *mm, uint16_t *__restrict__ out) {
+    const float mn = key_to_float(mm->kmin), mx = key_to_float(mm->kmax);
+    const bool scale = (mx != mn) && (mx != 0.f);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = quantize_u16(__ldg(in + i), mn, mx, scale);
+}
+
+// ---- contrast + sRGB ------------------------------------------------------------------------------
+// Normalizer(img, min=lo, max=hi).type_norm(): with NumPy >= 2 the float32 data meets float64 percentile
+// scalars, so (x-lo)/(hi-lo) is evaluated in float64, clipped, then cast to float32 (SURVEY §8c iv).
+// GammaConverter.srgb_conv then runs in float32.
+__device__ __forceinline__ float contrast_srgb_one(float x, double lo, double hi, bool scale) {
+    double n = scale ? ((double)x - lo) / (hi - lo) : (double)x;
+    n = n < 0.0 ? 0.0 : n;
+    n = n > 1.0 ? 1.0 : n;
+    const float y = (float)n;
+    return y >= 0.0031308f ? __fsub_rn(__fmul_rn(1.055f, powf(y, (float)(5.0 / 12.0))), 0.055f)
+                           : __fmul_rn(y, 12.92f);
+}
+
+__global__ void __launch_bounds__(256)
+contrast_srgb_kernel(const float *__restrict__ in, int64_t n, const double *__restrict__ lohi, float *__restrict__ out) {
+    const double lo = lohi[0], hi = lohi[1];
+    const bool scale = (hi != lo) && (hi != 0.0);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n >> 2;
+    const float4 *in4 = reinterpret_cast<const float4 *>(in);
+    float4 *out4 = reinterpret_cast<float4 *>(out);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec_ok) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float4 v = __ldg(in4 + i);
+            v.x = contrast_srgb_one(v.x, lo, hi, scale);
+            v.y = contrast_srgb_one(v.y, lo, hi, scale);
+            v.z = contrast_srgb_one(v.z, lo, hi, scale);
+            v.w = contrast_srgb_one(v.w, lo, hi, scale);
+            out4[i] = v;
+        }
+        for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            out[i] = contrast_srgb_one(__ldg(in + i), lo, hi, scale);
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            out[i] = contrast_srgb_one(__ldg(in + i), lo, hi, scale);
+    }
+}
+
+// ---- exact percentiles by radix select -------------------------------------------------------------
+// np.percentile(x, q) (default 'linear'): vidx = q/100*(n-1); lo = floor(vidx); t = vidx-lo;
+// result = lerp(sorted[lo], sorted[lo+1], t).  We find the needed order statistics exactly with four
+// 8-bit histogram passes over order-preserving keys; up to PS_MAXR ranks are resolved together.
+constexpr int PS_MAXQ = 4;
+constexpr int PS_MAXR = 2 * PS_MAXQ;
+
+struct SelectState {
+    uint32_t hist[PS_MAXR][256];
+    uint32_t prefix[PS_MAXR];     // key bits resolved so far (high bits)
+    unsigned long long rank[PS_MAXR];   // remaining rank inside the current prefix bucket
+    int nr;
+    int pad;
+    double q[PS_MAXQ];
+};
+
+__device__ __forceinline__ float select_value(const float *data, int64_t i, int luma) {
+    if (!luma) return __ldg(data + i);
+    // rgb2gry (color_space_converter, third party, unpinned): BT.709 luma
+    const float r = __ldg(data + 3 * i), g = __ldg(data + 3 * i + 1), b = __ldg(data + 3 * i + 2);
+    return (float)(0.2126 * (double)r + 0.7152 * (double)g + 0.0722 * (double)b);
+}
+
+__global__ void select_init_kernel(SelectState *st, int64_t n, int nq, double q0, double q1, double q2, double q3) {
+    const double q[PS_MAXQ] = {q0, q1, q2, q3};
+    if (threadIdx.x == 0) {
+        st->nr = 2 * nq;
+        for (int k = 0; k < nq; ++k) {
+            st->q[k] = q[k];
+            const double vidx = q[k] / 100.0 * (double)(n - 1);
+            long long lo = (long long)floor(vidx);
+            lo = lo < 0 ? 0 : (lo > n - 1 ? n - 1 : lo);
+            const long long hi = lo + 1 > n - 1 ? n - 1 : lo + 1;
+            st->rank[2 * k] = (unsigned long long)lo;
+            st->rank[2 * k + 1] = (unsigned long long)hi;
+            st->prefix[2 * k] = st->prefix[2 * k + 1] = 0;
+        }
+    }
+    for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const float *__restrict__ data, int64_t n, int luma, SelectState *st) {
+    __shared__ uint32_t sh[PS_MAXR][256];
+    __shared__ uint32_t s_prefix[PS_MAXR];
+    const int nr = st->nr;
+    for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+    if (threadIdx.x < PS_MAXR) s_prefix[threadIdx.x] = st->prefix[threadIdx.x];
+    __syncthreads();
+    constexpr int shift = 24 - 8 * PASS;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t key = float_to_key(select_value(data, i, luma));
+        const uint32_t bin = (key >> shift) & 0xffu;
+        if constexpr (PASS == 0) {
+            // all ranks share the first-level histogram
+            atomicAdd(&sh[0][bin], 1u);
+        } else {
+            const uint32_t hi = key >> (shift + 8);
+            for (int r = 0; r < nr; ++r)
+                if (hi == s_prefix[r]) atomicAdd(&sh[r][bin], 1u);
+        }
+    }
+    __syncthreads();
+    const int rows = PASS == 0 ? 1 : nr;
+    for (int i = threadIdx.x; i < rows * 256; i += blockDim.x) {
+        const uint32_t v = (&sh[0][0])[i];
+        if (v) atomicAdd(&(&st->hist[0][0])[i], v);
+    }
+}
+
+template <int PASS>
+__global__ void select_scan_kernel(SelectState *st) {
+    // one warp per rank would do; sizes are tiny, so thread r scans row r serially
+    const int r = threadIdx.x;
+    if (r < st->nr) {
+        const uint32_t *h = PASS == 0 ? st->hist[0] : st->hist[r];
+        unsigned long long k = st->rank[r], cum = 0;
+        int b = 0;
+        for (; b < 256; ++b) {
+            const unsigned long long c = h[b];
+            if (k < cum + c) break;
+            cum += c;
+        }
+        b = b > 255 ? 255 : b;
+        st->rank[r] = k - cum;
+        st->prefix[r] = (st->prefix[r] << 8) | (uint32_t)b;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+}
+
+__global__ void select_finish_kernel(const SelectState *st, int64_t n, double *result) {
+    const int k = threadIdx.x;
+    if (2 * k < st->nr) {
+        const double a = (double)key_to_float(st->prefix[2 * k]);
+        const double b = (double)key_to_float(st->prefix[2 * k + 1]);
+        const double vidx = st->q[k] / 100.0 * (double)(n - 1);
+        const double t = vidx - floor(vidx);
+        // numpy _lerp: a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
+        // (explicit _rn intrinsics: no FMA contraction, so the result is bit-identical to numpy's)
+        const double d = __dsub_rn(b, a);
+        double v = __dadd_rn(a, __dmul_rn(d, t));
+        if (t >= 0.5) v = __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t)));
+        result[k] = v;
+    }
+}
+
+static int run_percentile(const float *data, int64_t n, int luma, const double *q_host, int nq, double *result,
+                          void *scratch, cudaStream_t st) {
+    SelectState *ss = reinterpret_cast<SelectState *>(scratch);
+    double q[PS_MAXQ] = {0, 0, 0, 0};
+    for (int k = 0; k < nq; ++k) q[k] = q_host[k];
+    select_init_kernel<<<1, 256, 0, st>>>(ss, n, nq, q[0], q[1], q[2], q[3]);
+    PCB_LAUNCH_OK();
+    int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+    blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+    select_hist_kernel<0><<<blocks, 256, 0, st>>>(data, n, luma, ss);
+    select_scan_kernel<0><<<1, 256, 0, st>>>(ss);
+    select_hist_kernel<1><<<blocks, 256, 0, st>>>(data, n, luma, ss);
+    select_scan_kernel<1><<<1, 256, 0, st>>>(ss);
+    select_hist_kernel<2><<<blocks, 256, 0, st>>>(data, n, luma, ss);
+    select_scan_kernel<2><<<1, 256, 0, st>>>(ss);
+    select_hist_kernel<3><<<blocks, 256, 0, st>>>(data, n, luma, ss);
+    select_scan_kernel<3><<<1, 256, 0, st>>>(ss);
+    select_finish_kernel<<<1, 32, 0, st>>>(ss, n, result);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+}  // namespace pcb

@@ -1,0 +1,86 @@
+// (c) Integer shift-and-sum refocus stack.
+// Replaces lfp_refocuser/lfp_shiftandsum.py:77-139 (opt_refi off) with circular_view_aperture
+// (lfp_extractor/lfp_viewpoints.py:229-250) and the /M scaling (:89) fused:
+//
+//   out[n,y,x,c] = (1/M) * sum_{j,i active} vp[j,i, clamp(y + a_n(c0-j), 0, S-1), clamp(x + a_n(c0-i), 0, T-1), c]
+//
+// uint16/uint8 light fields are accumulated exactly in 32-bit integers (order independent, so the result
+// is the correctly rounded quotient), float32 ones in float32 in the reference's j-major / i-minor order.
+#pragma once
+#include "common.cuh"
+
+namespace pcb {
+
+template <typename T> struct AccOf { typedef uint32_t type; };
+template <> struct AccOf<float> { typedef float type; };
+
+__device__ __forceinline__ float finish_acc(uint32_t acc, int M) { return (float)((double)acc / (double)M); }
+__device__ __forceinline__ float finish_acc(float acc, int M) { return acc / (float)M; }
+
+constexpr int RF_THREADS = 256;
+constexpr int RF_EPT = 8;   // elements per thread: one CTA covers 2048 consecutive (x,c) elements of a row
+
+template <typename T, int CT>
+__global__ void __launch_bounds__(RF_THREADS)
+refocus_int_kernel(const T *__restrict__ vp, const int32_t *__restrict__ a_list,
+                   const uint8_t *__restrict__ view_zeroed, float *__restrict__ out,
+                   int M, int S, int Tn, int Crt) {
+    typedef typename AccOf<T>::type Acc;
+    const int C = CT ? CT : Crt;
+    const int y = blockIdx.x, n = blockIdx.y;
+    const int e0 = blockIdx.z * (RF_THREADS * RF_EPT);
+    const int ne = Tn * C;
+    const int a = a_list[n];
+    const int c0 = M / 2;
+
+    int xk[RF_EPT], ck[RF_EPT];
+    Acc acc[RF_EPT];
+#pragma unroll
+    for (int k = 0; k < RF_EPT; ++k) {
+        int e = e0 + threadIdx.x + k * RF_THREADS;
+        e = e < ne ? e : ne - 1;
+        xk[k] = e / C;
+        ck[k] = e - xk[k] * C;
+        acc[k] = 0;
+    }
+
+    const size_t view_stride = (size_t)S * Tn * C;
+    for (int j = 0; j < M; ++j) {
+        int r = y + a * (c0 - j);
+        r = max(0, min(S - 1, r));
+        for (int i = 0; i < M; ++i) {
+            if (view_zeroed[j * M + i]) continue;
+            const int dx = a * (c0 - i);
+            const T *rowp = vp + (size_t)(j * M + i) * view_stride + (size_t)r * Tn * C;
+#pragma unroll
+            for (int k = 0; k < RF_EPT; ++k) {
+                const int xs = max(0, min(Tn - 1, xk[k] + dx));
+                acc[k] += (Acc)__ldg(rowp + xs * C + ck[k]);
+            }
+        }
+    }
+
+    float *orow = out + ((size_t)n * S + y) * ne;
+#pragma unroll
+    for (int k = 0; k < RF_EPT; ++k) {
+        const int e = e0 + threadIdx.x + k * RF_THREADS;
+        if (e < ne) orow[e] = finish_acc(acc[k], M);
+    }
+}
+
+template <typename T>
+static int launch_refocus_int(const void *vp, int M, int S, int Tn, int C, const int32_t *a_list, int N,
+                              const uint8_t *view_zeroed, float *out, cudaStream_t st) {
+    const int ne = Tn * C;
+    dim3 grid(S, N, (ne + RF_THREADS * RF_EPT - 1) / (RF_THREADS * RF_EPT)), block(RF_THREADS);
+    if (C == 3)
+        refocus_int_kernel<T, 3><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C);
+    else if (C == 1)
+        refocus_int_kernel<T, 1><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C);
+    else
+        refocus_int_kernel<T, 0><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+}  // namespace pcb

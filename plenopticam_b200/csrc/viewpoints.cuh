@@ -1,0 +1,145 @@
+// (b) Viewpoint gather: aligned micro-image array <-> 4-D sub-aperture array, with the optional central
+// crop of each micro image folded in.  Pure copies, bit-exact, dtype preserved.
+// Replaces lfp_extractor/lfp_rearranger.py:79-137 and lfp_extractor/lfp_cropper.py:58-62.
+//
+//   vp[j, i, s, t, c] = aligned[s*M_in + k + j, t*M_in + k + i, c],   k = (M_in - M_out)/2
+//
+// One CTA owns one aligned row (s, j) (a tile of it when the row exceeds the smem budget): the row is
+// read once, fully coalesced, into shared memory and leaves as M_out contiguous runs, one per view i.
+#pragma once
+#include "common.cuh"
+
+namespace pcb {
+
+template <typename T, int CT>   // CT = compile-time channel count (0 = runtime)
+__global__ void __launch_bounds__(256)
+viewpoints_kernel(const T *__restrict__ aligned, T *__restrict__ vp, int cols_elems, int M_in, int M_out, int kc,
+                  int S, int Tn, int Crt, int tile_t) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *row = reinterpret_cast<T *>(smem_raw);
+    const int C = CT ? CT : Crt;
+    const int s = blockIdx.x, j = blockIdx.y;
+    const int t0 = blockIdx.z * tile_t;
+    const int nt = min(tile_t, Tn - t0);
+    if (nt <= 0) return;
+
+    const T *src = aligned + (size_t)(s * M_in + kc + j) * cols_elems + (size_t)t0 * M_in * C;
+    const int n_in = nt * M_in * C;
+    for (int idx = threadIdx.x; idx < n_in; idx += blockDim.x) row[idx] = __ldg(src + idx);
+    __syncthreads();
+
+    const int n_out = nt * C;
+    for (int i = 0; i < M_out; ++i) {
+        T *dst = vp + (((size_t)(j * M_out + i) * S + s) * Tn + t0) * C;
+        const int off = (kc + i) * C;
+        for (int idx = threadIdx.x; idx < n_out; idx += blockDim.x) {
+            const int t = idx / C;
+            const int c = idx - t * C;
+            dst[idx] = row[t * M_in * C + off + c];
+        }
+    }
+}
+
+template <typename T, int CT>
+__global__ void __launch_bounds__(256)
+viewpoints_inverse_kernel(const T *__restrict__ vp, T *__restrict__ aligned, int M, int S, int Tn, int Crt, int tile_t) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *row = reinterpret_cast<T *>(smem_raw);
+    const int C = CT ? CT : Crt;
+    const int s = blockIdx.x, j = blockIdx.y;
+    const int t0 = blockIdx.z * tile_t;
+    const int nt = min(tile_t, Tn - t0);
+    if (nt <= 0) return;
+
+    const int n_view = nt * C;
+    for (int i = 0; i < M; ++i) {
+        const T *src = vp + (((size_t)(j * M + i) * S + s) * Tn + t0) * C;
+        for (int idx = threadIdx.x; idx < n_view; idx += blockDim.x) {
+            const int t = idx / C;
+            const int c = idx - t * C;
+            row[(t * M + i) * C + c] = __ldg(src + idx);
+        }
+    }
+    __syncthreads();
+    T *dst = aligned + (size_t)(s * M + j) * ((size_t)Tn * M * C) + (size_t)t0 * M * C;
+    const int n_out = nt * M * C;
+    for (int idx = threadIdx.x; idx < n_out; idx += blockDim.x) dst[idx] = row[idx];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+crop_kernel(const T *__restrict__ aligned, T *__restrict__ cropped, int cols_elems_in, int M_in, int M_out, int kc,
+            int LX, int C) {
+    // one CTA per output row
+    const int orow = blockIdx.x;
+    const int ly = orow / M_out, v = orow - ly * M_out;
+    const T *src = aligned + (size_t)(ly * M_in + kc + v) * cols_elems_in;
+    T *dst = cropped + (size_t)orow * ((size_t)LX * M_out * C);
+    const int n = LX * M_out * C;
+    const int mc = M_out * C;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int lx = idx / mc;
+        const int rem = idx - lx * mc;   // u*C + c
+        dst[idx] = __ldg(src + (lx * M_in + kc) * C + rem);
+    }
+}
+
+static inline int vp_tile(int Tn, int M, int C, int esz, int *tile_t, int *ntile, size_t *smem) {
+    const size_t budget = 48 * 1024;
+    const size_t row_bytes = (size_t)Tn * M * C * esz;
+    int nt = (int)((row_bytes + budget - 1) / budget);
+    if (nt < 1) nt = 1;
+    int tt = (Tn + nt - 1) / nt;
+    if ((size_t)tt * M * C * esz > budget) return 1;   // a single micro-image row exceeds the budget
+    *tile_t = tt;
+    *ntile = (Tn + tt - 1) / tt;
+    *smem = (size_t)tt * M * C * esz;
+    return 0;
+}
+
+template <typename T>
+static int launch_viewpoints(const void *aligned, void *vp, int rows, int cols, int C, int M_in, int M_out,
+                             cudaStream_t st) {
+    const int S = rows / M_in, Tn = cols / M_in, kc = (M_in - M_out) / 2;
+    int tile_t, ntile;
+    size_t smem;
+    if (vp_tile(Tn, M_in, C, sizeof(T), &tile_t, &ntile, &smem))
+        return fail(PCB_ERR_UNSUPPORTED, "%s: micro image row too large for shared memory", "pcb_viewpoints");
+    dim3 grid(S, M_out, ntile), block(256);
+    if (C == 3)
+        viewpoints_kernel<T, 3><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t);
+    else if (C == 1)
+        viewpoints_kernel<T, 1><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t);
+    else
+        viewpoints_kernel<T, 0><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+template <typename T>
+static int launch_viewpoints_inverse(const void *vp, void *aligned, int M, int S, int Tn, int C, cudaStream_t st) {
+    int tile_t, ntile;
+    size_t smem;
+    if (vp_tile(Tn, M, C, sizeof(T), &tile_t, &ntile, &smem))
+        return fail(PCB_ERR_UNSUPPORTED, "%s: micro image row too large for shared memory", "pcb_viewpoints_inverse");
+    dim3 grid(S, M, ntile), block(256);
+    if (C == 3)
+        viewpoints_inverse_kernel<T, 3><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t);
+    else if (C == 1)
+        viewpoints_inverse_kernel<T, 1><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t);
+    else
+        viewpoints_inverse_kernel<T, 0><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+template <typename T>
+static int launch_crop(const void *aligned, void *cropped, int rows, int cols, int C, int M_in, int M_out,
+                       cudaStream_t st) {
+    const int LY = rows / M_in, LX = cols / M_in, kc = (M_in - M_out) / 2;
+    crop_kernel<T><<<LY * M_out, 256, 0, st>>>((const T *)aligned, (T *)cropped, cols * C, M_in, M_out, kc, LX, C);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+}  // namespace pcb

@@ -1,0 +1,4 @@
+from .lfp_microlenses import LfpMicroLenses, build_tables  # noqa: F401
+from .lfp_resampler import LfpResampler  # noqa: F401
+from .lfp_rotator import LfpRotator  # noqa: F401
+from .top_level import LfpAligner  # noqa: F401

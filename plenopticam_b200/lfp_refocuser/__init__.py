@@ -1,0 +1,2 @@
+from .lfp_shiftandsum import LfpShiftAndSum  # noqa: F401
+from .top_level import LfpRefocuser  # noqa: F401

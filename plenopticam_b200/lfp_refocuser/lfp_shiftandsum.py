@@ -1,0 +1,79 @@
+"""Drop-in `LfpShiftAndSum` (lfp_refocuser/lfp_shiftandsum.py:34-139,306-322): the whole refocus stack in one
+kernel launch (all slices, all views, aperture mask and the /M scaling fused) instead of
+N * M*M `np.pad` + `np.add` passes.
+
+`refo_stack` is float64 (N,S,T,C) like the reference's; the device result is float32 and is exposed as
+`refo_stack_device` for pipelines that stay in HBM.
+"""
+import numpy as np
+
+from .. import ops
+from ..lfp_extractor.lfp_viewpoints import LfpViewpoints
+
+
+class LfpShiftAndSum(LfpViewpoints):
+
+    def __init__(self, lfp_img_align=None, *args, **kwargs):
+        super(LfpShiftAndSum, self).__init__(*args, **kwargs)
+        self.lfp_img_align = lfp_img_align
+        self.validate_range()
+        self._refo_stack = list()
+        self._dev_stack = None
+
+    def validate_range(self):
+        """lfp_shiftandsum.py:306-315 (may bump cfg.params['ran_refo'][1])."""
+        ran = self.cfg.params[self.cfg.ran_refo]
+        if len(ran) != 2:
+            raise ValueError("Refocusing range list is supposed to contain only two entries")
+        if ran[0] >= ran[1]:
+            self.cfg.params[self.cfg.ran_refo][1] = ran[0] + 1
+            self.sta.status_msg('Refocusing range is not positive')
+
+    def main(self):
+        if self.sta.interrupt:
+            return False
+        prnt = self.cfg.params[self.cfg.opt_prnt]
+        self.sta.status_msg('Compute refocused image stack', prnt)
+        self.sta.progress(None, prnt)
+        if self.vp_img_arr is not None:
+            if self.refo_from_vp() is False:
+                return False
+        elif self.lfp_img_align is not None:
+            # refo_from_scratch* (lfp_shiftandsum.py:141-304) are `pragma: no cover` alternates never reached
+            # from LfpRefocuser
+            raise NotImplementedError('refocusing from the aligned image is not part of the B200 hot path; '
+                                      'pass vp_img_arr')
+        self._refo_stack = np.asarray(self._refo_stack)
+        return True
+
+    def refo_from_vp(self):
+        prnt = self.cfg.params[self.cfg.opt_prnt]
+        self.sta.progress(0, prnt)
+        M = int(self.cfg.params[self.cfg.ptc_leng])
+        ran = self.cfg.params[self.cfg.ran_refo]
+        vp = self._vp_device()
+        if vp.shape[0] != M or vp.shape[1] != M:
+            raise ValueError('vp_img_arr angular size %s does not match ptc_leng=%d' % (tuple(vp.shape[:2]), M))
+        if vp.shape[-1] != 3:
+            # the reference accumulator is hard-wired to 3 channels (lfp_shiftandsum.py:97)
+            raise ValueError('operands could not be broadcast together: refocusing needs 3 colour channels')
+        if self.cfg.params[self.cfg.opt_refi]:
+            from .refinement import refocus_refi
+            a_list = range(M * ran[0], M * ran[1])
+            self._dev_stack = refocus_refi(vp, a_list, self.circular_view_aperture_mask())
+        else:
+            a_list = range(*ran)
+            self._dev_stack = ops.refocus_int(vp, a_list, self.circular_view_aperture_mask())
+        if self.sta.interrupt:
+            return False
+        self._refo_stack = ops.to_host(self._dev_stack).astype(np.float64)
+        self.sta.progress(100, prnt)
+        return True
+
+    @property
+    def refo_stack(self):
+        return self._refo_stack.copy()
+
+    @property
+    def refo_stack_device(self):
+        return self._dev_stack

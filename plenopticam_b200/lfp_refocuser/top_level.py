@@ -1,0 +1,35 @@
+"""`LfpRefocuser` restricted to the hot path (lfp_refocuser/top_level.py:32-79): shift-and-sum stack, then
+percentile contrast alignment against slice 0 and the sRGB transfer, all on the device.  PNG/GIF export and
+the Scheimpflug composite (top_level.py:72-87) are out of scope."""
+from .. import ops
+from ..lfp_extractor.lfp_viewpoints import LfpViewpoints
+from .lfp_shiftandsum import LfpShiftAndSum
+
+
+class LfpRefocuser(LfpViewpoints):
+
+    def __init__(self, vp_img_arr=None, *args, **kwargs):
+        super(LfpRefocuser, self).__init__(*args, **kwargs)
+        self.vp_img_arr = vp_img_arr
+        self.refo_stack = []
+        self.refo_stack_device = None
+
+    def main(self):
+        if self.sta.interrupt:
+            return False
+        if self.cfg.params[self.cfg.opt_refo]:
+            self.shift_and_sum()
+        if self.cfg.params[self.cfg.opt_pflu]:
+            raise NotImplementedError('Scheimpflug rendering (lfp_refocuser/lfp_scheimpflug.py) is outside the '
+                                      'B200 hot path')
+        return True
+
+    def shift_and_sum(self):
+        obj = LfpShiftAndSum(vp_img_arr=self.vp_img_arr, cfg=self.cfg, sta=self.sta)
+        ok = obj.main()
+        dev = obj.refo_stack_device
+        del obj
+        if ok and dev is not None and not self.sta.interrupt:
+            self.refo_stack_device = ops.refocuser_postprocess(dev)
+            self.refo_stack = ops.to_host(self.refo_stack_device)      # float32 sRGB, like the reference
+        return True

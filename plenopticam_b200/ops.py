@@ -1,0 +1,293 @@
+"""Device-level operators: torch tensors in HBM in, torch tensors out, all work done by libpcb200.so.
+
+torch is used for device memory, streams and pinned staging only.  Every function enqueues on the current
+torch stream and does not synchronise.  There is no CPU fallback: without a CUDA device these raise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_TORCH2PCB = {torch.uint16: nat.PCB_U16, torch.float32: nat.PCB_F32, torch.uint8: nat.PCB_U8}
+_NP2TORCH = {np.dtype("uint16"): torch.uint16, np.dtype("float32"): torch.float32, np.dtype("uint8"): torch.uint8}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("plenopticam_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _pcb_dtype(t):
+    try:
+        return _TORCH2PCB[t.dtype]
+    except KeyError:
+        raise TypeError("unsupported device dtype %s (uint8, uint16, float32 are)" % t.dtype)
+
+
+def _chk_dev(*tensors):
+    for t in tensors:
+        if not (t.is_cuda and t.is_contiguous()):
+            raise ValueError("expected contiguous CUDA tensors")
+
+
+# ------------------------------------------------------------------------------------------------------
+# host <-> device staging
+# ------------------------------------------------------------------------------------------------------
+def device_dtype_for(arr):
+    """Narrowest dtype the kernels read that holds `arr` exactly enough: uint8/uint16 stay, every float and
+    wider integer goes to float32 unless it is integer-valued within uint16 (post-demosaic RGB is uint16
+    stored as float64: lfp_aligner/top_level.py:39, cfa_processor.py:73)."""
+    dt = np.asarray(arr).dtype
+    if dt in (np.dtype("uint8"), np.dtype("uint16")):
+        return dt
+    return np.dtype("float32")
+
+
+def to_device(arr, dtype=None, exact_u16=False):
+    """numpy -> contiguous CUDA tensor through a pinned staging buffer."""
+    dev = require_cuda()
+    arr = np.asarray(arr)
+    if dtype is None:
+        dtype = device_dtype_for(arr)
+        if exact_u16 and dtype == np.dtype("float32") and arr.size:
+            lo, hi = arr.min(), arr.max()
+            if lo >= 0 and hi <= 65535 and np.array_equal(arr, np.rint(arr)):
+                dtype = np.dtype("uint16")
+    host = np.ascontiguousarray(arr, dtype=dtype)
+    if host.dtype == np.dtype("uint16"):
+        pinned = torch.empty(host.shape, dtype=torch.uint16, pin_memory=True)
+        pinned.view(torch.int16).numpy()[...] = host.view(np.int16)
+    else:
+        pinned = torch.empty(host.shape, dtype=_NP2TORCH[host.dtype], pin_memory=True)
+        pinned.numpy()[...] = host
+    return pinned.to(dev, non_blocking=True)
+
+
+def to_host(t):
+    """CUDA tensor -> numpy (synchronises the current stream)."""
+    if t.dtype == torch.uint16:
+        return t.view(torch.int16).cpu().numpy().view(np.uint16)
+    return t.cpu().numpy()
+
+
+def struct_to_device(arr):
+    """Upload a numpy structured array (pcb_lens_t / pcb_hexcol_t tables) as raw bytes."""
+    dev = require_cuda()
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    return torch.from_numpy(raw.copy()).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------------
+# min / max
+# ------------------------------------------------------------------------------------------------------
+def new_minmax():
+    dev = require_cuda()
+    mm = torch.empty(2, dtype=torch.int32, device=dev)
+    nat.check(nat.lib().pcb_minmax_reset(_ptr(mm), _stream()))
+    return mm
+
+
+def minmax_values(mm):
+    """(min, max) as Python floats (synchronises)."""
+    keys = mm.cpu().numpy().view(np.uint32)
+    L = nat.lib()
+    return float(L.pcb_key_to_float(int(keys[0]))), float(L.pcb_key_to_float(int(keys[1])))
+
+
+def minmax_f32(data, mm=None):
+    _chk_dev(data)
+    mm = new_minmax() if mm is None else mm
+    nat.check(nat.lib().pcb_minmax_f32(_ptr(data), data.numel(), _ptr(mm), _stream()))
+    return mm
+
+
+# ------------------------------------------------------------------------------------------------------
+# (a) resampling
+# ------------------------------------------------------------------------------------------------------
+class LensTables:
+    """Device copies of the host-prepared tables (see microlens.build_tables)."""
+
+    def __init__(self, tables):
+        self.LY, self.LX, self.M = tables["LY"], tables["LX"], tables["M"]
+        self.pattern = nat.PCB_HEX if tables["pat_type"] == "hex" else nat.PCB_REC
+        self.Xs = tables["Xs"]
+        self.hex_odd = int(bool(tables["hex_odd"]))
+        self.lens = struct_to_device(tables["lens"])
+        self.hexcol = struct_to_device(tables["hexcol"]) if tables["hexcol"] is not None else None
+
+    def _args(self, raw, flip):
+        H, W, Cn = raw.shape
+        hexp = _ptr(self.hexcol) if self.hexcol is not None else C.c_void_p(0)
+        return [_ptr(raw), _pcb_dtype(raw), H, W, Cn, _ptr(self.lens), self.LY, self.LX, self.M,
+                self.pattern, hexp, self.Xs, self.hex_odd, int(bool(flip))]
+
+    def out_shape(self, raw):
+        return (self.LY * self.M, self.Xs * self.M, raw.shape[2])
+
+
+def resample_f32(raw, tabs, flip=False, want_minmax=False):
+    """float32 aligned image (LY*M, Xs*M, C) [+ running min/max keys]."""
+    _chk_dev(raw)
+    out = torch.empty(tabs.out_shape(raw), dtype=torch.float32, device=raw.device)
+    mm = new_minmax() if want_minmax else None
+    args = tabs._args(raw, flip) + [_ptr(out), _ptr(mm) if mm is not None else C.c_void_p(0), _stream()]
+    nat.check(nat.lib().pcb_resample_f32(*args))
+    return (out, mm) if want_minmax else out
+
+
+def resample_u16(raw, tabs, flip=False, out=None, mm=None):
+    """LfpResampler's product: the aligned image min-max normalised to uint16.  Two launches, no host sync:
+    a min/max pass and a recompute-and-quantise pass."""
+    _chk_dev(raw)
+    if out is None:
+        out = torch.empty(tabs.out_shape(raw), dtype=torch.uint16, device=raw.device)
+    if mm is None:
+        mm = torch.empty(2, dtype=torch.int32, device=raw.device)
+    L = nat.lib()
+    nat.check(L.pcb_minmax_reset(_ptr(mm), _stream()))
+    nat.check(L.pcb_resample_minmax(*(tabs._args(raw, flip) + [_ptr(mm), _stream()])))
+    nat.check(L.pcb_resample_u16(*(tabs._args(raw, flip) + [_ptr(mm), _ptr(out), _stream()])))
+    return out, mm
+
+
+def quantize_u16(data, mm):
+    _chk_dev(data)
+    out = torch.empty(data.shape, dtype=torch.uint16, device=data.device)
+    nat.check(nat.lib().pcb_quantize_u16(_ptr(data), data.numel(), _ptr(mm), _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# (a') rotation
+# ------------------------------------------------------------------------------------------------------
+def rotate(img, rad):
+    """scipy.ndimage.rotate(img, deg, reshape=False, order=3) -> float32 (H,W,C)."""
+    _chk_dev(img)
+    H, W, Cn = img.shape
+    tmp = torch.empty((H, W, Cn), dtype=torch.float32, device=img.device)
+    coef = torch.empty_like(tmp)
+    L = nat.lib()
+    nat.check(L.pcb_spline_prefilter(_ptr(img), _pcb_dtype(img), H, W, Cn, _ptr(tmp), _ptr(coef), _stream()))
+    nat.check(L.pcb_rotate_sample(_ptr(coef), H, W, Cn, float(rad), _ptr(tmp), _stream()))
+    return tmp
+
+
+# ------------------------------------------------------------------------------------------------------
+# (b) viewpoints
+# ------------------------------------------------------------------------------------------------------
+def viewpoints(aligned, M_in, M_out=None, out=None):
+    _chk_dev(aligned)
+    M_out = M_in if M_out is None else M_out
+    rows, cols, Cn = aligned.shape
+    S, T = rows // M_in, cols // M_in
+    if out is None:
+        out = torch.empty((M_out, M_out, S, T, Cn), dtype=aligned.dtype, device=aligned.device)
+    nat.check(nat.lib().pcb_viewpoints(_ptr(aligned), _pcb_dtype(aligned), rows, cols, Cn, M_in, M_out,
+                                       _ptr(out), _stream()))
+    return out
+
+
+def viewpoints_inverse(vp):
+    _chk_dev(vp)
+    M, M2, S, T, Cn = vp.shape
+    if M != M2:
+        raise ValueError("square angular resolution expected")
+    out = torch.empty((S * M, T * M, Cn), dtype=vp.dtype, device=vp.device)
+    nat.check(nat.lib().pcb_viewpoints_inverse(_ptr(vp), _pcb_dtype(vp), M, S, T, Cn, _ptr(out), _stream()))
+    return out
+
+
+def crop_micro_images(aligned, M_in, M_out):
+    _chk_dev(aligned)
+    rows, cols, Cn = aligned.shape
+    LY, LX = rows // M_in, cols // M_in
+    out = torch.empty((LY * M_out, LX * M_out, Cn), dtype=aligned.dtype, device=aligned.device)
+    nat.check(nat.lib().pcb_crop_micro_images(_ptr(aligned), _pcb_dtype(aligned), rows, cols, Cn, M_in, M_out,
+                                              _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# (c) refocus
+# ------------------------------------------------------------------------------------------------------
+def aperture_mask(M):
+    """View (j,i) is zeroed iff int(np.round(sqrt((i-c)^2+(j-c)^2))) > c
+    (lfp_extractor/lfp_viewpoints.py:229-250; np.round is round-half-even)."""
+    c = M // 2
+    jj, ii = np.meshgrid(np.arange(M) - c, np.arange(M) - c, indexing="ij")
+    return (np.rint(np.sqrt(ii.astype(np.float64) ** 2 + jj.astype(np.float64) ** 2)).astype(np.int64) > c)
+
+
+def refocus_int(vp, a_list, view_zeroed=None, out=None):
+    """(N,S,T,C) float32 stack of integer shift-and-sum slices (divided by M)."""
+    _chk_dev(vp)
+    M, M2, S, T, Cn = vp.shape
+    if M != M2:
+        raise ValueError("square angular resolution expected")
+    a_host = np.ascontiguousarray(np.asarray(list(a_list), dtype=np.int32))
+    N = int(a_host.size)
+    if view_zeroed is None:
+        view_zeroed = aperture_mask(M)
+    a_dev = torch.from_numpy(a_host).to(vp.device)
+    z_dev = torch.from_numpy(np.ascontiguousarray(view_zeroed, dtype=np.uint8).reshape(-1)).to(vp.device)
+    if out is None:
+        out = torch.empty((N, S, T, Cn), dtype=torch.float32, device=vp.device)
+    nat.check(nat.lib().pcb_refocus_int(_ptr(vp), _pcb_dtype(vp), M, S, T, Cn, _ptr(a_dev), N, _ptr(z_dev),
+                                        _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# post-processing
+# ------------------------------------------------------------------------------------------------------
+def percentile(data, q, luma=False):
+    """np.percentile(data, q) (or of the BT.709 luma of (...,3) pixels) -> float64 tensor of len(q)."""
+    _chk_dev(data)
+    if data.dtype != torch.float32:
+        raise TypeError("float32 expected")
+    L = nat.lib()
+    q = [float(v) for v in np.atleast_1d(q)]
+    n = data.numel() // 3 if luma else data.numel()
+    if luma and data.shape[-1] != 3:
+        raise ValueError("luma percentiles need 3 channels")
+    scratch = torch.empty(int(L.pcb_percentile_scratch_bytes()), dtype=torch.uint8, device=data.device)
+    res = torch.empty(len(q), dtype=torch.float64, device=data.device)
+    qarr = (C.c_double * len(q))(*q)
+    nat.check(L.pcb_percentile_f32(_ptr(data), n, int(bool(luma)), qarr, len(q), _ptr(res), _ptr(scratch), _stream()))
+    return res
+
+
+def contrast_srgb(stack, lohi, out=None):
+    """clip((x-lo)/(hi-lo)) then sRGB; `lohi` is a float64 CUDA tensor [lo, hi]."""
+    _chk_dev(stack, lohi)
+    if out is None:
+        out = torch.empty_like(stack)
+    nat.check(nat.lib().pcb_contrast_srgb(_ptr(stack), stack.numel(), _ptr(lohi), _ptr(out), _stream()))
+    return out
+
+
+def refocuser_postprocess(stack):
+    """LfpRefocuser.shift_and_sum's colour management (lfp_refocuser/top_level.py:68-70), on the device:
+    lo = P0.005(luma(stack[0])), hi = P99.9(stack[0]); falsy lo/hi fall back to the stack's min/max
+    (misc/normalizer.py:40-41)."""
+    ref = stack[0]
+    lo = percentile(ref, [0.005], luma=True)
+    hi = percentile(ref, [99.9], luma=False)
+    lohi = torch.cat([lo, hi])
+    vals = lohi.cpu().numpy()
+    if not vals[0] or not vals[1]:
+        mn, mx = minmax_values(minmax_f32(stack))
+        vals = np.array([vals[0] if vals[0] else mn, vals[1] if vals[1] else mx], dtype=np.float64)
+        lohi = torch.from_numpy(vals).to(stack.device)
+    return contrast_srgb(stack, lohi)

@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C-ABI in libpcb200.so) against the numpy oracle and against the
+golden vectors produced by the unmodified reference.  All tests need a GPU.
+
+Tolerances (BASELINE.json north_star):
+  * bit-exact : viewpoint gather / inverse / crop, centroid indexing, integer shift-and-sum of uint16 data
+                (compared after the float32 cast the reference's Normalizer applies next)
+  * <= 1e-4 max-abs on [0,1]-normalised data for the interpolated paths; the tests use tighter figures
+    where float32 allows it (stated per test).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names, make_cfg
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+
+def _norm01(x, ref):
+    lo, hi = float(ref.min()), float(ref.max())
+    return (np.asarray(x, dtype=np.float64) - lo) / (hi - lo if hi > lo else 1.0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# (a) resampling
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("resample_"))
+def test_resample_f32_vs_reference_golden(cuda, name):
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_aligner import build_tables
+    g = golden(name)
+    M = int(g["M_used"])
+    tabs = ops.LensTables(build_tables(g["centroids"], g["raw"].shape, M, str(g["pat_type"])))
+    raw = ops.to_device(g["raw"])
+    out, mm = ops.resample_f32(raw, tabs, flip=bool(g["flip"]), want_minmax=True)
+    got = ops.to_host(out)
+    ref = g["aligned_f64"]
+    assert got.shape == ref.shape
+    err = np.abs(_norm01(got, ref) - _norm01(ref, ref)).max()
+    assert err <= 2e-6, err                                   # float32 bilinear+lerp; bar is 1e-4
+    mn, mx = ops.minmax_values(mm)
+    assert mn == got.min() and mx == got.max()                # fused reduction is exact
+
+
+@pytest.mark.parametrize("name", golden_names("resample_"))
+def test_resampler_class_u16_vs_reference_golden(cuda, name, tmp_path):
+    from plenopticam_b200.lfp_aligner import LfpResampler
+    g = golden(name)
+    cfg, sta = make_cfg(g["centroids"], str(g["pat_type"]), int(g["M"]), tmpdir=tmp_path)
+    obj = LfpResampler(lfp_img=g["raw"], cfg=cfg, sta=sta, flip=bool(g["flip"]))
+    assert obj.main() is True
+    got = obj.lfp_img_align
+    assert got.dtype == np.uint16 and got.shape == g["aligned_u16"].shape
+    assert int(cfg.params[cfg.ptc_leng]) == int(g["M_used"])
+    diff = np.abs(got.astype(np.int64) - g["aligned_u16"].astype(np.int64))
+    assert diff.max() <= 1, diff.max()                        # 1 LSB = 1.5e-5 of full scale (bar 1e-4)
+    assert (diff != 0).mean() < 0.02
+    # checkpoint side effect of the reference (lfp_resampler.py:64-68)
+    import os, pickle
+    with open(os.path.join(cfg.exp_path, 'lfp_img_align.pkl'), 'rb') as f:
+        assert np.array_equal(pickle.load(f), got)
+
+
+def test_resample_even_M_gives_zero_image(cuda):
+    """Even M: the reference's window is (M+3)^2 != (M+2)^2 -> every patch is zero (lfp_local_resampler.py:50)."""
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_aligner import build_tables
+    cent = onp.synth_centroids(5, 6, 9.0, 'rec', jitter=0.1, seed=3)
+    raw = onp.synth_raw(60, 70, 3, seed=3)
+    tabs = ops.LensTables(build_tables(cent, raw.shape, 6, 'rec'))
+    out, _ = ops.resample_u16(ops.to_device(raw), tabs)
+    assert not ops.to_host(out).any()
+    assert not onp.resample(raw, cent, 6, 'rec').any()
+
+
+@pytest.mark.parametrize("pat,dtype", [("hex", np.uint16), ("rec", np.float32), ("hex", np.uint8)])
+def test_resample_medium_vs_oracle(cuda, pat, dtype):
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_aligner import build_tables
+    LY, LX, pitch, M = 40, 53, 14.285, 15
+    cent = onp.synth_centroids(LY, LX, pitch, pat, hex_odd=True, jitter=0.15, rot_deg=0.05, origin=(9.5, 9.5), seed=5)
+    H, W = int(cent[:, 0].max() + 10), int(cent[:, 1].max() + 10)
+    raw = onp.synth_raw(H, W, 3, seed=5, dtype=np.uint16 if dtype != np.float32 else np.float32)
+    if dtype == np.uint8:
+        raw = (raw >> 8).astype(np.uint8)
+    ref = onp.resample(raw, cent, M, pat)
+    tabs = ops.LensTables(build_tables(cent, raw.shape, M, pat))
+    dev = ops.to_device(raw)
+    assert str(dev.dtype).endswith(np.dtype(dtype).name)
+    got = ops.to_host(ops.resample_f32(dev, tabs))
+    assert np.abs(_norm01(got, ref) - _norm01(ref, ref)).max() <= 2e-6
+    q, _ = ops.resample_u16(dev, tabs)
+    d = np.abs(ops.to_host(q).astype(np.int64) - onp.uint16_norm(ref).astype(np.int64))
+    assert d.max() <= 1
+
+
+# ------------------------------------------------------------------------------------------------------
+# (a') rotation
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rotator_hex", "rotator_rec_f32"])
+def test_rotator_vs_reference_golden(cuda, name):
+    from plenopticam_b200.lfp_aligner import LfpRotator
+    g = golden(name)
+    cfg, sta = make_cfg(g["centroids"], 'hex', 7)
+    obj = LfpRotator(g["raw"], g["centroids"].tolist(), cfg=cfg, sta=sta)
+    assert obj.main() is True
+    assert abs(obj._rad - float(g["rad"])) < 1e-12
+    assert np.abs(np.asarray(obj.centroids) - g["rot_centroids"]).max() < 1e-9
+    got, ref = obj.lfp_img, g["rot_img"]
+    assert got.shape == ref.shape and got.dtype == np.float64
+    scale = float(np.abs(g["raw"]).max())
+    assert np.abs(got - ref).max() / scale <= 5e-6            # float32 spline, FIR-truncated prefilter; bar 1e-4
+
+
+def test_rotate_large_angle_and_zero(cuda):
+    from plenopticam_b200 import ops
+    raw = onp.synth_raw(97, 131, 3, seed=9, dtype=np.float32)
+    for rad in (0.3, -1.1):
+        ref = onp.rotate_img(raw.astype(np.float64), rad)
+        got = ops.to_host(ops.rotate(ops.to_device(raw), rad))
+        assert np.abs(got - ref).max() <= 5e-6
+    from plenopticam_b200.lfp_aligner import LfpRotator
+    cfg, sta = make_cfg()
+    obj = LfpRotator(raw, [[0, 0, 0, 0]], rad=0.0, cfg=cfg, sta=sta)
+    assert obj.main() is True and np.array_equal(obj.lfp_img, raw)        # deg == 0 -> untouched (:138)
+
+
+# ------------------------------------------------------------------------------------------------------
+# (b) viewpoints
+# ------------------------------------------------------------------------------------------------------
+def test_rearranger_vs_reference_golden_bit_exact(cuda):
+    from plenopticam_b200.lfp_extractor import LfpRearranger
+    g = golden("rearranger_u16")
+    cfg, sta = make_cfg(M=int(g["M"]))
+    obj = LfpRearranger(g["aligned"], cfg=cfg, sta=sta)
+    assert obj.main() is None
+    assert obj.vp_img_arr.dtype == np.uint16 and np.array_equal(obj.vp_img_arr, g["vp"])
+    back = LfpRearranger(vp_img_arr=g["vp"], cfg=cfg, sta=sta)
+    assert back.decompose_viewpoints() is True
+    assert np.array_equal(back.lfp_img_align, g["back"])
+
+
+def test_cropper_vs_reference_golden_bit_exact(cuda):
+    from plenopticam_b200.lfp_extractor import LfpCropper
+    g = golden("cropper_u16")
+    cent = onp.synth_centroids(6, 8, 9.3, 'rec', jitter=0.0, seed=22)
+    cfg, sta = make_cfg(cent, 'rec', int(g["M_out"]))
+    obj = LfpCropper(lfp_img_align=g["aligned"], cfg=cfg, sta=sta)
+    obj.main()
+    assert np.array_equal(obj.lfp_img_align, g["cropped"])
+    assert int(cfg.params[cfg.ptc_leng]) == int(g["M_used"])
+
+
+@pytest.mark.parametrize("dtype,C,M,S,T", [(np.uint16, 3, 15, 21, 700), (np.float32, 3, 9, 17, 33),
+                                            (np.uint8, 1, 5, 8, 9), (np.uint16, 4, 7, 6, 11)])
+def test_viewpoints_roundtrip_and_oracle(cuda, dtype, C, M, S, T):
+    from plenopticam_b200 import ops
+    rng = np.random.default_rng(1)
+    aligned = (rng.random((S * M + 3, T * M + 2, C)) * 250).astype(dtype)      # ragged border is ignored
+    ref = onp.compose_viewpoints(aligned, M)
+    dev = ops.to_device(aligned)
+    vp = ops.viewpoints(dev, M)
+    assert np.array_equal(ops.to_host(vp), ref)
+    back = ops.to_host(ops.viewpoints_inverse(vp))
+    assert np.array_equal(back, aligned[:S * M, :T * M])
+    if M >= 7:
+        fused = ops.to_host(ops.viewpoints(dev, M, M - 4))
+        two_step = onp.compose_viewpoints(onp.crop_micro_images(aligned[:S * M, :T * M], M, M - 4), M - 4)
+        assert np.array_equal(fused, two_step)
+
+
+# ------------------------------------------------------------------------------------------------------
+# (c) refocus
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["refocus_int_u16", "refocus_int_f32"])
+def test_shiftandsum_vs_reference_golden(cuda, name):
+    from plenopticam_b200.lfp_refocuser import LfpShiftAndSum
+    g = golden(name)
+    cfg, sta = make_cfg(M=int(g["M"]), ran_refo=[int(v) for v in g["ran_refo"]])
+    vp_in = g["vp"].copy()
+    obj = LfpShiftAndSum(vp_img_arr=vp_in, cfg=cfg, sta=sta)
+    assert obj.main() is True
+    got = obj.refo_stack
+    assert got.dtype == np.float64 and got.shape == g["stack"].shape
+    assert np.array_equal(vp_in, g["vp"])                               # caller's array untouched
+    if name.endswith("u16"):
+        # exact integer accumulation: equals the reference after its next step (float32 cast in Normalizer)
+        assert np.array_equal(got.astype(np.float32), g["stack"].astype(np.float32))
+    else:
+        assert np.abs(got - g["stack"]).max() <= 2e-6 * np.abs(g["stack"]).max()
+
+
+def test_refocus_int_large_shifts_and_all_views(cuda):
+    from plenopticam_b200 import ops
+    rng = np.random.default_rng(3)
+    M, S, T = 9, 23, 31
+    vp = rng.integers(0, 65536, size=(M, M, S, T, 3), dtype=np.uint16)
+    a_list = [-40, -7, -1, 0, 1, 5, 33]
+    ref = np.asarray([onp.refocus_int_slice(onp._apply_aperture(vp, M) / M, a, M) for a in a_list])
+    got = ops.to_host(ops.refocus_int(ops.to_device(vp), a_list))
+    assert np.array_equal(got, ref.astype(np.float32))
+    # no aperture: every view contributes
+    none = np.zeros((M, M), dtype=bool)
+    ref_all = np.zeros((S, T, 3))
+    c = M // 2
+    for j in range(M):
+        for i in range(M):
+            yi = np.clip(np.arange(S) + 2 * (c - j), 0, S - 1)
+            xi = np.clip(np.arange(T) + 2 * (c - i), 0, T - 1)
+            ref_all += vp[j, i][yi][:, xi]
+    got_all = ops.to_host(ops.refocus_int(ops.to_device(vp), [2], view_zeroed=none))[0]
+    assert np.array_equal(got_all, (ref_all / M).astype(np.float32))
+
+
+def test_refocus_wide_rows_use_several_column_chunks(cuda):
+    from plenopticam_b200 import ops
+    rng = np.random.default_rng(4)
+    M, S, T = 5, 6, 900                                                 # T*C = 2700 > 2048 elements per CTA
+    vp = rng.integers(0, 65536, size=(M, M, S, T, 3), dtype=np.uint16)
+    ref = onp.refocus_int(vp, (-2, 3), M)
+    got = ops.to_host(ops.refocus_int(ops.to_device(vp), range(-2, 3)))
+    assert np.array_equal(got, ref.astype(np.float32))
+
+
+def test_percentile_matches_numpy(cuda):
+    from plenopticam_b200 import ops
+    import torch
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((97, 113, 3)) * 1000).astype(np.float32)
+    x[3, 4, 1] = 0.0
+    d = ops.to_device(x)
+    for q in ([0.005], [99.9], [0.0, 50.0, 100.0], [37.123]):
+        got = ops.percentile(d, q).cpu().numpy()
+        assert np.array_equal(got, np.percentile(x.astype(np.float64), q)), q
+    lum = ops.percentile(d, [0.005, 50.0], luma=True).cpu().numpy()
+    ref = np.percentile(onp.rgb2gry(x.astype(np.float64)), [0.005, 50.0])
+    assert np.abs(lum - ref).max() <= 1e-6 * np.abs(ref).max() + 1e-4
+    assert torch.cuda.is_available()
+
+
+def test_refocuser_vs_reference_golden(cuda):
+    from plenopticam_b200.lfp_refocuser import LfpRefocuser
+    g = golden("refocuser_post_u16")
+    cfg, sta = make_cfg(M=int(g["M"]), ran_refo=[int(v) for v in g["ran_refo"]])
+    cfg.params[cfg.opt_refo] = True
+    cfg.params[cfg.opt_pflu] = False
+    obj = LfpRefocuser(vp_img_arr=g["vp"], cfg=cfg, sta=sta)
+    assert obj.main() is True
+    got = obj.refo_stack
+    assert got.dtype == np.float32 and got.shape == g["stack"].shape
+    assert np.abs(got.astype(np.float64) - g["stack"]).max() <= 2e-6     # [0,1] sRGB values; bar 1e-4
+
+
+def test_interrupt_returns_false(cuda):
+    from plenopticam_b200.lfp_aligner import LfpResampler
+    from plenopticam_b200.lfp_refocuser import LfpShiftAndSum
+    g = golden("resample_rec_u16")
+    cfg, sta = make_cfg(g["centroids"], 'rec', 7)
+    sta.interrupt = True
+    assert LfpResampler(lfp_img=g["raw"], cfg=cfg, sta=sta).main() is False
+    g = golden("refocus_int_u16")
+    assert LfpShiftAndSum(vp_img_arr=g["vp"], cfg=cfg, sta=sta).main() is False
