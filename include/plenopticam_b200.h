@@ -119,10 +119,21 @@ int pcb_crop_micro_images(const void *aligned, int dtype, int rows, int cols, in
  *     (lfp_extractor/lfp_viewpoints.py:229-250) and the /M scaling (:89):
  *       out[n,y,x,c] = (1/M) * sum_{(j,i): !view_zeroed[j*M+i]} vp[j,i,clamp(y+a_n(c0-j)),clamp(x+a_n(c0-i)),c]
  *   uint16 input is accumulated exactly in integers; out is float32 (N,S,T,C).  M must be odd.
+ *   `a_list_host` (N refocus parameters) and `view_zeroed_host` (M*M flags) are small HOST arrays.
+ *   `scratch` is device memory of at least pcb_refocus_int_scratch_bytes(...) bytes (same arguments).
+ *   uint16 light fields with M <= 16 take the row-stationary kernel (each view row staged once in shared
+ *   memory and used for every slice); other inputs take the direct kernel.  Both are exact for integer
+ *   data; pcb_refocus_int_direct exposes the direct kernel alone (device-resident control arrays).
  * ------------------------------------------------------------------------------------------------ */
+int64_t pcb_refocus_int_scratch_bytes(int dtype, int M, int S, int T, int C,
+                                      const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host);
 int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C,
-                    const int32_t *a_list, int N, const uint8_t *view_zeroed,
-                    float *out, void *stream);
+                    const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host,
+                    void *scratch, int64_t scratch_bytes,
+                    float *out, pcb_minmax_t *mm /* nullable: fused min/max of the stack */, void *stream);
+int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C,
+                           const int32_t *a_list_dev, int N, const uint8_t *view_zeroed_dev,
+                           float *out, pcb_minmax_t *mm, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Post-processing of the stack — replaces LfpContrast.auto_hist_align + GammaConverter.srgb_conv as used
@@ -133,12 +144,15 @@ int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C,
  *                        `q_host` are percents in [0,100]; results (float64) go to `result` (device, nq).
  *                        `scratch` >= pcb_percentile_scratch_bytes() bytes.
  *   pcb_contrast_srgb  : y = clip((x-lo)/(hi-lo),0,1) evaluated in float64, cast to float32, then sRGB OETF.
- *                        lo/hi are read from the device (`lohi` = 2 doubles).
+ *                        lo/hi are read from the device (`lohi` = 2 doubles); a bound that is exactly 0 is
+ *                        replaced by the data min / max in *mm (Normalizer's falsy fallback, normalizer.py:40-41).
  * ------------------------------------------------------------------------------------------------ */
 int64_t pcb_percentile_scratch_bytes(void);
 int pcb_percentile_f32(const float *data, int64_t n, int luma, const double *q_host, int nq,
                        double *result, void *scratch, void *stream);
-int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, float *out, void *stream);
+int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi,
+                      const pcb_minmax_t *mm /* nullable: fallback for a bound that is exactly 0 */,
+                      float *out, void *stream);
 
 #ifdef __cplusplus
 }

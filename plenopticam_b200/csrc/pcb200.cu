@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "post.cuh"
 #include "refocus.cuh"
+#include "refocus_rows.cuh"
 #include "resample.cuh"
 #include "rotate.cuh"
 #include "viewpoints.cuh"
@@ -148,16 +149,75 @@ int pcb_crop_micro_images(const void *aligned, int dtype, int rows, int cols, in
     PCB_DISPATCH_COPY_DTYPE(dtype, launch_crop, aligned, cropped, rows, cols, C, M_in, M_out, as_stream(stream));
 }
 
-int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C, const int32_t *a_list, int N,
-                    const uint8_t *view_zeroed, float *out, void *stream) {
-    PCB_REQUIRE(vp != nullptr && a_list != nullptr && view_zeroed != nullptr && out != nullptr, "pointers");
+// Planning shared by pcb_refocus_int_scratch_bytes and pcb_refocus_int (host-only, deterministic).
+static RowsPlan refocus_plan(int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
+                             const uint8_t *view_zeroed_host) {
+    RowsPlan none;
+    memset(&none, 0, sizeof(none));
+    if (dtype != PCB_U16 || M > 16) return none;
+    int max_abs_a = 0;
+    for (int n = 0; n < N; ++n) {
+        const long long v = a_list_host[n] < 0 ? -(long long)a_list_host[n] : a_list_host[n];
+        if (v > 1000000) return none;
+        if (v > max_abs_a) max_abs_a = (int)v;
+    }
+    int max_act = 0;
+    for (int j = 0; j < M; ++j) {
+        int n = 0;
+        for (int i = 0; i < M; ++i) n += view_zeroed_host[j * M + i] ? 0 : 1;
+        if (n > max_act) max_act = n;
+    }
+    if (max_act == 0) return none;
+    return plan_refocus_rows(M, S, T, C, N, max_abs_a, max_act);
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int64_t pcb_refocus_int_scratch_bytes(int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
+                                      const uint8_t *view_zeroed_host) {
+    if (a_list_host == nullptr || view_zeroed_host == nullptr || M <= 0 || S <= 0 || T <= 0 || C <= 0 || N <= 0)
+        return -1;
+    const RowsPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host);
+    if (pl.ok) return (int64_t)(pl.acc_bytes + pl.edge_bytes);
+    return (int64_t)(align256((size_t)N * 4) + align256((size_t)M * M));
+}
+
+int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
+                    const uint8_t *view_zeroed_host, void *scratch, int64_t scratch_bytes, float *out,
+                    pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(vp != nullptr && a_list_host != nullptr && view_zeroed_host != nullptr && out != nullptr &&
+                scratch != nullptr, "pointers");
     PCB_REQUIRE(M > 0 && S > 0 && T > 0 && C > 0 && N > 0 && N <= 65535, "sizes");
     PCB_REQUIRE(M % 2 == 1, "odd M (even M changes the slice shape, lfp_shiftandsum.py:123-124)");
-    PCB_REQUIRE(dtype != PCB_F32 || true, "");
+    PCB_REQUIRE(scratch_bytes >= pcb_refocus_int_scratch_bytes(dtype, M, S, T, C, a_list_host, N, view_zeroed_host),
+                "scratch_bytes >= pcb_refocus_int_scratch_bytes(...)");
+    cudaStream_t st = as_stream(stream);
+    const RowsPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host);
+    if (pl.ok)
+        return launch_refocus_rows(pl, (const uint16_t *)vp, a_list_host, view_zeroed_host, scratch, out, mm, st);
+    // direct form: control arrays staged at the head of the scratch buffer
+    int32_t *a_dev = reinterpret_cast<int32_t *>(scratch);
+    uint8_t *z_dev = reinterpret_cast<uint8_t *>(scratch) + align256((size_t)N * 4);
+    PCB_CUDA(cudaMemcpyAsync(a_dev, a_list_host, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    PCB_CUDA(cudaMemcpyAsync(z_dev, view_zeroed_host, (size_t)M * M, cudaMemcpyHostToDevice, st));
     switch (dtype) {
-    case PCB_U16: return launch_refocus_int<uint16_t>(vp, M, S, T, C, a_list, N, view_zeroed, out, as_stream(stream));
-    case PCB_F32: return launch_refocus_int<float>(vp, M, S, T, C, a_list, N, view_zeroed, out, as_stream(stream));
-    case PCB_U8:  return launch_refocus_int<uint8_t>(vp, M, S, T, C, a_list, N, view_zeroed, out, as_stream(stream));
+    case PCB_U16: return launch_refocus_int<uint16_t>(vp, M, S, T, C, a_dev, N, z_dev, out, mm, st);
+    case PCB_F32: return launch_refocus_int<float>(vp, M, S, T, C, a_dev, N, z_dev, out, mm, st);
+    case PCB_U8:  return launch_refocus_int<uint8_t>(vp, M, S, T, C, a_dev, N, z_dev, out, mm, st);
+    }
+    return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
+// The direct (slice-stationary) form only; kept addressable for A/B measurements and as the general path.
+int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C, const int32_t *a_list_dev, int N,
+                           const uint8_t *view_zeroed_dev, float *out, pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(vp != nullptr && a_list_dev != nullptr && view_zeroed_dev != nullptr && out != nullptr, "pointers");
+    PCB_REQUIRE(M > 0 && S > 0 && T > 0 && C > 0 && N > 0 && N <= 65535 && M % 2 == 1, "sizes, odd M");
+    cudaStream_t st = as_stream(stream);
+    switch (dtype) {
+    case PCB_U16: return launch_refocus_int<uint16_t>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st);
+    case PCB_F32: return launch_refocus_int<float>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st);
+    case PCB_U8:  return launch_refocus_int<uint8_t>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st);
     }
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
@@ -172,9 +232,10 @@ int pcb_percentile_f32(const float *data, int64_t n, int luma, const double *q_h
     return run_percentile(data, n, luma, q_host, nq, result, scratch, as_stream(stream));
 }
 
-int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, float *out, void *stream) {
+int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, const pcb_minmax_t *mm, float *out,
+                      void *stream) {
     PCB_REQUIRE(in != nullptr && out != nullptr && lohi != nullptr && n > 0, "in, out, lohi, n > 0");
-    contrast_srgb_kernel<<<grid_for(n, 256 * 8), 256, 0, as_stream(stream)>>>(in, n, lohi, out);
+    contrast_srgb_kernel<<<grid_for(n, 256 * 8), 256, 0, as_stream(stream)>>>(in, n, lohi, mm, out);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }

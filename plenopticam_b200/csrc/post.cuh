@@ -48,8 +48,13 @@ __device__ __forceinline__ float contrast_srgb_one(float x, double lo, double hi
 }
 
 __global__ void __launch_bounds__(256)
-contrast_srgb_kernel(const float *__restrict__ in, int64_t n, const double *__restrict__ lohi, float *__restrict__ out) {
-    const double lo = lohi[0], hi = lohi[1];
+contrast_srgb_kernel(const float *__restrict__ in, int64_t n, const double *__restrict__ lohi,
+                     const pcb_minmax_t *__restrict__ mm, float *__restrict__ out) {
+    double lo = lohi[0], hi = lohi[1];
+    if (mm != nullptr) {   // misc/normalizer.py:40-41: a falsy bound falls back to the data's own min / max
+        if (lo == 0.0) lo = (double)key_to_float(mm->kmin);
+        if (hi == 0.0) hi = (double)key_to_float(mm->kmax);
+    }
     const bool scale = (hi != lo) && (hi != 0.0);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = n >> 2;

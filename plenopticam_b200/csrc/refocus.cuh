@@ -24,7 +24,7 @@ template <typename T, int CT>
 __global__ void __launch_bounds__(RF_THREADS)
 refocus_int_kernel(const T *__restrict__ vp, const int32_t *__restrict__ a_list,
                    const uint8_t *__restrict__ view_zeroed, float *__restrict__ out,
-                   int M, int S, int Tn, int Crt) {
+                   int M, int S, int Tn, int Crt, pcb_minmax_t *mm) {
     typedef typename AccOf<T>::type Acc;
     const int C = CT ? CT : Crt;
     const int y = blockIdx.x, n = blockIdx.y;
@@ -61,24 +61,31 @@ refocus_int_kernel(const T *__restrict__ vp, const int32_t *__restrict__ a_list,
     }
 
     float *orow = out + ((size_t)n * S + y) * ne;
+    float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < RF_EPT; ++k) {
         const int e = e0 + threadIdx.x + k * RF_THREADS;
-        if (e < ne) orow[e] = finish_acc(acc[k], M);
+        if (e < ne) {
+            const float v = finish_acc(acc[k], M);
+            orow[e] = v;
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
     }
+    if (mm != nullptr) block_minmax_commit(mn, mx, mm);   // stack min/max for Normalizer's falsy-bound fallback
 }
 
 template <typename T>
 static int launch_refocus_int(const void *vp, int M, int S, int Tn, int C, const int32_t *a_list, int N,
-                              const uint8_t *view_zeroed, float *out, cudaStream_t st) {
+                              const uint8_t *view_zeroed, float *out, pcb_minmax_t *mm, cudaStream_t st) {
     const int ne = Tn * C;
     dim3 grid(S, N, (ne + RF_THREADS * RF_EPT - 1) / (RF_THREADS * RF_EPT)), block(RF_THREADS);
     if (C == 3)
-        refocus_int_kernel<T, 3><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C);
+        refocus_int_kernel<T, 3><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C, mm);
     else if (C == 1)
-        refocus_int_kernel<T, 1><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C);
+        refocus_int_kernel<T, 1><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C, mm);
     else
-        refocus_int_kernel<T, 0><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C);
+        refocus_int_kernel<T, 0><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C, mm);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }

@@ -229,12 +229,53 @@ def aperture_mask(M):
     return (np.rint(np.sqrt(ii.astype(np.float64) ** 2 + jj.astype(np.float64) ** 2)).astype(np.int64) > c)
 
 
-def refocus_int(vp, a_list, view_zeroed=None, out=None):
-    """(N,S,T,C) float32 stack of integer shift-and-sum slices (divided by M)."""
+class RefocusPlan(object):
+    """Host control arrays + device scratch for pcb_refocus_int; reusable across exposures of one camera."""
+
+    def __init__(self, vp_shape, vp_dtype, a_list, view_zeroed, device):
+        M, M2, S, T, Cn = vp_shape
+        if M != M2:
+            raise ValueError("square angular resolution expected")
+        self.shape = (int(M), int(S), int(T), int(Cn))
+        self.dtype = _TORCH2PCB[vp_dtype]
+        self.a_host = np.ascontiguousarray(np.asarray(list(a_list), dtype=np.int32))
+        self.N = int(self.a_host.size)
+        if view_zeroed is None:
+            view_zeroed = aperture_mask(M)
+        self.z_host = np.ascontiguousarray(np.asarray(view_zeroed, dtype=np.uint8).reshape(-1))
+        if self.z_host.size != M * M:
+            raise ValueError("view mask must have M*M entries")
+        self.a_ptr = self.a_host.ctypes.data_as(C.c_void_p)
+        self.z_ptr = self.z_host.ctypes.data_as(C.c_void_p)
+        nbytes = int(nat.lib().pcb_refocus_int_scratch_bytes(self.dtype, M, S, T, Cn, self.a_ptr, self.N, self.z_ptr))
+        if nbytes < 0:
+            raise ValueError("invalid refocus configuration")
+        self.scratch = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+
+    def launch(self, vp, out, mm=None):
+        M, S, T, Cn = self.shape
+        nat.check(nat.lib().pcb_refocus_int(_ptr(vp), self.dtype, M, S, T, Cn, self.a_ptr, self.N, self.z_ptr,
+                                            _ptr(self.scratch), self.scratch.numel(), _ptr(out),
+                                            _ptr(mm) if mm is not None else C.c_void_p(0), _stream()))
+        return out
+
+
+def refocus_int(vp, a_list, view_zeroed=None, out=None, mm=None, plan=None):
+    """(N,S,T,C) float32 stack of integer shift-and-sum slices (divided by M); `mm` (from new_minmax())
+    optionally receives the stack's min/max from the same launch."""
+    _chk_dev(vp)
+    if plan is None:
+        plan = RefocusPlan(tuple(vp.shape), vp.dtype, a_list, view_zeroed, vp.device)
+    M, S, T, Cn = plan.shape
+    if out is None:
+        out = torch.empty((plan.N, S, T, Cn), dtype=torch.float32, device=vp.device)
+    return plan.launch(vp, out, mm)
+
+
+def refocus_int_direct(vp, a_list, view_zeroed=None, out=None, mm=None):
+    """Same result through the direct (slice-stationary) kernel only; used for A/B checks."""
     _chk_dev(vp)
     M, M2, S, T, Cn = vp.shape
-    if M != M2:
-        raise ValueError("square angular resolution expected")
     a_host = np.ascontiguousarray(np.asarray(list(a_list), dtype=np.int32))
     N = int(a_host.size)
     if view_zeroed is None:
@@ -243,8 +284,8 @@ def refocus_int(vp, a_list, view_zeroed=None, out=None):
     z_dev = torch.from_numpy(np.ascontiguousarray(view_zeroed, dtype=np.uint8).reshape(-1)).to(vp.device)
     if out is None:
         out = torch.empty((N, S, T, Cn), dtype=torch.float32, device=vp.device)
-    nat.check(nat.lib().pcb_refocus_int(_ptr(vp), _pcb_dtype(vp), M, S, T, Cn, _ptr(a_dev), N, _ptr(z_dev),
-                                        _ptr(out), _stream()))
+    nat.check(nat.lib().pcb_refocus_int_direct(_ptr(vp), _pcb_dtype(vp), M, S, T, Cn, _ptr(a_dev), N, _ptr(z_dev),
+                                               _ptr(out), _ptr(mm) if mm is not None else C.c_void_p(0), _stream()))
     return out
 
 
@@ -268,26 +309,25 @@ def percentile(data, q, luma=False):
     return res
 
 
-def contrast_srgb(stack, lohi, out=None):
-    """clip((x-lo)/(hi-lo)) then sRGB; `lohi` is a float64 CUDA tensor [lo, hi]."""
+def contrast_srgb(stack, lohi, mm=None, out=None):
+    """clip((x-lo)/(hi-lo)) then sRGB; `lohi` is a float64 CUDA tensor [lo, hi]; a bound that is exactly 0
+    is replaced on the device by the data min/max in `mm` (misc/normalizer.py:40-41)."""
     _chk_dev(stack, lohi)
     if out is None:
         out = torch.empty_like(stack)
-    nat.check(nat.lib().pcb_contrast_srgb(_ptr(stack), stack.numel(), _ptr(lohi), _ptr(out), _stream()))
+    nat.check(nat.lib().pcb_contrast_srgb(_ptr(stack), stack.numel(), _ptr(lohi),
+                                          _ptr(mm) if mm is not None else C.c_void_p(0), _ptr(out), _stream()))
     return out
 
 
-def refocuser_postprocess(stack):
-    """LfpRefocuser.shift_and_sum's colour management (lfp_refocuser/top_level.py:68-70), on the device:
-    lo = P0.005(luma(stack[0])), hi = P99.9(stack[0]); falsy lo/hi fall back to the stack's min/max
-    (misc/normalizer.py:40-41)."""
+def refocuser_postprocess(stack, mm=None, out=None):
+    """LfpRefocuser.shift_and_sum's colour management (lfp_refocuser/top_level.py:68-70), on the device and
+    without a host round trip: lo = P0.005(luma(stack[0])), hi = P99.9(stack[0]), normalise, sRGB.
+    `mm`: min/max keys of the stack (computed here if not supplied by the refocus launch)."""
     ref = stack[0]
-    lo = percentile(ref, [0.005], luma=True)
-    hi = percentile(ref, [99.9], luma=False)
-    lohi = torch.cat([lo, hi])
-    vals = lohi.cpu().numpy()
-    if not vals[0] or not vals[1]:
-        mn, mx = minmax_values(minmax_f32(stack))
-        vals = np.array([vals[0] if vals[0] else mn, vals[1] if vals[1] else mx], dtype=np.float64)
-        lohi = torch.from_numpy(vals).to(stack.device)
-    return contrast_srgb(stack, lohi)
+    lohi = torch.empty(2, dtype=torch.float64, device=stack.device)
+    lohi[0:1] = percentile(ref, [0.005], luma=True)
+    lohi[1:2] = percentile(ref, [99.9], luma=False)
+    if mm is None:
+        mm = minmax_f32(stack)
+    return contrast_srgb(stack, lohi, mm=mm, out=out)

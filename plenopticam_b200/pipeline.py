@@ -1,0 +1,138 @@
+"""Device-resident light-field pipeline: raw exposure -> aligned uint16 LF -> 4-D viewpoints -> refocus stack
+-> contrast/sRGB, with every buffer pre-allocated in HBM and nothing but kernel launches in the steady state.
+
+This is the batch / serving form of the three stage classes: the same kernels, same results, but the aligned
+image, the viewpoint array and the stack never leave the GPU unless asked for.  `run()` is the host-buffer
+entry point (pinned H2D of the raw exposure in, D2H of the finished stack out).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import ops
+from .lfp_aligner.lfp_microlenses import build_tables
+
+
+class LightFieldPipeline(object):
+    """One calibrated camera (centroid table + angular size) -> reusable executor.
+
+    centroids : (N,4) table rows [y, x, ly, lx] (cfg.calibs['mic_list'])
+    raw_shape : (H, W, C) of the exposures;  raw_dtype: numpy dtype of the device copy (uint16/uint8/float32)
+    M         : micro-image size (cfg.params['ptc_leng'], already validated by LfpMicroLenses.safe_pitch_eval)
+    ran_refo  : cfg.params['ran_refo'] -> slices a in range(*ran_refo)
+    """
+
+    def __init__(self, centroids, raw_shape, raw_dtype, M, pat_type, ran_refo=(0, 2), flip=False,
+                 postprocess=True, device=None):
+        self.device = ops.require_cuda() if device is None else torch.device(device)
+        self.M = int(M)
+        self.flip = bool(flip)
+        self.postprocess = bool(postprocess)
+        self.raw_shape = tuple(int(v) for v in raw_shape)
+        self.raw_dtype = np.dtype(raw_dtype)
+        if self.M % 2 == 0:
+            raise ValueError("odd micro-image size required for refocusing (lfp_shiftandsum.py:123-124)")
+        if self.raw_shape[2] != 3:
+            raise ValueError("the refocus accumulator is 3-channel (lfp_shiftandsum.py:97)")
+        self.tables = build_tables(centroids, self.raw_shape, self.M, pat_type)
+        with torch.cuda.device(self.device):
+            self.tabs = ops.LensTables(self.tables)
+            LY, Xs, Cn = self.tables["LY"], self.tables["Xs"], self.raw_shape[2]
+            self.S, self.T = LY, Xs
+            self.a_list = list(range(*ran_refo))
+            self.N = len(self.a_list)
+            dev = self.device
+            tdt = ops._NP2TORCH[self.raw_dtype]
+            self.raw = torch.empty(self.raw_shape, dtype=tdt, device=dev)
+            self.aligned = torch.empty((LY * self.M, Xs * self.M, Cn), dtype=torch.uint16, device=dev)
+            self.vp = torch.empty((self.M, self.M, LY, Xs, Cn), dtype=torch.uint16, device=dev)
+            self.stack = torch.empty((self.N, LY, Xs, Cn), dtype=torch.float32, device=dev)
+            self.post = torch.empty_like(self.stack) if self.postprocess else None
+            self.mm_align = torch.empty(2, dtype=torch.int32, device=dev)
+            self.mm_stack = torch.empty(2, dtype=torch.int32, device=dev)
+            self.refocus_plan = ops.RefocusPlan(tuple(self.vp.shape), self.vp.dtype, self.a_list,
+                                                ops.aperture_mask(self.M), dev)
+            self.lohi = torch.empty(2, dtype=torch.float64, device=dev)
+            self.scratch = torch.empty(int(nat.lib().pcb_percentile_scratch_bytes()), dtype=torch.uint8, device=dev)
+            self._q_lo = (C.c_double * 1)(0.005)
+            self._q_hi = (C.c_double * 1)(99.9)
+            # pinned staging for the host-buffer entry point
+            self._pin_in = None
+            self._pin_out = None
+        self.n_active_views = int((~ops.aperture_mask(self.M)).sum())
+
+    # -- stage launches (enqueue only) ---------------------------------------------------------------------
+    def align(self, raw=None):
+        raw = self.raw if raw is None else raw
+        ops.resample_u16(raw, self.tabs, flip=self.flip, out=self.aligned, mm=self.mm_align)
+        return self.aligned
+
+    def viewpoints(self):
+        ops.viewpoints(self.aligned, self.M, out=self.vp)
+        return self.vp
+
+    def refocus(self):
+        L, p, st = nat.lib(), ops._ptr, ops._stream()
+        nat.check(L.pcb_minmax_reset(p(self.mm_stack), st))
+        self.refocus_plan.launch(self.vp, self.stack, self.mm_stack)
+        return self.stack
+
+    def post_process(self):
+        L, p, st = nat.lib(), ops._ptr, ops._stream()
+        n0 = self.S * self.T * 3
+        nat.check(L.pcb_percentile_f32(p(self.stack), n0 // 3, 1, self._q_lo, 1, C.c_void_p(self.lohi.data_ptr()),
+                                       p(self.scratch), st))
+        nat.check(L.pcb_percentile_f32(p(self.stack), n0, 0, self._q_hi, 1, C.c_void_p(self.lohi.data_ptr() + 8),
+                                       p(self.scratch), st))
+        nat.check(L.pcb_contrast_srgb(p(self.stack), self.stack.numel(), p(self.lohi), p(self.mm_stack),
+                                      p(self.post), st))
+        return self.post
+
+    def run_device(self, raw=None):
+        """All stages on the current stream; returns the final device tensor (sRGB stack, or the linear
+        stack if postprocess=False)."""
+        self.align(raw)
+        self.viewpoints()
+        self.refocus()
+        return self.post_process() if self.postprocess else self.stack
+
+    # -- host-buffer entry point -----------------------------------------------------------------------------
+    def _staging(self):
+        if self._pin_in is None:
+            tdt = ops._NP2TORCH[self.raw_dtype]
+            self._pin_in = torch.empty(self.raw_shape, dtype=tdt, pin_memory=True)
+            self._pin_out = torch.empty(tuple(self.stack.shape), dtype=torch.float32, pin_memory=True)
+        return self._pin_in, self._pin_out
+
+    def pinned_input(self):
+        """Pinned host buffer the caller may fill directly (numpy view) to skip one host copy."""
+        pin_in, _ = self._staging()
+        return pin_in.view(torch.int16).numpy().view(np.uint16) if pin_in.dtype == torch.uint16 else pin_in.numpy()
+
+    def run(self, raw_host=None):
+        """raw exposure (numpy, host) -> finished stack (numpy view of a pinned buffer, valid until next run)."""
+        pin_in, pin_out = self._staging()
+        if raw_host is not None:
+            self.pinned_input()[...] = raw_host
+        self.raw.copy_(pin_in, non_blocking=True)
+        out = self.run_device()
+        pin_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pin_out.numpy()
+
+    # -- byte accounting used by bench.py / DESIGN.md --------------------------------------------------------
+    def algorithmic_bytes(self):
+        H, W, Cn = self.raw_shape
+        b_raw = H * W * Cn * self.raw_dtype.itemsize
+        b_al = self.aligned.numel() * 2
+        b_sl = self.S * self.T * 3 * 4
+        b_vp_active = self.n_active_views * self.S * self.T * 3 * 2
+        return {
+            "resample_minmax": b_raw,
+            "resample_u16": b_raw + b_al,
+            "viewpoints": 2 * b_al,
+            "refocus_int": b_vp_active + self.N * b_sl,
+            "post": 2 * self.N * b_sl + 2 * 4 * b_sl,
+        }

@@ -260,3 +260,50 @@ def test_interrupt_returns_false(cuda):
     assert LfpResampler(lfp_img=g["raw"], cfg=cfg, sta=sta).main() is False
     g = golden("refocus_int_u16")
     assert LfpShiftAndSum(vp_img_arr=g["vp"], cfg=cfg, sta=sta).main() is False
+
+
+# ------------------------------------------------------------------------------------------------------
+# row-stationary refocus kernel vs direct kernel vs oracle
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,S,T,a_list", [
+    (15, 37, 61, list(range(-32, 32))),          # Illum-like angular size, shifts far larger than the image
+    (7, 19, 1300, [-3, 0, 2, 5]),                # wide rows -> several x chunks, several words per thread
+    (5, 3, 4, list(range(-40, 40))),             # tiny image, N > 64 -> two launches, shift >> T
+    (9, 1, 33, [-2, -1, 0, 1, 2]),               # single row: top and bottom edge are the same row
+    (3, 40, 7, [100, -100, 1]),                  # |a| huge
+])
+def test_refocus_rows_equals_direct_and_oracle(cuda, M, S, T, a_list):
+    from plenopticam_b200 import ops
+    rng = np.random.default_rng(M * 1000 + S)
+    vp = rng.integers(0, 65536, size=(M, M, S, T, 3), dtype=np.uint16)
+    vp[:, :, :, :, 0] |= 0xff00                    # exercise the carry between the packed halves
+    dev = ops.to_device(vp)
+    mm = ops.new_minmax()
+    fast = ops.to_host(ops.refocus_int(dev, a_list, mm=mm))
+    direct = ops.to_host(ops.refocus_int_direct(dev, a_list))
+    assert np.array_equal(fast, direct)
+    vp64 = onp._apply_aperture(vp, M) / M
+    for k in sorted(set([0, len(a_list) // 2, len(a_list) - 1])):
+        ref = onp.refocus_int_slice(vp64, a_list[k], M).astype(np.float32)
+        assert np.array_equal(fast[k], ref), (k, a_list[k])
+    mn, mx = ops.minmax_values(mm)
+    assert mn == fast.min() and mx == fast.max()
+
+
+def test_refocus_rows_custom_mask_and_mono_fallback(cuda):
+    from plenopticam_b200 import ops
+    rng = np.random.default_rng(11)
+    M, S, T = 7, 9, 14
+    vp = rng.integers(0, 65536, size=(M, M, S, T, 3), dtype=np.uint16)
+    mask = rng.random((M, M)) < 0.4
+    mask[2, :] = True                               # a fully masked view row
+    dev = ops.to_device(vp)
+    a_list = [-4, 1, 3]
+    fast = ops.to_host(ops.refocus_int(dev, a_list, view_zeroed=mask))
+    direct = ops.to_host(ops.refocus_int_direct(dev, a_list, view_zeroed=mask))
+    assert np.array_equal(fast, direct)
+    # float32 light field -> direct kernel through the same entry point
+    vpf = rng.random((M, M, S, T, 3), dtype=np.float32)
+    got = ops.to_host(ops.refocus_int(ops.to_device(vpf), a_list))
+    ref = np.asarray([onp.refocus_int_slice(onp._apply_aperture(vpf, M) / M, a, M) for a in a_list])
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
