@@ -161,14 +161,15 @@ static RowsPlan refocus_plan(int dtype, int M, int S, int T, int C, const int32_
         if (v > 1000000) return none;
         if (v > max_abs_a) max_abs_a = (int)v;
     }
-    int max_act = 0;
+    int max_act = 0, tot_act = 0;
     for (int j = 0; j < M; ++j) {
         int n = 0;
         for (int i = 0; i < M; ++i) n += view_zeroed_host[j * M + i] ? 0 : 1;
         if (n > max_act) max_act = n;
+        tot_act += n;
     }
     if (max_act == 0) return none;
-    return plan_refocus_rows(M, S, T, C, N, max_abs_a, max_act);
+    return plan_refocus_rows(M, S, T, C, N, max_abs_a, max_act, tot_act);
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }

@@ -25,18 +25,34 @@ viewpoints_kernel(const T *__restrict__ aligned, T *__restrict__ vp, int cols_el
 
     const T *src = aligned + (size_t)(s * M_in + kc + j) * cols_elems + (size_t)t0 * M_in * C;
     const int n_in = nt * M_in * C;
-    for (int idx = threadIdx.x; idx < n_in; idx += blockDim.x) row[idx] = __ldg(src + idx);
+    // read the row with VP_UNROLL independent loads in flight per thread (the copy is latency-bound otherwise)
+    constexpr int VP_UNROLL = 8;
+    for (int base = threadIdx.x; base < n_in; base += 256 * VP_UNROLL) {
+        T v[VP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < VP_UNROLL; ++u) {
+            const int idx = base + u * 256;
+            if (idx < n_in) v[u] = __ldg(src + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < VP_UNROLL; ++u) {
+            const int idx = base + u * 256;
+            if (idx < n_in) row[idx] = v[u];
+        }
+    }
     __syncthreads();
 
+    // every thread keeps its (t, c) decomposition and walks the M_out views: no division in the store loop
     const int n_out = nt * C;
-    for (int i = 0; i < M_out; ++i) {
-        T *dst = vp + (((size_t)(j * M_out + i) * S + s) * Tn + t0) * C;
-        const int off = (kc + i) * C;
-        for (int idx = threadIdx.x; idx < n_out; idx += blockDim.x) {
-            const int t = idx / C;
-            const int c = idx - t * C;
-            dst[idx] = row[t * M_in * C + off + c];
-        }
+    const int mc = M_in * C;
+    for (int idx = threadIdx.x; idx < n_out; idx += 256) {
+        const int t = idx / C;
+        const int c = idx - t * C;
+        const T *rp = row + t * mc + kc * C + c;
+        T *dst = vp + (((size_t)(j * M_out) * S + s) * Tn + t0) * C + idx;
+        const size_t view_stride = (size_t)S * Tn * C;
+#pragma unroll 5
+        for (int i = 0; i < M_out; ++i) dst[i * view_stride] = rp[i * C];
     }
 }
 
