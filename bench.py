@@ -33,7 +33,7 @@ SMALL = dict(H=0, W=0, C=3, LY=60, LX=75, M=15, pitch=14.25, origin=(9.5, 9.5), 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slices", type=int, default=64)
@@ -89,7 +89,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -149,7 +149,7 @@ def _cpu_slices(job):
     return [onp.refocus_int_slice(_G["vp64"], a, _G["M"]) for a in job]
 
 
-def cpu_pipeline_sample(w, n_slices, cores, area_div=16):
+def cpu_pipeline_sample(w, n_slices, cores, area_div=4):
     """Oracle port on a bounded sample: a 1/area_div-area crop of the lens grid and `n_slices` slices, the
     independent parts (lens rows, slices) spread over `cores` forked processes.  Returns (seconds, dict)."""
     import multiprocessing as mp
@@ -211,7 +211,7 @@ def run_reference_arm(args):
     w = workload(args)
     make_centroids(w)
     cores = os.cpu_count() or 1
-    n_slices = min(8, args.slices)
+    n_slices = min(16, args.slices)
     steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
     for _ in range(warm):
         cpu_pipeline_sample(w, n_slices, cores)
@@ -222,7 +222,7 @@ def run_reference_arm(args):
     t_full = float(np.mean(ts))
     n_total = w["ran_refo"][1] - w["ran_refo"][0]
     val = n_total / t_full
-    sample = ("1/16-area crop of the Illum lens grid (%dx%d lenslets) and %d of %d slices per step, "
+    sample = ("1/4-area crop of the Illum lens grid (%dx%d lenslets) and %d of %d slices per step, "
               "extrapolated linearly in lenslets x slices" % (info["lens_grid"][0], info["lens_grid"][1], n_slices, n_total))
     line = {
         "impl": "reference", "metric": "refocus_slices_per_s", "value": val, "unit": "slices/s",
@@ -389,9 +389,9 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        t_full, info = cpu_pipeline_sample(w, min(4, n_slices), 1)
+        t_full, info = cpu_pipeline_sample(w, min(8, n_slices), 1)
         cpu_baseline = {"value": n_slices / t_full, "unit": "slices/s", "cores": 1, "kind": "port",
-                        "sample": "numpy oracle, 1 core: 1/16-area crop (%dx%d lenslets), %d of %d slices, extrapolated "
+                        "sample": "numpy oracle, 1 core: 1/4-area crop (%dx%d lenslets), %d of %d slices, extrapolated "
                                   "linearly in lenslets x slices" % (info["lens_grid"][0], info["lens_grid"][1],
                                                                      info["slices"], n_slices),
                         "detail": info}

@@ -27,11 +27,11 @@ minmax_f32_kernel(const float *__restrict__ data, int64_t n, pcb_minmax_t *mm) {
 
 __global__ void __launch_bounds__(256)
 quantize_u16_kernel(const float *__restrict__ in, int64_t n, const pcb_minmax_t *mm, uint16_t *__restrict__ out) {
-    const float mn = key_to_float(mm->kmin), mx = key_to_float(mm->kmax);
-    const bool scale = (mx != mn) && (mx != 0.f);
+    QuantU16 qz;
+    qz.init(key_to_float(mm->kmin), key_to_float(mm->kmax));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = quantize_u16(__ldg(in + i), mn, mx, scale);
+        out[i] = qz(__ldg(in + i));
 }
 
 // ---- contrast + sRGB ------------------------------------------------------------------------------

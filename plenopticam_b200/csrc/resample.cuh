@@ -38,40 +38,107 @@ template <int MODE>
 struct ResampleOut {
     float *f32;
     uint16_t *u16;
-    float q_mn, q_mx;
-    bool q_scale;
+    QuantU16 qz;
     __device__ __forceinline__ void put(size_t o, float val) const {
         if (MODE == RS_F32) f32[o] = val;
-        if (MODE == RS_U16) u16[o] = quantize_u16(val, q_mn, q_mx, q_scale);
+        if (MODE == RS_U16) u16[o] = qz(val);
     }
 };
 
-// One output column from a row-addressable source: src(r) points at the sample (row r, column u, ch) of the
-// patch; src(r)[C] is its right neighbour.
-template <int MODE, typename Ld0, typename Ld1>
+template <typename T> __device__ __forceinline__ float as_float(T v) { return (float)v; }
+
+// One output column.  s0 / s1 point at the sample (row 0, column u, ch) of the two source patches inside a
+// row-addressable source (the shared-memory tile or the raw image); the right neighbour is C elements on, the
+// next row `stride` elements on.
+template <int MODE, typename TS>
 __device__ __forceinline__ void resample_column(const ResampleArgs &p, const ResampleOut<MODE> &out, int ly, int col,
-                                                bool ok0, bool ok1, bool two, float wx0, float wy0, float wx1,
-                                                float wy1, float w, Ld0 ld0, Ld1 ld1, float &mn, float &mx) {
+                                                int C, bool ok0, bool ok1, bool two, float wx0, float wy0, float wx1,
+                                                float wy1, float w, const TS *s0, const TS *s1, size_t stride,
+                                                float &mn, float &mx) {
     const int M = p.M;
     float h0p = 0.f, h1p = 0.f;
-    if (ok0) { float a, b; ld0(0, a, b); h0p = fmaf(b - a, wx0, a); }
-    if (ok1) { float a, b; ld1(0, a, b); h1p = fmaf(b - a, wx1, a); }
-    const size_t out_row0 = (size_t)ly * M;
+    if (ok0) { const float a = as_float(s0[0]), b = as_float(s0[C]); h0p = fmaf(b - a, wx0, a); }
+    if (ok1) { const float a = as_float(s1[0]), b = as_float(s1[C]); h1p = fmaf(b - a, wx1, a); }
+    // output element of patch row v = 0 and the step to the next written row (reversed when flipping)
+    size_t o = ((size_t)ly * M + (p.flip ? M - 1 : 0)) * (size_t)p.ncols + col;
+    const long long ostep = p.flip ? -(long long)p.ncols : (long long)p.ncols;
 #pragma unroll 5
     for (int r = 1; r <= M; ++r) {
+        s0 += stride;
+        s1 += stride;
         float h0 = 0.f, h1 = 0.f;
-        if (ok0) { float a, b; ld0(r, a, b); h0 = fmaf(b - a, wx0, a); }
-        if (ok1) { float a, b; ld1(r, a, b); h1 = fmaf(b - a, wx1, a); }
+        if (ok0) { const float a = as_float(s0[0]), b = as_float(s0[C]); h0 = fmaf(b - a, wx0, a); }
+        if (ok1) { const float a = as_float(s1[0]), b = as_float(s1[C]); h1 = fmaf(b - a, wx1, a); }
         float val = fmaf(h0 - h0p, wy0, h0p);
-        if (two) {
-            const float v1 = fmaf(h1 - h1p, wy1, h1p);
-            val = fmaf(v1 - val, w, val);
-        }
+        const float v1 = fmaf(h1 - h1p, wy1, h1p);
+        val = two ? fmaf(v1 - val, w, val) : val;
         h0p = h0; h1p = h1;
-        const int v = p.flip ? (M - r) : (r - 1);
-        out.put((out_row0 + v) * (size_t)p.ncols + col, val);
+        out.put(o, val);
+        o += ostep;
         mn = fminf(mn, val);
         mx = fmaxf(mx, val);
+    }
+}
+
+// Stage `R` rows of `Wt` elements starting at raw element (ymin*W + xmin)*C into the float tile.
+// uint16 rows go through aligned 32-bit loads (two samples per load); RS_STAGE_UNROLL loads stay in flight.
+constexpr int RS_STAGE_UNROLL = 12;
+template <typename TIn>
+__device__ __forceinline__ void stage_tile(const ResampleArgs &p, float *tile, int ymin, int xmin, int R, int Wt, int C) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t total_elems = (size_t)p.H * p.W * C;
+    for (int rr = warp; rr < R; rr += RS_THREADS / 32) {
+        const size_t gE = ((size_t)(ymin + rr) * p.W + xmin) * C;
+        const TIn *src = (const TIn *)p.raw + gE;
+        float *dst = tile + rr * Wt;
+        bool done = false;
+        if constexpr (sizeof(TIn) == 2) {
+            if ((reinterpret_cast<uintptr_t>(p.raw) & 3) == 0) {
+                const int g = (int)(gE & 1);
+                const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(src - g);
+                int nw = (Wt + g + 1) >> 1;
+                if (gE - g + 2 * (size_t)nw > total_elems) --nw;          // never read past the image
+                for (int base = lane; base < nw; base += 32 * RS_STAGE_UNROLL) {
+                    uint32_t v[RS_STAGE_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < RS_STAGE_UNROLL; ++u) {
+                        const int m = base + u * 32;
+                        if (m < nw) v[u] = __ldg(wsrc + m);
+                    }
+#pragma unroll
+                    for (int u = 0; u < RS_STAGE_UNROLL; ++u) {
+                        const int m = base + u * 32;
+                        if (m < nw) {
+                            const int e = 2 * m - g;
+                            const float f0 = (float)(v[u] & 0xffffu), f1 = (float)(v[u] >> 16);
+                            if (g == 0 && !(Wt & 1) && e + 1 < Wt) {
+                                *reinterpret_cast<float2 *>(dst + e) = make_float2(f0, f1);   // 8-byte aligned pair
+                            } else {
+                                if (e >= 0) dst[e] = f0;
+                                if (e + 1 < Wt) dst[e + 1] = f1;
+                            }
+                        }
+                    }
+                }
+                for (int e = 2 * nw - g + lane; e < Wt; e += 32) dst[e] = ld_as_float(src + e);   // tail sample
+                done = true;
+            }
+        }
+        if (!done) {
+            for (int base = lane; base < Wt; base += 32 * RS_STAGE_UNROLL) {
+                float v[RS_STAGE_UNROLL];
+#pragma unroll
+                for (int u = 0; u < RS_STAGE_UNROLL; ++u) {
+                    const int e = base + u * 32;
+                    if (e < Wt) v[u] = ld_as_float(src + e);
+                }
+#pragma unroll
+                for (int u = 0; u < RS_STAGE_UNROLL; ++u) {
+                    const int e = base + u * 32;
+                    if (e < Wt) dst[e] = v[u];
+                }
+            }
+        }
     }
 }
 
@@ -93,12 +160,9 @@ resample_tile_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
     const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((ly + p.hex_odd) & 1) * p.Xs : nullptr;
 
     ResampleOut<MODE> out;
-    out.f32 = out_f32; out.u16 = out_u16; out.q_mn = 0.f; out.q_mx = 0.f; out.q_scale = false;
-    if (MODE == RS_U16) {
-        out.q_mn = key_to_float(mm_ro->kmin);
-        out.q_mx = key_to_float(mm_ro->kmax);
-        out.q_scale = (out.q_mx != out.q_mn) && (out.q_mx != 0.f);
-    }
+    out.f32 = out_f32; out.u16 = out_u16;
+    out.qz.init(0.f, 0.f);
+    if (MODE == RS_U16) out.qz.init(key_to_float(mm_ro->kmin), key_to_float(mm_ro->kmax));
 
     // ---- source lens range of this tile (hexcol x0/x1 are non-decreasing in k)
     if (tid == 0) {
@@ -131,15 +195,7 @@ resample_tile_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
     const bool any_valid = s_box[1] != INT32_MIN;
     const bool use_tile = lens_in_smem && any_valid && (long long)R * Wt <= p.cap_floats;
 
-    if (use_tile) {
-        // stage: warps take rows, lanes run along the contiguous (x, ch) axis
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int rr = warp; rr < R; rr += RS_THREADS / 32) {
-            const TIn *src = (const TIn *)p.raw + ((size_t)(ymin + rr) * p.W + xmin) * C;
-            float *dst = tile + rr * Wt;
-            for (int e = lane; e < Wt; e += 32) dst[e] = ld_as_float(src + e);
-        }
-    }
+    if (use_tile) stage_tile<TIn>(p, tile, ymin, xmin, R, Wt, C);   // warps take rows, lanes run along (x, ch)
     __syncthreads();
 
     float mn = INFINITY, mx = -INFINITY;
@@ -166,16 +222,14 @@ resample_tile_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
         if (use_tile) {
             const float *t0 = tile + (ok0 ? (L0.oy - ymin) * Wt + (L0.ox - xmin + us) * C + ch : 0);
             const float *t1 = tile + (ok1 ? (L1.oy - ymin) * Wt + (L1.ox - xmin + us) * C + ch : 0);
-            auto ld0 = [&](int r, float &a, float &b) { a = t0[r * Wt]; b = t0[r * Wt + C]; };
-            auto ld1 = [&](int r, float &a, float &b) { a = t1[r * Wt]; b = t1[r * Wt + C]; };
-            resample_column<MODE>(p, out, ly, col, ok0, ok1, two, L0.wx, L0.wy, L1.wx, L1.wy, w, ld0, ld1, mn, mx);
+            resample_column<MODE, float>(p, out, ly, col, C, ok0, ok1, two, L0.wx, L0.wy, L1.wx, L1.wy, w, t0, t1,
+                                         (size_t)Wt, mn, mx);
         } else {
             const size_t stride = (size_t)p.W * C;
             const TIn *g0 = (const TIn *)p.raw + ((size_t)(ok0 ? L0.oy : 0) * p.W + (ok0 ? L0.ox : 0) + us) * C + ch;
             const TIn *g1 = (const TIn *)p.raw + ((size_t)(ok1 ? L1.oy : 0) * p.W + (ok1 ? L1.ox : 0) + us) * C + ch;
-            auto ld0 = [&](int r, float &a, float &b) { a = ld_as_float(g0 + r * stride); b = ld_as_float(g0 + r * stride + C); };
-            auto ld1 = [&](int r, float &a, float &b) { a = ld_as_float(g1 + r * stride); b = ld_as_float(g1 + r * stride + C); };
-            resample_column<MODE>(p, out, ly, col, ok0, ok1, two, L0.wx, L0.wy, L1.wx, L1.wy, w, ld0, ld1, mn, mx);
+            resample_column<MODE, TIn>(p, out, ly, col, C, ok0, ok1, two, L0.wx, L0.wy, L1.wx, L1.wy, w, g0, g1, stride,
+                                       mn, mx);
         }
     }
     if (MODE != RS_U16 && mm_rw != nullptr) block_minmax_commit(mn, mx, mm_rw);
@@ -183,7 +237,7 @@ resample_tile_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
 
 // Tile geometry chosen on the host from the nominal lens pitch; the kernel guards the real box per CTA.
 static void resample_geometry(ResampleArgs &a, size_t *smem_bytes) {
-    const int cap_bytes = 56 * 1024;                       // 4 CTAs of 256 threads per SM
+    const int cap_bytes = 54 * 1024;                       // 4 CTAs of 256 threads per SM (with the static smem)
     const double pitch = (double)a.W / (double)a.LX;      // nominal lens pitch in raw pixels
     const double src_per_out = (double)a.LX / (double)a.Xs;
     const int rows = a.M + 1 + 4;                          // M+1 rows plus centroid scatter allowance

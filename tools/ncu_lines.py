@@ -25,12 +25,17 @@ for blk in txt.split('"File Path",')[1:]:
     rd = csv.reader(io.StringIO("\n".join(lines[2:])))
     hdr = next(rd)
     i_line, i_src, i_samp, i_inst = 0, 1, hdr.index("# Samples"), hdr.index("Instructions Executed")
+    def num(x):
+        try:
+            return float(x)
+        except ValueError:
+            return 0.0
     rows = [r for r in rd if len(r) > i_inst and r[i_line]]
-    tot_i = sum(float(r[i_inst] or 0) for r in rows) or 1
-    tot_s = sum(float(r[i_samp] or 0) for r in rows) or 1
+    tot_i = sum(num(r[i_inst]) for r in rows) or 1
+    tot_s = sum(num(r[i_samp]) for r in rows) or 1
     print("=" * 110)
     print(fn, "|", cur_file.split("/")[-1], "| inst %.3g samples %d" % (tot_i, tot_s))
     for r in rows:
-        pi, ps = float(r[i_inst] or 0) / tot_i * 100, float(r[i_samp] or 0) / tot_s * 100
+        pi, ps = num(r[i_inst]) / tot_i * 100, num(r[i_samp]) / tot_s * 100
         if pi >= minpct or ps >= minpct:
             print("%5s  inst %5.1f%%  samp %5.1f%%  %s" % (r[i_line], pi, ps, r[i_src][:95]))

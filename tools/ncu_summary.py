@@ -43,9 +43,13 @@ def main():
                 print("  %-72s %-10s %s" % (k, units[hdr.index(k)], d[k]))
     txt = run(["-i", rep, "--page", "source", "--csv", "--print-source", "sass"])
     blocks = txt.split('"Kernel Name",')
+    seen = set()
     for blk in blocks[1:]:
         lines = blk.splitlines()
         name = lines[0][:90]
+        if name in seen:
+            continue
+        seen.add(name)
         rows = list(csv.DictReader(lines[1:]))
         if not rows:
             continue
