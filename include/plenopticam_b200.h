@@ -136,6 +136,23 @@ int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C
                            float *out, pcb_minmax_t *mm, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * (c') Sub-pixel "refocus refinement" — replaces refo_from_vp with opt_refi (lfp_refocuser/lfp_shiftandsum.py:93-135)
+ *     and the two misc.img_resize calls per view / per slice (misc/data_proc.py:57-92).
+ *     The up-sample (not-a-knot bicubic) / shift / sum / down-sample chain is linear and separable:
+ *       out[n] = (1/M) * sum_{j,i active}  A_{a_n(c0-j)} . vp[j,i] . B_{a_n(c0-i)}^T
+ *     The band operators are prepared on the host in float64 (plenopticam_b200/lfp_refocuser/refinement.py):
+ *       ay_vals[nsy][ceil(S/4)][Kgy][4], ay_first[nsy][ceil(S/4)]   (groups of 4 output rows share a window)
+ *       bx_vals[nsx][ceil(T/4)][Kgx][4], bx_first[nsx][ceil(T/4)]
+ *       iy[N][M], ix[N][M]: operator index for slice n and view-row j / view-column i
+ *     tmp: float32 scratch (M,S,T,3); out: float32 (N,S,T,3); mm: nullable fused min/max of the stack.
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_refocus_refi(const void *vp, int dtype, int M, int S, int T, int C, int N,
+                     const float *ay_vals, const int32_t *ay_first, int Kgy,
+                     const float *bx_vals, const int32_t *bx_first, int Kgx,
+                     const int32_t *iy, const int32_t *ix, const uint8_t *view_zeroed,
+                     float *tmp, float *out, pcb_minmax_t *mm, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Post-processing of the stack — replaces LfpContrast.auto_hist_align + GammaConverter.srgb_conv as used
  * by LfpRefocuser.shift_and_sum (lfp_refocuser/top_level.py:68-70; lfp_extractor/lfp_contrast.py:249-263;
  * misc/normalizer.py:53-78; misc/gamma_converter.py:32-44).

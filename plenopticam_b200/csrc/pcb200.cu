@@ -4,6 +4,7 @@
 #include "post.cuh"
 #include "refocus.cuh"
 #include "refocus_rows.cuh"
+#include "refine.cuh"
 #include "resample.cuh"
 #include "rotate.cuh"
 #include "viewpoints.cuh"
@@ -219,6 +220,23 @@ int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C
     case PCB_U16: return launch_refocus_int<uint16_t>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st);
     case PCB_F32: return launch_refocus_int<float>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st);
     case PCB_U8:  return launch_refocus_int<uint8_t>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st);
+    }
+    return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
+int pcb_refocus_refi(const void *vp, int dtype, int M, int S, int T, int C, int N, const float *ay_vals,
+                     const int32_t *ay_first, int Kgy, const float *bx_vals, const int32_t *bx_first, int Kgx,
+                     const int32_t *iy, const int32_t *ix, const uint8_t *view_zeroed, float *tmp, float *out,
+                     pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(vp && ay_vals && ay_first && bx_vals && bx_first && iy && ix && view_zeroed && tmp && out, "pointers");
+    PCB_REQUIRE(M > 0 && M <= 127 && M % 2 == 1 && S >= 4 && T >= 4 && N > 0 && Kgy > 0 && Kgx > 0, "sizes, odd M");
+    PCB_REQUIRE(C == 3, "3 colour channels (lfp_shiftandsum.py:97)");
+    PCB_REQUIRE(S <= 65535 * RF_GROUP, "S");
+    cudaStream_t st = as_stream(stream);
+    switch (dtype) {
+    case PCB_U16: return launch_refine<uint16_t>(vp, M, S, T, N, ay_vals, ay_first, Kgy, bx_vals, bx_first, Kgx, iy, ix, view_zeroed, tmp, out, mm, st);
+    case PCB_F32: return launch_refine<float>(vp, M, S, T, N, ay_vals, ay_first, Kgy, bx_vals, bx_first, Kgx, iy, ix, view_zeroed, tmp, out, mm, st);
+    case PCB_U8:  return launch_refine<uint8_t>(vp, M, S, T, N, ay_vals, ay_first, Kgy, bx_vals, bx_first, Kgx, iy, ix, view_zeroed, tmp, out, mm, st);
     }
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
