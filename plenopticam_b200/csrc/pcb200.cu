@@ -4,6 +4,7 @@
 #include "post.cuh"
 #include "refocus.cuh"
 #include "refocus_rows.cuh"
+#include "refocus_px.cuh"
 #include "refine.cuh"
 #include "resample.cuh"
 #include "rotate.cuh"
@@ -151,11 +152,22 @@ int pcb_crop_micro_images(const void *aligned, int dtype, int rows, int cols, in
 }
 
 // Planning shared by pcb_refocus_int_scratch_bytes and pcb_refocus_int (host-only, deterministic).
-static RowsPlan refocus_plan(int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
-                             const uint8_t *view_zeroed_host) {
-    RowsPlan none;
+struct RefocusPlan {
+    PxPlan px;       // uint16 RGB, M <= 16: packed-pixel row-stationary kernel
+    RowsPlan rows;   // uint16, any C, M <= 16: element-pair row-stationary kernel
+};
+
+static int refocus_force_kernel() {   // A/B knob: PCB_REFOCUS_KERNEL=rows|direct (default: best available)
+    const char *e = getenv("PCB_REFOCUS_KERNEL");
+    if (!e) return 0;
+    return !strcmp(e, "rows") ? 1 : (!strcmp(e, "direct") ? 2 : 0);
+}
+
+static RefocusPlan refocus_plan(int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
+                                const uint8_t *view_zeroed_host) {
+    RefocusPlan none;
     memset(&none, 0, sizeof(none));
-    if (dtype != PCB_U16 || M > 16) return none;
+    if (dtype != PCB_U16 || M > 16 || refocus_force_kernel() == 2) return none;
     int max_abs_a = 0;
     for (int n = 0; n < N; ++n) {
         const long long v = a_list_host[n] < 0 ? -(long long)a_list_host[n] : a_list_host[n];
@@ -170,7 +182,10 @@ static RowsPlan refocus_plan(int dtype, int M, int S, int T, int C, const int32_
         tot_act += n;
     }
     if (max_act == 0) return none;
-    return plan_refocus_rows(M, S, T, C, N, max_abs_a, max_act, tot_act);
+    RefocusPlan pl = none;
+    if (C == 3 && refocus_force_kernel() != 1) pl.px = plan_refocus_px(M, S, T, N, max_abs_a, max_act, tot_act, view_zeroed_host);
+    if (!pl.px.ok) pl.rows = plan_refocus_rows(M, S, T, C, N, max_abs_a, max_act, tot_act);
+    return pl;
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -179,8 +194,9 @@ int64_t pcb_refocus_int_scratch_bytes(int dtype, int M, int S, int T, int C, con
                                       const uint8_t *view_zeroed_host) {
     if (a_list_host == nullptr || view_zeroed_host == nullptr || M <= 0 || S <= 0 || T <= 0 || C <= 0 || N <= 0)
         return -1;
-    const RowsPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host);
-    if (pl.ok) return (int64_t)(pl.acc_bytes + pl.edge_bytes);
+    const RefocusPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host);
+    if (pl.px.ok) return (int64_t)pl.px.scratch_bytes();
+    if (pl.rows.ok) return (int64_t)(pl.rows.acc_bytes + pl.rows.edge_bytes);
     return (int64_t)(align256((size_t)N * 4) + align256((size_t)M * M));
 }
 
@@ -194,9 +210,11 @@ int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C, const
     PCB_REQUIRE(scratch_bytes >= pcb_refocus_int_scratch_bytes(dtype, M, S, T, C, a_list_host, N, view_zeroed_host),
                 "scratch_bytes >= pcb_refocus_int_scratch_bytes(...)");
     cudaStream_t st = as_stream(stream);
-    const RowsPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host);
-    if (pl.ok)
-        return launch_refocus_rows(pl, (const uint16_t *)vp, a_list_host, view_zeroed_host, scratch, out, mm, st);
+    const RefocusPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host);
+    if (pl.px.ok)
+        return launch_refocus_px(pl.px, (const uint16_t *)vp, a_list_host, view_zeroed_host, scratch, out, mm, st);
+    if (pl.rows.ok)
+        return launch_refocus_rows(pl.rows, (const uint16_t *)vp, a_list_host, view_zeroed_host, scratch, out, mm, st);
     // direct form: control arrays staged at the head of the scratch buffer
     int32_t *a_dev = reinterpret_cast<int32_t *>(scratch);
     uint8_t *z_dev = reinterpret_cast<uint8_t *>(scratch) + align256((size_t)N * 4);
