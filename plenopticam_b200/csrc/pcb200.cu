@@ -5,6 +5,7 @@
 #include "refocus.cuh"
 #include "refocus_rows.cuh"
 #include "refocus_px.cuh"
+#include "refocus_pxp.cuh"
 #include "refine.cuh"
 #include "resample.cuh"
 #include "rotate.cuh"
@@ -153,6 +154,7 @@ int pcb_crop_micro_images(const void *aligned, int dtype, int rows, int cols, in
 
 // Planning shared by pcb_refocus_int_scratch_bytes and pcb_refocus_int (host-only, deterministic).
 struct RefocusPlan {
+    PxpPlan pxp;     // ... persistent TMA-fed form of it when the whole row and the next tile's raw rows fit one SM
     PxPlan px;       // uint16 RGB, M <= 16: packed-pixel row-stationary kernel
     RowsPlan rows;   // uint16, any C, M <= 16: element-pair row-stationary kernel
 };
@@ -160,11 +162,11 @@ struct RefocusPlan {
 static int refocus_force_kernel() {   // A/B knob: PCB_REFOCUS_KERNEL=rows|direct (default: best available)
     const char *e = getenv("PCB_REFOCUS_KERNEL");
     if (!e) return 0;
-    return !strcmp(e, "rows") ? 1 : (!strcmp(e, "direct") ? 2 : 0);
+    return !strcmp(e, "rows") ? 1 : (!strcmp(e, "direct") ? 2 : (!strcmp(e, "px") ? 3 : 0));
 }
 
 static RefocusPlan refocus_plan(int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
-                                const uint8_t *view_zeroed_host) {
+                                const uint8_t *view_zeroed_host, const void *vp = nullptr) {
     RefocusPlan none;
     memset(&none, 0, sizeof(none));
     if (dtype != PCB_U16 || M > 16 || refocus_force_kernel() == 2) return none;
@@ -184,6 +186,8 @@ static RefocusPlan refocus_plan(int dtype, int M, int S, int T, int C, const int
     if (max_act == 0) return none;
     RefocusPlan pl = none;
     if (C == 3 && refocus_force_kernel() != 1) pl.px = plan_refocus_px(M, S, T, N, max_abs_a, max_act, tot_act, view_zeroed_host);
+    if (pl.px.ok && vp != nullptr && refocus_force_kernel() != 3)
+        pl.pxp = plan_refocus_pxp(pl.px, M, S, T, N, max_abs_a, view_zeroed_host, vp);
     if (!pl.px.ok) pl.rows = plan_refocus_rows(M, S, T, C, N, max_abs_a, max_act, tot_act);
     return pl;
 }
@@ -210,7 +214,9 @@ int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C, const
     PCB_REQUIRE(scratch_bytes >= pcb_refocus_int_scratch_bytes(dtype, M, S, T, C, a_list_host, N, view_zeroed_host),
                 "scratch_bytes >= pcb_refocus_int_scratch_bytes(...)");
     cudaStream_t st = as_stream(stream);
-    const RefocusPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host);
+    const RefocusPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host, vp);
+    if (pl.pxp.ok)
+        return launch_refocus_pxp(pl.px, pl.pxp, (const uint16_t *)vp, a_list_host, view_zeroed_host, scratch, out, mm, st);
     if (pl.px.ok)
         return launch_refocus_px(pl.px, (const uint16_t *)vp, a_list_host, view_zeroed_host, scratch, out, mm, st);
     if (pl.rows.ok)
