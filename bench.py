@@ -336,25 +336,32 @@ def main():
             hb.copy_(r)
             host_ring.append(hb)
         torch.cuda.synchronize()
-        pin_in, pin_out = pipe._staging()
-        Ke = max(3, min(K, 10))
+        Ke = max(4, min(K, 20))
+        DEPTH = 3
+        es = pipe.exposure_stream(depth=DEPTH)
+        s_first, s_last = es.s_in, es.s_out
 
-        def e2e_step(hb):
-            pipe.raw.copy_(hb, non_blocking=True)
-            out = pipe.run_device()
-            pin_out.copy_(out, non_blocking=True)
-            stream.synchronize()
-            return float(pin_out[0, 0, 0, 0])         # touch the result on the host
+        def e2e_run(n, e_b=None, e_e=None):
+            """n exposures through the pipelined host-buffer API; every result is read on the host."""
+            acc = 0.0
+            if e_b is not None:
+                e_b.record(s_first)
+            k0 = es.k
+            for i in range(n):
+                k = es.submit(host_ring[i % 2])
+                if k - k0 >= DEPTH - 1:
+                    acc += float(es.result(k - (DEPTH - 1))[0, 0, 0, 0])
+            for k in range(max(k0, es.k - (DEPTH - 1)), es.k):
+                acc += float(es.result(k)[0, 0, 0, 0])
+            if e_e is not None:
+                e_e.record(s_last)
+            return acc
 
-        for i in range(2):
-            e2e_step(host_ring[i % 2])
+        e2e_run(3)
         barrier()
         t0 = time.perf_counter()
         e_b, e_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e_b.record(stream)
-        for i in range(Ke):
-            e2e_step(host_ring[i % 2])
-        e_e.record(stream)
+        e2e_run(Ke, e_b, e_e)
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         e_ms = max(e_b.elapsed_time(e_e), 0.0)
@@ -365,7 +372,8 @@ def main():
         e2e = {"value": world * Ke * n_slices / (e_ms * 1e-3), "unit": "slices/s",
                "h2d_bytes_per_step": int(pipe.raw.numel() * 2), "d2h_bytes_per_step": int(pipe.stack.numel() * 4),
                "ms_per_step": e_ms / Ke, "wall_ms_per_step": wall_ms / Ke, "steps": Ke,
-               "api": "LightFieldPipeline: pinned raw -> H2D -> align, viewpoints, refocus, post -> D2H sRGB stack"}
+               "api": "LightFieldPipeline.exposure_stream: pinned raw -> H2D | align, viewpoints, refocus, post | D2H sRGB "
+                      "stack, three streams, three exposures in flight; every exposure crosses PCIe both ways inside the timed region"}
 
     if rank != 0:
         if world > 1:

@@ -79,7 +79,8 @@ class LightFieldPipeline(object):
         self.refocus_plan.launch(self.vp, self.stack, self.mm_stack)
         return self.stack
 
-    def post_process(self):
+    def post_process(self, out=None):
+        out = self.post if out is None else out
         L, p, st = nat.lib(), ops._ptr, ops._stream()
         n0 = self.S * self.T * 3
         nat.check(L.pcb_percentile_f32(p(self.stack), n0 // 3, 1, self._q_lo, 1, C.c_void_p(self.lohi.data_ptr()),
@@ -87,16 +88,21 @@ class LightFieldPipeline(object):
         nat.check(L.pcb_percentile_f32(p(self.stack), n0, 0, self._q_hi, 1, C.c_void_p(self.lohi.data_ptr() + 8),
                                        p(self.scratch), st))
         nat.check(L.pcb_contrast_srgb(p(self.stack), self.stack.numel(), p(self.lohi), p(self.mm_stack),
-                                      p(self.post), st))
-        return self.post
+                                      p(out), st))
+        return out
 
-    def run_device(self, raw=None):
+    def run_device(self, raw=None, out=None):
         """All stages on the current stream; returns the final device tensor (sRGB stack, or the linear
         stack if postprocess=False)."""
         self.align(raw)
         self.viewpoints()
         self.refocus()
-        return self.post_process() if self.postprocess else self.stack
+        if self.postprocess:
+            return self.post_process(out)
+        if out is not None:
+            out.copy_(self.stack)
+            return out
+        return self.stack
 
     # -- host-buffer entry point -----------------------------------------------------------------------------
     def _staging(self):
@@ -122,6 +128,10 @@ class LightFieldPipeline(object):
         torch.cuda.current_stream().synchronize()
         return pin_out.numpy()
 
+    def exposure_stream(self, depth=2):
+        """Pipelined host-buffer entry point for a sequence of exposures (see ExposureStream)."""
+        return ExposureStream(self, depth)
+
     # -- byte accounting used by bench.py / DESIGN.md --------------------------------------------------------
     def algorithmic_bytes(self):
         H, W, Cn = self.raw_shape
@@ -136,3 +146,76 @@ class LightFieldPipeline(object):
             "refocus_int": b_vp_active + self.N * b_sl,
             "post": 2 * self.N * b_sl + 2 * 4 * b_sl,
         }
+
+
+class ExposureStream(object):
+    """Host-buffer entry point for a SEQUENCE of exposures of one camera (batch / serving form of `run`).
+
+    Three CUDA streams work on consecutive exposures at the same time: exposure k+1 is copied host->device
+    while exposure k runs through align/viewpoints/refocus/post and the finished stack of exposure k-1 is
+    copied device->host, so the steady-state cost per exposure is the longest of the three instead of their
+    sum.  Every exposure still crosses PCIe in both directions.
+
+        es = pipe.exposure_stream()
+        for raw_pinned in exposures:            # pinned torch tensors (or use es.pinned_input(k))
+            k = es.submit(raw_pinned)
+            if k >= 1: stack = es.result(k - 1)  # numpy view of a pinned buffer, valid until slot reuse
+        stack = es.result(k)
+    """
+
+    def __init__(self, pipe, depth=2):
+        self.pipe = pipe
+        self.depth = int(depth)
+        dev = pipe.device
+        tdt = ops._NP2TORCH[pipe.raw_dtype]
+        with torch.cuda.device(dev):
+            self.raw_dev = [torch.empty(pipe.raw_shape, dtype=tdt, device=dev) for _ in range(self.depth)]
+            self.out_dev = [torch.empty(tuple(pipe.stack.shape), dtype=torch.float32, device=dev)
+                            for _ in range(self.depth)]
+            self.pin_in = [None] * self.depth
+            self.pin_out = [torch.empty(tuple(pipe.stack.shape), dtype=torch.float32, pin_memory=True)
+                            for _ in range(self.depth)]
+            self.s_in = torch.cuda.Stream(device=dev)
+            self.s_out = torch.cuda.Stream(device=dev)
+            self.ev_in = [torch.cuda.Event() for _ in range(self.depth)]      # raw slot filled
+            self.ev_run = [torch.cuda.Event() for _ in range(self.depth)]     # slot consumed / result slot produced
+            self.ev_out = [torch.cuda.Event() for _ in range(self.depth)]     # result slot copied to the host
+        self.k = 0
+
+    def pinned_input(self, k=None):
+        """Pinned host buffer of slot k % depth that the caller may fill directly (numpy view)."""
+        s = (self.k if k is None else k) % self.depth
+        if self.pin_in[s] is None:
+            self.pin_in[s] = torch.empty(self.pipe.raw_shape, dtype=ops._NP2TORCH[self.pipe.raw_dtype], pin_memory=True)
+        t = self.pin_in[s]
+        return t.view(torch.int16).numpy().view(np.uint16) if t.dtype == torch.uint16 else t.numpy()
+
+    def submit(self, raw_pinned=None):
+        """Enqueue one exposure (a pinned host tensor, or the slot's own pinned_input buffer); returns its index."""
+        k, s = self.k, self.k % self.depth
+        src = self.pin_in[s] if raw_pinned is None else raw_pinned
+        cur = torch.cuda.current_stream(self.pipe.device)
+        with torch.cuda.stream(self.s_in):
+            if k >= self.depth:
+                self.s_in.wait_event(self.ev_run[s])          # the kernels of exposure k-depth have read this slot
+            self.raw_dev[s].copy_(src, non_blocking=True)
+            self.ev_in[s].record(self.s_in)
+        cur.wait_event(self.ev_in[s])
+        if k >= self.depth:
+            cur.wait_event(self.ev_out[s])                    # result slot has left for the host
+        self.pipe.run_device(self.raw_dev[s], out=self.out_dev[s])
+        self.ev_run[s].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_run[s])
+            self.pin_out[s].copy_(self.out_dev[s], non_blocking=True)
+            self.ev_out[s].record(self.s_out)
+        self.k += 1
+        return k
+
+    def result(self, k):
+        """Block until exposure k has arrived on the host; numpy view valid until slot k % depth is resubmitted."""
+        if not (self.k - self.depth <= k < self.k):
+            raise IndexError("result %d is not in flight" % k)
+        s = k % self.depth
+        self.ev_out[s].synchronize()
+        return self.pin_out[s].numpy()

@@ -307,3 +307,69 @@ def test_refocus_rows_custom_mask_and_mono_fallback(cuda):
     got = ops.to_host(ops.refocus_int(ops.to_device(vpf), a_list))
     ref = np.asarray([onp.refocus_int_slice(onp._apply_aperture(vpf, M) / M, a, M) for a in a_list])
     assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("kernel", ["", "px", "rows", "direct"])
+@pytest.mark.parametrize("mask_kind", ["circle", "contiguous_asymmetric"])
+def test_refocus_kernel_variants_agree(cuda, kernel, mask_kind, monkeypatch):
+    """Persistent packed-pixel (default), chunked packed-pixel, element-pair rows and direct kernels are all
+    exact; a contiguous but off-centre run of views takes the packed-pixel kernels without centre-view reuse."""
+    from plenopticam_b200 import ops
+    rng = np.random.default_rng(21)
+    M, S, T = 11, 29, 83
+    vp = rng.integers(0, 65536, size=(M, M, S, T, 3), dtype=np.uint16)
+    vp[:, :, :, :, 1] |= 0xfff0                     # large values: 21-bit fields close to their limit
+    if mask_kind == "circle":
+        mask = ops.aperture_mask(M)
+    else:
+        mask = np.ones((M, M), dtype=bool)
+        for j in range(M):
+            lo = (3 * j) % 5
+            mask[j, lo:lo + 2 + (j % 6)] = False    # one run per row, not centred; row widths 2..7
+        mask[4, :] = True                           # a fully masked view row
+    a_list = [-9, -2, 0, 1, 4, 17]
+    if kernel:
+        monkeypatch.setenv("PCB_REFOCUS_KERNEL", kernel)
+    else:
+        monkeypatch.delenv("PCB_REFOCUS_KERNEL", raising=False)
+    mm = ops.new_minmax()
+    got = ops.to_host(ops.refocus_int(ops.to_device(vp), a_list, view_zeroed=mask, mm=mm))
+    c = M // 2
+    vp64 = vp.astype(np.float64)
+    for k, a in enumerate(a_list):
+        ref = np.zeros((S, T, 3))
+        for j in range(M):
+            for i in range(M):
+                if mask[j, i]:
+                    continue
+                yi = np.clip(np.arange(S) + a * (c - j), 0, S - 1)
+                xi = np.clip(np.arange(T) + a * (c - i), 0, T - 1)
+                ref += vp64[j, i][yi][:, xi]
+        assert np.array_equal(got[k], (ref / M).astype(np.float32)), (kernel, a)
+    mn, mx = ops.minmax_values(mm)
+    assert mn == got.min() and mx == got.max()
+
+
+def test_exposure_stream_matches_single_runs(cuda):
+    """Pipelined host-buffer entry point (three streams) returns exactly what run() returns, in order."""
+    import torch
+    from plenopticam_b200.pipeline import LightFieldPipeline
+    LY, LX, M = 20, 26, 9
+    cent = onp.synth_centroids(LY, LX, 11.0, 'hex', hex_odd=True, jitter=0.1, origin=(7.5, 7.5), seed=2)
+    H, W = int(cent[:, 0].max() + 9), int(cent[:, 1].max() + 9)
+    pipe = LightFieldPipeline(cent, (H, W, 3), np.uint16, M, 'hex', ran_refo=(-3, 4))
+    raws = [onp.synth_raw(H, W, 3, seed=s) for s in range(5)]
+    singles = [pipe.run(r).copy() for r in raws]
+    es = pipe.exposure_stream(depth=2)
+    outs = {}
+    for k, r in enumerate(raws):
+        es.pinned_input(k)[...] = r
+        assert es.submit() == k
+        if k >= 1:
+            outs[k - 1] = es.result(k - 1).copy()
+    outs[len(raws) - 1] = es.result(len(raws) - 1).copy()
+    with pytest.raises(IndexError):
+        es.result(0)
+    for k in range(len(raws)):
+        assert np.array_equal(outs[k], singles[k]), k
+    assert torch.cuda.is_available()
