@@ -139,17 +139,31 @@ int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C
  * (c') Sub-pixel "refocus refinement" — replaces refo_from_vp with opt_refi (lfp_refocuser/lfp_shiftandsum.py:93-135)
  *     and the two misc.img_resize calls per view / per slice (misc/data_proc.py:57-92).
  *     The up-sample (not-a-knot bicubic) / shift / sum / down-sample chain is linear and separable:
- *       out[n] = (1/M) * sum_{j,i active}  A_{a_n(c0-j)} . vp[j,i] . B_{a_n(c0-i)}^T
- *     The band operators are prepared on the host in float64 (plenopticam_b200/lfp_refocuser/refinement.py):
- *       ay_vals[nsy][ceil(S/4)][Kgy][4], ay_first[nsy][ceil(S/4)]   (groups of 4 output rows share a window)
- *       bx_vals[nsx][ceil(T/4)][Kgx][4], bx_first[nsx][ceil(T/4)]
- *       iy[N][M], ix[N][M]: operator index for slice n and view-row j / view-column i
- *     tmp: float32 scratch (M,S,T,3); out: float32 (N,S,T,3); mm: nullable fused min/max of the stack.
+ *       out[n] = (1/M) * sum_{j,i active}  A_{a_n(c0-j)} . vp[j,i] . B_{a_n(c0-i)}^T ,     A_s = D_s . P
+ *     P (samples -> cubic B-spline coefficients) is independent of the slice, D_s is a band of <= 5 taps.  All
+ *     operators are prepared on the host in float64 (plenopticam_b200/lfp_refocuser/refinement.py).
+ *   pcb_refi_prefilter : once per light field, coef[j,i] = Py . vp[j,i] . Px^T for every unmasked view
+ *       py_vals[S][Kpy], py_first[S];  px_vals[Kpx][T], px_first[T];  view_zeroed[M*M] (device)
+ *       tmp, coef: float32 (M,M,S,T,3)
+ *   pcb_refocus_refi   : a batch of N slices from the coefficients
+ *       dy_vals[nsy][ceil(S/4)][Kgy][4], dy_first[nsy][ceil(S/4)]  (groups of 4 output rows share a window)
+ *       dx_vals[nsx][Kx][T], dx_first[nsx][T]
+ *       iy[N][M], ix[N][M]: operator index for slice n and view-row j / view-column i (device)
+ *       xlo_host[M], xhi_host[M]: per view column, smallest / largest coefficient offset relative to the output
+ *                                 pixel that any slice of the batch reads (sizes the shared-memory windows)
+ *       view_zeroed_host / view_zeroed: the M*M mask on the host and on the device
+ *       tmp: float32 scratch (N,M,S,T,3); out: float32 (N,S,T,3); mm: nullable fused min/max of the stack.
  * ------------------------------------------------------------------------------------------------ */
-int pcb_refocus_refi(const void *vp, int dtype, int M, int S, int T, int C, int N,
-                     const float *ay_vals, const int32_t *ay_first, int Kgy,
-                     const float *bx_vals, const int32_t *bx_first, int Kgx,
-                     const int32_t *iy, const int32_t *ix, const uint8_t *view_zeroed,
+int pcb_refi_prefilter(const void *vp, int dtype, int M, int S, int T, int C,
+                       const float *py_vals, const int32_t *py_first, int Kpy,
+                       const float *px_vals, const int32_t *px_first, int Kpx,
+                       const uint8_t *view_zeroed, float *tmp, float *coef, void *stream);
+int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N,
+                     const float *dy_vals, const int32_t *dy_first, int Kgy,
+                     const float *dx_vals, const int32_t *dx_first, int Kx,
+                     const int32_t *iy, const int32_t *ix,
+                     const int32_t *xlo_host, const int32_t *xhi_host,
+                     const uint8_t *view_zeroed_host, const uint8_t *view_zeroed,
                      float *tmp, float *out, pcb_minmax_t *mm, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -88,7 +88,9 @@ _SIGNATURES = {
     "pcb_refocus_int_scratch_bytes": (_i64, [_i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pcb_refocus_int": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "pcb_refocus_int_direct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
-    "pcb_refocus_refi": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcb_refi_prefilter": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "pcb_refocus_refi": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _vp, _vp]),
     "pcb_percentile_scratch_bytes": (_i64, []),
     "pcb_percentile_f32": (_i, [_vp, _i64, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
     "pcb_contrast_srgb": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),

@@ -248,21 +248,34 @@ int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
 
-int pcb_refocus_refi(const void *vp, int dtype, int M, int S, int T, int C, int N, const float *ay_vals,
-                     const int32_t *ay_first, int Kgy, const float *bx_vals, const int32_t *bx_first, int Kgx,
-                     const int32_t *iy, const int32_t *ix, const uint8_t *view_zeroed, float *tmp, float *out,
-                     pcb_minmax_t *mm, void *stream) {
-    PCB_REQUIRE(vp && ay_vals && ay_first && bx_vals && bx_first && iy && ix && view_zeroed && tmp && out, "pointers");
-    PCB_REQUIRE(M > 0 && M <= 127 && M % 2 == 1 && S >= 4 && T >= 4 && N > 0 && Kgy > 0 && Kgx > 0, "sizes, odd M");
+int pcb_refi_prefilter(const void *vp, int dtype, int M, int S, int T, int C, const float *py_vals,
+                       const int32_t *py_first, int Kpy, const float *px_vals, const int32_t *px_first, int Kpx,
+                       const uint8_t *view_zeroed, float *tmp, float *coef, void *stream) {
+    PCB_REQUIRE(vp && py_vals && py_first && px_vals && px_first && view_zeroed && tmp && coef, "pointers");
+    PCB_REQUIRE(M > 0 && M * M <= 65535 && S >= 4 && T >= 4 && S <= 65535 && Kpy > 0 && Kpx > 0, "sizes");
     PCB_REQUIRE(C == 3, "3 colour channels (lfp_shiftandsum.py:97)");
-    PCB_REQUIRE(S <= 65535 * RF_GROUP, "S");
     cudaStream_t st = as_stream(stream);
     switch (dtype) {
-    case PCB_U16: return launch_refine<uint16_t>(vp, M, S, T, N, ay_vals, ay_first, Kgy, bx_vals, bx_first, Kgx, iy, ix, view_zeroed, tmp, out, mm, st);
-    case PCB_F32: return launch_refine<float>(vp, M, S, T, N, ay_vals, ay_first, Kgy, bx_vals, bx_first, Kgx, iy, ix, view_zeroed, tmp, out, mm, st);
-    case PCB_U8:  return launch_refine<uint8_t>(vp, M, S, T, N, ay_vals, ay_first, Kgy, bx_vals, bx_first, Kgx, iy, ix, view_zeroed, tmp, out, mm, st);
+    case PCB_U16: return launch_refi_prefilter<uint16_t>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st);
+    case PCB_F32: return launch_refi_prefilter<float>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st);
+    case PCB_U8:  return launch_refi_prefilter<uint8_t>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st);
     }
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
+int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N, const float *dy_vals,
+                     const int32_t *dy_first, int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx,
+                     const int32_t *iy, const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
+                     const uint8_t *view_zeroed_host, const uint8_t *view_zeroed, float *tmp, float *out,
+                     pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(coef && dy_vals && dy_first && dx_vals && dx_first && iy && ix && xlo_host && xhi_host &&
+                view_zeroed_host && view_zeroed && tmp && out, "pointers");
+    PCB_REQUIRE(M > 0 && M <= RF_MAXM && M % 2 == 1 && S >= 4 && T >= 4 && N > 0 && N <= 65535 && Kgy > 0 && Kx > 0,
+                "sizes, odd M <= 32");
+    PCB_REQUIRE(C == 3, "3 colour channels (lfp_shiftandsum.py:97)");
+    PCB_REQUIRE((S + RH_ROWS - 1) / RH_ROWS <= 65535, "S");
+    return launch_refine(coef, M, S, T, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host, xhi_host,
+                         view_zeroed_host, tmp, out, mm, as_stream(stream));
 }
 
 int64_t pcb_percentile_scratch_bytes(void) { return (int64_t)sizeof(SelectState); }

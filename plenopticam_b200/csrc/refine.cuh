@@ -2,102 +2,182 @@
 // lfp_refocuser/lfp_shiftandsum.py:93-135 + misc/data_proc.py:57-92.
 //
 // The chain is linear and separable (see lfp_refocuser/refinement.py):
-//     R_a = (1/M) * sum_{j,i active}  A_{a(c-j)} . V_ji . B_{a(c-i)}^T
-// with A_s, B_s narrow-band operators prepared on the host in float64.  Per slice two banded passes:
-//   horizontal  H[j][r][x][c] = sum_{i active} sum_m  Bx[ix[i]][g(x)][m][q(x)] * vp[j,i,r, first+m, c]
-//   vertical    out[y][x][c]  = (1/M) sum_{j active} sum_m  Ay[iy[j]][g(y)][m][q(y)] * H[j][first+m][x][c]
-// Outputs come in groups of 4 that share one sample window, so each loaded sample feeds 4 outputs x 3 channels
-// (12 FMAs per 3 shared-memory loads + one 16-byte weight load).
+//     R_a = (1/M) * sum_{j,i active}  A_{a(c-j)} . V_ji . B_{a(c-i)}^T ,      A_s = D_s . P
+// P (samples -> cubic B-spline coefficients, ~29 taps) does not depend on the slice; D_s is a band of <= 5 taps.
+//
+//   once per light field   coef[j,i] = Py . V_ji . Px^T                            (refi_prefilter_{x,y}_kernel)
+//   per batch of slices    H[n][j][r][x]  = sum_{i active} sum_m Dx[s(n,i)][m][x] * coef[j,i][r][fx+m]   (refine_h_kernel)
+//                          out[n][y][x]   = (1/M) sum_{j active} sum_m Dy[s(n,j)][g(y)][m][q(y)] * H[n][j][fy+m][x]
+//
+// refine_h_kernel is where the work is (177 views x K taps per output and slice).  One CTA owns view-row j, RH_ROWS
+// image rows and a chunk of RH_XC pixels; it stages, once, the coefficient windows every slice of the batch can
+// reach (per view: chunk + the offsets its own shifts produce) and then walks all slices.  Lanes run along x, so
+// the K weights + window start of a thread are coalesced loads, fetched once per (slice, view) and used for all
+// RH_ROWS rows from registers; the samples come from shared memory at a 3-word lane stride (conflict free).
 #pragma once
 #include "common.cuh"
 
 namespace pcb {
 
 constexpr int RF_GROUP = 4;
-constexpr int RFH_THREADS = 160;
+constexpr int RF_MAXM = 32;          // view columns per row supported by the control block
 
-// grid (S, M): one CTA per (image row r, view-row j); thread = one group of 4 output pixels, all 3 channels.
+// ---- prefilter -------------------------------------------------------------------------------------------------
+constexpr int RP_THREADS = 320;
+
+// grid (S, M*M): one CTA per (image row r, view); tmp[view][r][x][c] = sum_m px[m][x] * V[view][r][pf[x]+m][c]
 template <typename TIn>
-__global__ void __launch_bounds__(RFH_THREADS)
-refine_rows_kernel(const TIn *__restrict__ vp, int M, int S, int T, const float *__restrict__ bx_vals,
-                   const int32_t *__restrict__ bx_first, int Kg, const int32_t *__restrict__ ix_n,
-                   const uint8_t *__restrict__ view_zeroed, float *__restrict__ H) {
-    extern __shared__ __align__(16) float s_rows[];      // [nact][T*3]
-    __shared__ int s_act[128];
-    __shared__ int s_nact;
-    const int r = blockIdx.x, j = blockIdx.y;
+__global__ void __launch_bounds__(RP_THREADS)
+refi_prefilter_x_kernel(const TIn *__restrict__ vp, int S, int T, const float *__restrict__ px_vals,
+                        const int32_t *__restrict__ px_first, int Kp, const uint8_t *__restrict__ view_zeroed,
+                        float *__restrict__ tmp) {
+    extern __shared__ __align__(16) float s_row[];        // [T*3]
+    const int r = blockIdx.x, view = blockIdx.y;
+    if (view_zeroed[view]) return;
     const int E = T * 3;
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int i = 0; i < M; ++i)
-            if (!view_zeroed[j * M + i]) s_act[n++] = i;
-        s_nact = n;
-    }
+    const TIn *src = vp + ((size_t)view * S + r) * E;
+    for (int e = threadIdx.x; e < E; e += RP_THREADS) s_row[e] = ld_as_float(src + e);
     __syncthreads();
-    const int nact = s_nact;
-    if (nact == 0) return;
-    for (int ii = 0; ii < nact; ++ii) {
-        const TIn *src = vp + ((size_t)(j * M + s_act[ii]) * S + r) * E;
-        float *dst = s_rows + (size_t)ii * E;
-        for (int e = threadIdx.x; e < E; e += RFH_THREADS) dst[e] = ld_as_float(src + e);
-    }
-    __syncthreads();
-
-    const int G = (T + RF_GROUP - 1) / RF_GROUP;
-    for (int g = threadIdx.x; g < G; g += RFH_THREADS) {
-        float acc[RF_GROUP][3];
-#pragma unroll
-        for (int q = 0; q < RF_GROUP; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
-        for (int ii = 0; ii < nact; ++ii) {
-            const int sidx = ix_n[s_act[ii]];
-            const int f = bx_first[(size_t)sidx * G + g];
-            const float4 *w = reinterpret_cast<const float4 *>(bx_vals) + ((size_t)sidx * G + g) * Kg;
-            const float *row = s_rows + (size_t)ii * E;
+    float *dst = tmp + ((size_t)view * S + r) * E;
+    for (int x = threadIdx.x; x < T; x += RP_THREADS) {
+        const float *px = s_row + px_first[x] * 3;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 4
-            for (int m = 0; m < Kg; ++m) {
-                const float4 w4 = __ldg(w + m);
-                const float *px = row + min(f + m, T - 1) * 3;
-                const float v0 = px[0], v1 = px[1], v2 = px[2];
-                acc[0][0] = fmaf(w4.x, v0, acc[0][0]); acc[0][1] = fmaf(w4.x, v1, acc[0][1]); acc[0][2] = fmaf(w4.x, v2, acc[0][2]);
-                acc[1][0] = fmaf(w4.y, v0, acc[1][0]); acc[1][1] = fmaf(w4.y, v1, acc[1][1]); acc[1][2] = fmaf(w4.y, v2, acc[1][2]);
-                acc[2][0] = fmaf(w4.z, v0, acc[2][0]); acc[2][1] = fmaf(w4.z, v1, acc[2][1]); acc[2][2] = fmaf(w4.z, v2, acc[2][2]);
-                acc[3][0] = fmaf(w4.w, v0, acc[3][0]); acc[3][1] = fmaf(w4.w, v1, acc[3][1]); acc[3][2] = fmaf(w4.w, v2, acc[3][2]);
+        for (int m = 0; m < Kp; ++m) {
+            const float w = __ldg(px_vals + (size_t)m * T + x);
+            a0 = fmaf(w, px[m * 3 + 0], a0);
+            a1 = fmaf(w, px[m * 3 + 1], a1);
+            a2 = fmaf(w, px[m * 3 + 2], a2);
+        }
+        dst[x * 3 + 0] = a0; dst[x * 3 + 1] = a1; dst[x * 3 + 2] = a2;
+    }
+}
+
+// grid (ceil(E/256), S, M*M): coef[view][y][e] = sum_m py[y][m] * tmp[view][pf[y]+m][e]
+__global__ void __launch_bounds__(256)
+refi_prefilter_y_kernel(const float *__restrict__ tmp, int S, int E, const float *__restrict__ py_vals,
+                        const int32_t *__restrict__ py_first, int Kp, const uint8_t *__restrict__ view_zeroed,
+                        float *__restrict__ coef) {
+    const int y = blockIdx.y, view = blockIdx.z;
+    if (view_zeroed[view]) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const float *w = py_vals + (size_t)y * Kp;                        // uniform over the CTA
+    const float *col = tmp + ((size_t)view * S + py_first[y]) * E + e;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int m = 0; m < Kp; ++m) acc = fmaf(__ldg(w + m), __ldg(col + (size_t)m * E), acc);
+    coef[((size_t)view * S + y) * E + e] = acc;
+}
+
+// ---- horizontal pass ---------------------------------------------------------------------------------------------
+constexpr int RH_XC = 160;           // output pixels (= threads) per CTA
+constexpr int RH_ROWS = 3;           // image rows per CTA: the weights of a thread are reused for all of them
+
+struct RefineHCtl {                  // per-launch control block, passed by value
+    int32_t lo[RF_MAXM];             // per view column: smallest / largest coefficient offset (relative to the output
+    int32_t hi[RF_MAXM];             //   pixel) any slice of the batch reads
+    uint32_t active[RF_MAXM];        // bit i of active[j]: view (j, i) is not masked
+};
+
+template <int K>
+__global__ void __launch_bounds__(RH_XC)
+refine_h_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, const float *__restrict__ dx_vals,
+                const int32_t *__restrict__ dx_first, const int32_t *__restrict__ ix, RefineHCtl ctl,
+                float *__restrict__ H) {
+    extern __shared__ __align__(16) float s_win[];         // [view][row][width_i * 3]
+    __shared__ int s_off[RF_MAXM];                         // float offset of view i's block in s_win
+    __shared__ int s_x0[RF_MAXM];                          // first staged pixel of view i
+    const int j = blockIdx.z;
+    const int r0 = blockIdx.y * RH_ROWS;
+    const int xc0 = blockIdx.x * RH_XC;
+    const int tid = threadIdx.x;
+    const uint32_t act = ctl.active[j];
+    if (act == 0u) return;
+    const int nrow = min(RH_ROWS, S - r0);
+    const int xcn = min(RH_XC, T - xc0);
+
+    if (tid == 0) {
+        int off = 0;
+        for (int i = 0; i < M; ++i) {
+            const int a = max(xc0 + ctl.lo[i], 0), b = min(xc0 + xcn - 1 + ctl.hi[i], T - 1);
+            s_x0[i] = a;
+            s_off[i] = off;
+            if ((act >> i) & 1u) off += (b - a + 1) * 3 * RH_ROWS;
+        }
+    }
+    __syncthreads();
+    // ---- stage the coefficient windows (rows beyond S replicate nothing: they are never read)
+    for (int i = 0; i < M; ++i) {
+        if (!((act >> i) & 1u)) continue;
+        const int a = s_x0[i];
+        const int wE = (min(xc0 + xcn - 1 + ctl.hi[i], T - 1) - a + 1) * 3;
+        float *dst = s_win + s_off[i];
+        for (int rr = 0; rr < nrow; ++rr) {
+            const float *src = coef + (((size_t)(j * M + i) * S + r0 + rr) * T + a) * 3;
+            for (int e = tid; e < wE; e += RH_XC) dst[rr * wE + e] = __ldg(src + e);
+        }
+    }
+    __syncthreads();
+    if (tid >= xcn) return;
+    const int x = xc0 + tid;
+
+    for (int n = 0; n < nb; ++n) {
+        float acc[RH_ROWS][3];
+#pragma unroll
+        for (int rr = 0; rr < RH_ROWS; ++rr) acc[rr][0] = acc[rr][1] = acc[rr][2] = 0.f;
+        const int32_t *ixn = ix + (size_t)n * M;
+        for (int i = 0; i < M; ++i) {
+            if (!((act >> i) & 1u)) continue;
+            const int sidx = __ldg(ixn + i);                               // uniform
+            const int f = __ldg(dx_first + (size_t)sidx * T + x);
+            float w[K];
+#pragma unroll
+            for (int m = 0; m < K; ++m) w[m] = __ldg(dx_vals + ((size_t)sidx * K + m) * T + x);
+            const int a = s_x0[i];
+            const int wE = (min(xc0 + xcn - 1 + ctl.hi[i], T - 1) - a + 1) * 3;
+            const float *px = s_win + s_off[i] + (f - a) * 3;
+#pragma unroll
+            for (int rr = 0; rr < RH_ROWS; ++rr) {
+#pragma unroll
+                for (int m = 0; m < K; ++m) {
+                    acc[rr][0] = fmaf(w[m], px[rr * wE + m * 3 + 0], acc[rr][0]);
+                    acc[rr][1] = fmaf(w[m], px[rr * wE + m * 3 + 1], acc[rr][1]);
+                    acc[rr][2] = fmaf(w[m], px[rr * wE + m * 3 + 2], acc[rr][2]);
+                }
             }
         }
-        float *out = H + ((size_t)j * S + r) * E;
 #pragma unroll
-        for (int q = 0; q < RF_GROUP; ++q) {
-            const int x = g * RF_GROUP + q;
-            if (x < T) { out[x * 3 + 0] = acc[q][0]; out[x * 3 + 1] = acc[q][1]; out[x * 3 + 2] = acc[q][2]; }
+        for (int rr = 0; rr < RH_ROWS; ++rr) {
+            if (rr < nrow) {
+                float *o = H + ((((size_t)n * M + j) * S + r0 + rr) * T + x) * 3;
+                o[0] = acc[rr][0]; o[1] = acc[rr][1]; o[2] = acc[rr][2];
+            }
         }
     }
 }
 
-// grid (Gy, ceil(E/256)): thread = one (x, c) element of a group of 4 output rows.
+// ---- vertical pass -----------------------------------------------------------------------------------------------
+// grid (Gy, ceil(E/256), nb): thread = one (x, c) element of a group of 4 output rows of slice n.
 __global__ void __launch_bounds__(256)
-refine_cols_kernel(const float *__restrict__ H, int M, int S, int E, const float *__restrict__ ay_vals,
-                   const int32_t *__restrict__ ay_first, int Kg, const int32_t *__restrict__ iy_n,
-                   const uint8_t *__restrict__ view_zeroed, float *__restrict__ out_n, pcb_minmax_t *mm) {
-    __shared__ int s_rowact[128];
+refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *__restrict__ dy_vals,
+                const int32_t *__restrict__ dy_first, int Kg, const int32_t *__restrict__ iy, RefineHCtl ctl,
+                float *__restrict__ out, pcb_minmax_t *mm) {
     const int gy = blockIdx.x;
     const int Gy = gridDim.x;
+    const int n = blockIdx.z;
     const int e = blockIdx.y * blockDim.x + threadIdx.x;
-    for (int j = threadIdx.x; j < M; j += blockDim.x) {
-        int any = 0;
-        for (int i = 0; i < M; ++i) any |= !view_zeroed[j * M + i];
-        s_rowact[j] = any;
-    }
-    __syncthreads();
+    const int32_t *iy_n = iy + (size_t)n * M;
     float mn = INFINITY, mx = -INFINITY;
     if (e < E) {
         float acc[RF_GROUP] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < M; ++j) {
-            if (!s_rowact[j]) continue;
-            const int sidx = iy_n[j];
-            const int f = ay_first[(size_t)sidx * Gy + gy];
-            const float4 *w = reinterpret_cast<const float4 *>(ay_vals) + ((size_t)sidx * Gy + gy) * Kg;
-            const float *col = H + (size_t)j * S * E + e;
-#pragma unroll 4
+            if (ctl.active[j] == 0u) continue;
+            const int sidx = __ldg(iy_n + j);
+            const int f = __ldg(dy_first + (size_t)sidx * Gy + gy);
+            const float4 *w = reinterpret_cast<const float4 *>(dy_vals) + ((size_t)sidx * Gy + gy) * Kg;
+            const float *col = H + (((size_t)n * M + j) * S) * E + e;
+#pragma unroll 3
             for (int m = 0; m < Kg; ++m) {
                 const float4 w4 = __ldg(w + m);                      // same address for the whole CTA: broadcast
                 const float v = __ldg(col + (size_t)min(f + m, S - 1) * E);
@@ -108,6 +188,7 @@ refine_cols_kernel(const float *__restrict__ H, int M, int S, int E, const float
             }
         }
         const float invM = 1.0f / (float)M;
+        float *out_n = out + (size_t)n * S * E;
 #pragma unroll
         for (int q = 0; q < RF_GROUP; ++q) {
             const int y = gy * RF_GROUP + q;
@@ -122,25 +203,75 @@ refine_cols_kernel(const float *__restrict__ H, int M, int S, int E, const float
     if (mm != nullptr) block_minmax_commit(mn, mx, mm);
 }
 
+// ---- launchers ---------------------------------------------------------------------------------------------------
 template <typename TIn>
-static int launch_refine(const void *vp, int M, int S, int T, int N, const float *ay_vals, const int32_t *ay_first,
-                         int Kgy, const float *bx_vals, const int32_t *bx_first, int Kgx, const int32_t *iy,
-                         const int32_t *ix, const uint8_t *view_zeroed, float *tmp, float *out, pcb_minmax_t *mm,
-                         cudaStream_t st) {
+static int launch_refi_prefilter(const void *vp, int M, int S, int T, const float *py_vals, const int32_t *py_first,
+                                 int Kpy, const float *px_vals, const int32_t *px_first, int Kpx,
+                                 const uint8_t *view_zeroed, float *tmp, float *coef, cudaStream_t st) {
     const int E = T * 3;
-    const size_t smem = (size_t)M * E * sizeof(float);
-    if (smem > 200 * 1024) return fail(PCB_ERR_UNSUPPORTED, "%s: view rows do not fit shared memory", "pcb_refocus_refi");
-    PCB_CUDA(cudaFuncSetAttribute(refine_rows_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int Gy = (S + RF_GROUP - 1) / RF_GROUP;
-    for (int n = 0; n < N; ++n) {
-        refine_rows_kernel<TIn><<<dim3(S, M), RFH_THREADS, smem, st>>>((const TIn *)vp, M, S, T, bx_vals, bx_first, Kgx,
-                                                                      ix + (size_t)n * M, view_zeroed, tmp);
-        PCB_LAUNCH_OK();
-        refine_cols_kernel<<<dim3(Gy, (E + 255) / 256), 256, 0, st>>>(tmp, M, S, E, ay_vals, ay_first, Kgy,
-                                                                     iy + (size_t)n * M, view_zeroed,
-                                                                     out + (size_t)n * S * E, mm);
-        PCB_LAUNCH_OK();
+    const size_t smem = (size_t)E * sizeof(float);
+    if (smem > 200 * 1024) return fail(PCB_ERR_UNSUPPORTED, "%s: image row does not fit shared memory", "pcb_refi_prefilter");
+    PCB_CUDA(cudaFuncSetAttribute(refi_prefilter_x_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    refi_prefilter_x_kernel<TIn><<<dim3(S, M * M), RP_THREADS, smem, st>>>((const TIn *)vp, S, T, px_vals, px_first, Kpx,
+                                                                         view_zeroed, tmp);
+    PCB_LAUNCH_OK();
+    refi_prefilter_y_kernel<<<dim3((E + 255) / 256, S, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
+                                                                           view_zeroed, coef);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+template <int K>
+static int launch_refine_h(const float *coef, int M, int S, int T, int nb, const float *dx_vals, const int32_t *dx_first,
+                           const int32_t *ix, const RefineHCtl &ctl, size_t smem, float *H, cudaStream_t st) {
+    PCB_CUDA(cudaFuncSetAttribute(refine_h_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((T + RH_XC - 1) / RH_XC, (S + RH_ROWS - 1) / RH_ROWS, M);
+    refine_h_kernel<K><<<grid, RH_XC, smem, st>>>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, H);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+static int launch_refine(const float *coef, int M, int S, int T, int nb, const float *dy_vals, const int32_t *dy_first,
+                         int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx, const int32_t *iy,
+                         const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
+                         const uint8_t *view_zeroed_host, float *H, float *out, pcb_minmax_t *mm, cudaStream_t st) {
+    const int E = T * 3;
+    RefineHCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    size_t max_px = 0;
+    for (int j = 0; j < M; ++j) {
+        size_t px = 0;
+        for (int i = 0; i < M; ++i) {
+            if (view_zeroed_host[j * M + i]) continue;
+            ctl.active[j] |= 1u << i;
+            px += (size_t)RH_XC + (size_t)(xhi_host[i] - xlo_host[i]);
+        }
+        if (px > max_px) max_px = px;
     }
+    for (int i = 0; i < M; ++i) { ctl.lo[i] = xlo_host[i]; ctl.hi[i] = xhi_host[i]; }
+    const size_t smem = max_px * 3 * RH_ROWS * sizeof(float);
+    if (smem > 220 * 1024)
+        return fail(PCB_ERR_UNSUPPORTED, "%s: coefficient windows of one view row do not fit shared memory", "pcb_refocus_refi");
+    int rc;
+    switch (Kx) {
+    case 1: rc = launch_refine_h<1>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 2: rc = launch_refine_h<2>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 3: rc = launch_refine_h<3>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 4: rc = launch_refine_h<4>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 5: rc = launch_refine_h<5>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 6: rc = launch_refine_h<6>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 7: rc = launch_refine_h<7>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 8: rc = launch_refine_h<8>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 9: rc = launch_refine_h<9>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 10: rc = launch_refine_h<10>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 11: rc = launch_refine_h<11>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    case 12: rc = launch_refine_h<12>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, smem, H, st); break;
+    default: return fail(PCB_ERR_UNSUPPORTED, "%s: band of %lld taps (1..12 supported)", "pcb_refocus_refi", Kx);
+    }
+    if (rc) return rc;
+    const int Gy = (S + RF_GROUP - 1) / RF_GROUP;
+    refine_v_kernel<<<dim3(Gy, (E + 255) / 256, nb), 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, Kgy, iy, ctl, out, mm);
+    PCB_LAUNCH_OK();
     return PCB_OK;
 }
 

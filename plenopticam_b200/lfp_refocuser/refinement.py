@@ -9,10 +9,17 @@ FITPACK's interpolating spline = a separable not-a-knot cubic spline, so the who
     A_s = Wdn_y . Shift_s . Wup_y   (S x S),      B_s = Wdn_x . Shift_s . Wup_x   (T x T)
 
 with Wup (n*M x n) / Wdn (n x n*M) the spline sampling matrices and Shift_s the clamped row selection
-`X[clamp(Y + s)]`.  The operators are narrow bands around the shifted diagonal (spline cardinal functions decay
-by 0.268 per sample): they are built here ONCE per (n, M, set of shifts) in float64 with sparse algebra and
-truncated at 1e-9, and the device evaluates two banded passes (csrc/refine.cuh).  Nothing of size (S*M x T*M) is
-ever materialised (the reference's 6510 x 9375 x 3 float64 intermediates per view).
+`X[clamp(Y + s)]`.  The long tails of A_s come from ONE factor only: Wup = Ev . P, where P = colloc^-1 turns
+samples into B-spline coefficients (an IIR-like prefilter whose rows decay by 0.268 per sample) and Ev evaluates
+four basis functions per up-sampled point.  P does not depend on the shift, so
+
+    A_s = D_s . P,     D_s = Wdn . Shift_s . Ev        (<= 5 taps at 1e-8: a down-sampled shifted spline is again
+                                                         almost exactly a spline on the coarse knots)
+
+and the device work splits into a prefilter of every view, done ONCE per light field (both axes), and two
+narrow banded passes per slice (csrc/refine.cuh).  All operators are built here in float64 with sparse algebra
+and truncated at BAND_EPS; nothing of size (S*M x T*M) is ever materialised (the reference's 6510 x 9375 x 3
+float64 intermediates per view and slice).
 """
 import numpy as np
 import scipy.sparse as sp
@@ -20,19 +27,26 @@ import scipy.sparse.linalg as spla
 from scipy.interpolate import BSpline
 
 BAND_EPS = 1e-8
-GROUP = 4           # outputs that share one sample window on the device
+GROUP = 4           # output rows that share one sample window in the vertical device pass
 
 
-def spline_matrix(n_in, n_out):
-    """Sparse (n_out x n_in) matrix W with  W @ f = not-a-knot cubic spline through f[0..n_in) sampled at
-    linspace(0, n_in-1, n_out)  (== scipy.interpolate.make_interp_spline(k=3) == FITPACK s=0 for n_in >= 4)."""
+def spline_factors(n_in, n_out):
+    """(colloc, ev): not-a-knot cubic B-spline collocation matrix on the integer grid [0, n_in) (n_in x n_in) and
+    evaluation matrix at linspace(0, n_in-1, n_out) (n_out x n_in).  Interpolation = ev @ colloc^-1."""
     if n_in < 4:
         raise NotImplementedError("refocus refinement needs at least 4 samples per axis (cubic spline)")
     x = np.arange(n_in, dtype=np.float64)
     t = np.concatenate([[x[0]] * 4, x[2:-2], [x[-1]] * 4])                 # not-a-knot knot vector
     colloc = BSpline.design_matrix(x, t, 3).tocsc()                        # n_in x n_in, banded
     xe = np.linspace(0, n_in - 1, n_out)
-    ev = BSpline.design_matrix(xe, t, 3).tocsr()                           # n_out x n_in
+    ev = BSpline.design_matrix(xe, t, 3).tocsr()                           # n_out x n_in, 4 per row
+    return colloc, ev
+
+
+def spline_matrix(n_in, n_out):
+    """Sparse (n_out x n_in) matrix W with  W @ f = not-a-knot cubic spline through f[0..n_in) sampled at
+    linspace(0, n_in-1, n_out)  (== scipy.interpolate.make_interp_spline(k=3) == FITPACK s=0 for n_in >= 4)."""
+    colloc, ev = spline_factors(n_in, n_out)
     # W = ev @ colloc^-1  ->  W^T = colloc^-T @ ev^T
     lu = spla.splu(colloc.T.tocsc())
     Wt = lu.solve(ev.T.toarray())
@@ -41,43 +55,73 @@ def spline_matrix(n_in, n_out):
     return sp.csr_matrix(W)
 
 
+def _band(A, eps, kmin=1):
+    """Dense (n x n) -> (first (n,), vals (n, K)) keeping |a| > eps; windows are kept inside [0, n)."""
+    n = A.shape[0]
+    sig = np.abs(A) > eps
+    lo = np.argmax(sig, axis=1)
+    hi = n - 1 - np.argmax(sig[:, ::-1], axis=1)
+    K = max(int((hi - lo).max()) + 1, kmin)
+    lo = np.minimum(lo, max(n - K, 0)).astype(np.int64)
+    cols = lo[:, None] + np.arange(K)[None, :]
+    vals = np.where(cols < n, A[np.arange(n)[:, None], np.minimum(cols, n - 1)], 0.0)
+    return lo.astype(np.int32), vals
+
+
 class AxisOperators(object):
-    """All A_s (or B_s) of one axis, as a band: values (n_shift, n, K) float32 + first column (n_shift, n) int32."""
+    """All A_s (or B_s) of one axis in factorised band form:
+
+        prefilter  P    : p_first (n,) int32, p_vals (n, Kp) float32          (shift independent)
+        per shift  D_s  : first (n_shift, n) int32, vals (n_shift, n, K) float32,   A_s = D_s . P
+    """
 
     def __init__(self, n, M, shifts):
         self.n, self.M = int(n), int(M)
         self.shifts = sorted(set(int(s) for s in shifts))
         self.index = {s: k for k, s in enumerate(self.shifts)}
         nf = int(round(n * M))
-        up = spline_matrix(n, nf)                       # img_resize(view, M):   n -> n*M
+        colloc, ev_up = spline_factors(n, nf)           # img_resize(view, M):   n -> n*M  =  ev_up @ colloc^-1
         nd = int(round(nf * (1.0 / M)))
         if nd != n:
             raise ValueError("down-sampled size %d != %d" % (nd, n))
         dn = spline_matrix(nf, nd)                      # img_resize(sum, 1/M):  n*M -> n
+        P = np.linalg.inv(colloc.toarray())
+        self.p_first, pv = _band(P, BAND_EPS)
+        self.p_vals = pv.astype(np.float32)
+        self.Kp = self.p_vals.shape[1]
         rows = np.arange(nf)
-        dense, lo_all, hi_all = [], [], []
+        firsts, dense = [], []
         for s in self.shifts:
-            A = (dn @ up[np.clip(rows + s, 0, nf - 1)]).toarray()          # (n, n) float64
-            sig = np.abs(A) > BAND_EPS
+            D = (dn @ ev_up[np.clip(rows + s, 0, nf - 1)]).toarray()       # (n, n) float64, ~5 per row
+            dense.append(D)
+        K = 1
+        for D in dense:
+            sig = np.abs(D) > BAND_EPS
             lo = np.argmax(sig, axis=1)
             hi = n - 1 - np.argmax(sig[:, ::-1], axis=1)
-            dense.append(A)
-            lo_all.append(lo)
-            hi_all.append(hi)
-        K = int(max((hi - lo).max() for lo, hi in zip(lo_all, hi_all))) + 1
-        self.K = (K + 3) & ~3
+            K = max(K, int((hi - lo).max()) + 1)
+        self.K = K
         ns = len(self.shifts)
         self.first = np.zeros((ns, n), dtype=np.int32)
-        self.vals = np.zeros((ns, n, self.K), dtype=np.float32)
-        for k, (A, lo) in enumerate(zip(dense, lo_all)):
-            lo = np.minimum(lo, max(n - self.K, 0)).astype(np.int64)       # keep the window inside [0, n)
-            self.first[k] = lo
-            cols = lo[:, None] + np.arange(self.K)[None, :]
-            ok = cols < n
-            self.vals[k] = np.where(ok, A[np.arange(n)[:, None], np.minimum(cols, n - 1)], 0.0)
+        self.vals = np.zeros((ns, n, K), dtype=np.float32)
+        for k, D in enumerate(dense):
+            f, v = _band(D, BAND_EPS, kmin=K)
+            self.first[k], self.vals[k] = f, v[:, :K]
+
+    # -- device layouts ------------------------------------------------------------------------------------
+    def tap_major(self):
+        """Horizontal pass (one thread per output sample, lanes along the axis): vals (n_shift, K, n), first
+        (n_shift, n), and per shift the smallest / largest sample offset (relative to the output index) a
+        window touches."""
+        vals = np.ascontiguousarray(self.vals.transpose(0, 2, 1))
+        rel = self.first.astype(np.int64) - np.arange(self.n)[None, :]
+        return vals, self.first, rel.min(axis=1).astype(np.int32), (rel.max(axis=1) + self.K - 1).astype(np.int32)
+
+    def prefilter_tap_major(self):
+        return np.ascontiguousarray(self.p_vals.T), self.p_first
 
     def grouped(self):
-        """Device layout: outputs in groups of GROUP share one window start (the minimum of their band starts),
+        """Vertical pass: outputs in groups of GROUP share one window start (the minimum of their band starts),
         weights (n_shift, G, Kg, GROUP) float32 with zeros where an output's band does not reach; first (n_shift, G)."""
         ns, n, K = self.vals.shape
         G = (n + GROUP - 1) // GROUP
@@ -97,13 +141,24 @@ class AxisOperators(object):
                     vals[si, gi, d:d + K, q] = self.vals[si, idx[gi, q]]
         return vals, start.astype(np.int32), Kg
 
-    def apply(self, s, f, axis=0):
-        """numpy evaluation of the banded operator (used by the CPU tests)."""
-        k = self.index[int(s)]
+    # -- numpy evaluation of the truncated float32 bands (CPU tests) ---------------------------------------
+    def prefilter(self, f, axis=0):
         f = np.moveaxis(np.asarray(f, dtype=np.float64), axis, 0)
+        cols = np.minimum(self.p_first[:, None] + np.arange(self.Kp)[None, :], self.n - 1)
+        out = np.einsum('nk,nk...->n...', self.p_vals.astype(np.float64), f[cols])
+        return np.moveaxis(out, 0, axis)
+
+    def apply_coef(self, s, coef, axis=0):
+        """D_s applied to B-spline coefficients."""
+        k = self.index[int(s)]
+        f = np.moveaxis(np.asarray(coef, dtype=np.float64), axis, 0)
         cols = np.minimum(self.first[k][:, None] + np.arange(self.K)[None, :], self.n - 1)
         out = np.einsum('nk,nk...->n...', self.vals[k].astype(np.float64), f[cols])
         return np.moveaxis(out, 0, axis)
+
+    def apply(self, s, f, axis=0):
+        """A_s = D_s . P applied to samples."""
+        return self.apply_coef(s, self.prefilter(f, axis), axis)
 
 
 _PLAN_CACHE = {}
@@ -120,33 +175,76 @@ def build_operators(S, T, M, a_list):
     return _PLAN_CACHE[key]
 
 
-def refocus_refi(vp, a_list, view_zeroed, mm=None):
+class RefinementPlan(object):
+    """Device-resident operators of one (S, T, M, a_list) configuration; reusable across light fields."""
+
+    def __init__(self, S, T, M, a_list, view_zeroed, device, tmp_budget_bytes=3 << 30):
+        import torch
+        self.S, self.T, self.M = int(S), int(T), int(M)
+        self.a_list = [int(a) for a in a_list]
+        self.N = len(self.a_list)
+        Ay, Bx = build_operators(S, T, M, self.a_list)
+        c = M // 2
+        t = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+        self.z_host = np.ascontiguousarray(np.asarray(view_zeroed, dtype=np.uint8).reshape(-1))
+        if self.z_host.size != M * M:
+            raise ValueError("view mask must have M*M entries")
+        self.z_dev = t(self.z_host)
+        # prefilter
+        pyv, pyf = Ay.p_vals, Ay.p_first                    # vertical: weights uniform per output row -> (S, Kp)
+        pxv, pxf = Bx.prefilter_tap_major()                 # horizontal: lanes along x -> (Kp, T)
+        self.py_v, self.py_f, self.Kpy = t(pyv), t(pyf), int(Ay.Kp)
+        self.px_v, self.px_f, self.Kpx = t(pxv), t(pxf), int(Bx.Kp)
+        # per-slice bands
+        dyv, dyf, self.Kgy = Ay.grouped()
+        dxv, dxf, xlo, xhi = Bx.tap_major()
+        self.dy_v, self.dy_f = t(dyv), t(dyf)
+        self.dx_v, self.dx_f, self.Kx = t(dxv), t(dxf), int(Bx.K)
+        self.iy = np.array([[Ay.index[a * (c - j)] for j in range(M)] for a in self.a_list], dtype=np.int32)
+        self.ix = np.array([[Bx.index[a * (c - i)] for i in range(M)] for a in self.a_list], dtype=np.int32)
+        self.iy_d, self.ix_d = t(self.iy), t(self.ix)
+        self._xlo, self._xhi = xlo, xhi
+        per_slice = M * S * T * 3 * 4                       # horizontal pass of one slice: (M, S, T, 3) float32
+        self.batch = int(max(1, min(self.N, tmp_budget_bytes // per_slice)))
+        self.device = device
+
+    def window(self, n0, nb):
+        """Per view column: smallest / largest sample offset any slice of the batch reads, relative to x."""
+        sl = self.ix[n0:n0 + nb]                             # (nb, M)
+        lo = self._xlo[sl].min(axis=0).astype(np.int32)
+        hi = self._xhi[sl].max(axis=0).astype(np.int32)
+        return np.ascontiguousarray(lo), np.ascontiguousarray(hi)
+
+
+def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None):
     """Device evaluation: vp (M,M,S,T,3) CUDA tensor (uint16 / uint8 / float32) -> (N,S,T,3) float32 stack."""
+    import ctypes as C
     import torch
     from .. import _native as nat
     from .. import ops
-    import ctypes as C
 
     M, M2, S, T, Cn = vp.shape
-    a_list = [int(a) for a in a_list]
-    Ay, Bx = build_operators(S, T, M, a_list)
+    if plan is None:
+        plan = RefinementPlan(S, T, M, a_list, view_zeroed, vp.device)
     dev = vp.device
-    N = len(a_list)
-    c = M // 2
-    # per (slice, view-row / view-column): index of the operator to use
-    iy = np.array([[Ay.index[a * (c - j)] for j in range(M)] for a in a_list], dtype=np.int32)
-    ix = np.array([[Bx.index[a * (c - i)] for i in range(M)] for a in a_list], dtype=np.int32)
-    t = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
-    ayv, ayf, Kgy = Ay.grouped()
-    bxv, bxf, Kgx = Bx.grouped()
-    ay_v, ay_f, bx_v, bx_f = t(ayv), t(ayf), t(bxv), t(bxf)
-    iy_d, ix_d = t(iy), t(ix)
-    z_d = t(np.asarray(view_zeroed, dtype=np.uint8).reshape(-1))
-    tmp = torch.empty((M, S, T, Cn), dtype=torch.float32, device=dev)      # horizontal pass of one slice
+    N = plan.N
+    L, p, st = nat.lib(), ops._ptr, ops._stream()
+    coef = torch.empty((M, M, S, T, Cn), dtype=torch.float32, device=dev)     # B-spline coefficients of every view
+    tmp = torch.empty((M, M, S, T, Cn), dtype=torch.float32, device=dev)
+    nat.check(L.pcb_refi_prefilter(p(vp), ops._pcb_dtype(vp), M, S, T, Cn, p(plan.py_v), p(plan.py_f), plan.Kpy,
+                                   p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp), p(coef), st))
+    del tmp
     out = torch.empty((N, S, T, Cn), dtype=torch.float32, device=dev)
-    p = ops._ptr
-    nat.check(nat.lib().pcb_refocus_refi(p(vp), ops._pcb_dtype(vp), M, S, T, Cn, N,
-                                         p(ay_v), p(ay_f), Kgy, p(bx_v), p(bx_f), Kgx,
-                                         p(iy_d), p(ix_d), p(z_d), p(tmp), p(out),
-                                         p(mm) if mm is not None else C.c_void_p(0), ops._stream()))
+    hbuf = torch.empty((plan.batch, M, S, T, Cn), dtype=torch.float32, device=dev)
+    z_ptr = plan.z_host.ctypes.data_as(C.c_void_p)
+    for n0 in range(0, N, plan.batch):
+        nb = min(plan.batch, N - n0)
+        lo, hi = plan.window(n0, nb)
+        nat.check(L.pcb_refocus_refi(p(coef), M, S, T, Cn, nb,
+                                     p(plan.dy_v), p(plan.dy_f), plan.Kgy, p(plan.dx_v), p(plan.dx_f), plan.Kx,
+                                     C.c_void_p(plan.iy_d.data_ptr() + n0 * M * 4),
+                                     C.c_void_p(plan.ix_d.data_ptr() + n0 * M * 4),
+                                     lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), z_ptr,
+                                     p(plan.z_dev), p(hbuf), C.c_void_p(out.data_ptr() + n0 * S * T * Cn * 4),
+                                     p(mm) if mm is not None else C.c_void_p(0), st))
     return out

@@ -34,16 +34,44 @@ def test_band_operators_reproduce_reference_refinement():
                 if not mask[j, i]:
                     acc += Ay.apply(a * (c - j), Bx.apply(a * (c - i), vp[j, i].astype(np.float64), axis=1), axis=0)
         assert np.abs(acc / M - g["stack"][n]).max() <= 1e-6 * np.abs(g["stack"]).max()
-    # grouped device layout == plain band
-    vals, first, Kg = Bx.grouped()
-    f = np.random.default_rng(0).random(T)
-    for s in Bx.shifts[::7]:
-        k = Bx.index[s]
+    # device layouts == plain band (applied to B-spline coefficients)
+    rng = np.random.default_rng(0)
+    vals, first, Kg = Ay.grouped()                              # vertical pass: groups of 4 outputs share a window
+    f = rng.random(S)
+    for s in Ay.shifts[::7]:
+        k = Ay.index[s]
         out = np.zeros(vals.shape[1] * 4)
         for gi in range(vals.shape[1]):
             for m in range(Kg):
-                out[4 * gi:4 * gi + 4] += vals[k, gi, m] * f[min(first[k, gi] + m, T - 1)]
-        assert np.abs(out[:T] - Bx.apply(s, f)).max() < 1e-6
+                out[4 * gi:4 * gi + 4] += vals[k, gi, m] * f[min(first[k, gi] + m, S - 1)]
+        assert np.abs(out[:S] - Ay.apply_coef(s, f)).max() < 1e-6
+    tv, tf, lo, hi = Bx.tap_major()                             # horizontal pass: one thread per output, tap-major weights
+    f = rng.random(T)
+    for s in Bx.shifts[::7]:
+        k = Bx.index[s]
+        out = np.zeros(T)
+        for x in range(T):
+            assert lo[k] <= tf[k, x] - x and tf[k, x] - x + Bx.K - 1 <= hi[k]
+            for m in range(Bx.K):
+                out[x] += tv[k, m, x] * f[tf[k, x] + m]
+        assert np.abs(out - Bx.apply_coef(s, f)).max() < 1e-6
+    # the factorisation itself: D_s . P == Wdn . Shift_s . Wup
+    nf = T * M
+    full = (rf.spline_matrix(nf, T) @ rf.spline_matrix(T, nf)[np.clip(np.arange(nf) + Bx.shifts[1], 0, nf - 1)]).toarray()
+    assert np.abs(Bx.apply(Bx.shifts[1], np.eye(T)) - full).max() < 1e-6
+    assert Bx.K <= 8 and Ay.K <= 8
+
+
+def test_refinement_band_is_narrow_at_illum_size():
+    """At Lytro-Illum size the per-slice band is 5 taps (the prefilter carries the long tails)."""
+    from plenopticam_b200.lfp_refocuser import refinement as rf
+    ops_x = rf.AxisOperators(625, 15, [0, 7, -105, 224])
+    assert ops_x.K <= 5 and 20 <= ops_x.Kp <= 32
+    f = np.random.default_rng(1).random(625)
+    nf = 625 * 15
+    for s in ops_x.shifts:
+        full = rf.spline_matrix(nf, 625) @ (rf.spline_matrix(625, nf) @ f)[np.clip(np.arange(nf) + s, 0, nf - 1)]
+        assert np.abs(ops_x.apply(s, f) - full).max() < 1e-6
 
 
 @pytest.mark.gpu
