@@ -143,7 +143,8 @@ int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C
  *     P (samples -> cubic B-spline coefficients) is independent of the slice, D_s is a band of <= 5 taps.  All
  *     operators are prepared on the host in float64 (plenopticam_b200/lfp_refocuser/refinement.py).
  *   pcb_refi_prefilter : once per light field, coef[j,i] = Py . vp[j,i] . Px^T for every unmasked view
- *       py_vals[S][Kpy], py_first[S];  px_vals[Kpx][T], px_first[T];  view_zeroed[M*M] (device)
+ *       py_vals[ceil(S/8)][Kpy][8], py_first[ceil(S/8)] (groups of 8 output rows share a window);
+ *       px_vals[Kpx][T], px_first[T];  view_zeroed[M*M] (device)
  *       tmp, coef: float32 (M,M,S,T,3)
  *   pcb_refocus_refi   : a batch of N slices from the coefficients
  *       dy_vals[nsy][ceil(S/4)][Kgy][4], dy_first[nsy][ceil(S/4)]  (groups of 4 output rows share a window)

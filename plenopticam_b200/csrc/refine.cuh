@@ -53,26 +53,46 @@ refi_prefilter_x_kernel(const TIn *__restrict__ vp, int S, int T, const float *_
     }
 }
 
-// grid (ceil(E/256), S, M*M): coef[view][y][e] = sum_m py[y][m] * tmp[view][pf[y]+m][e]
+// grid (ceil(E/256), Gy, M*M): thread = one (x, c) element of a group of RP_GY output rows that share one window
+//   coef[view][y][e] = sum_m py[g(y)][m][q(y)] * tmp[view][pf[g]+m][e]        (weights uniform over the CTA)
+constexpr int RP_GY = 8;
 __global__ void __launch_bounds__(256)
 refi_prefilter_y_kernel(const float *__restrict__ tmp, int S, int E, const float *__restrict__ py_vals,
-                        const int32_t *__restrict__ py_first, int Kp, const uint8_t *__restrict__ view_zeroed,
+                        const int32_t *__restrict__ py_first, int Kg, const uint8_t *__restrict__ view_zeroed,
                         float *__restrict__ coef) {
-    const int y = blockIdx.y, view = blockIdx.z;
+    const int gy = blockIdx.y, view = blockIdx.z;
     if (view_zeroed[view]) return;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const float *w = py_vals + (size_t)y * Kp;                        // uniform over the CTA
-    const float *col = tmp + ((size_t)view * S + py_first[y]) * E + e;
-    float acc = 0.f;
+    const float4 *w = reinterpret_cast<const float4 *>(py_vals) + (size_t)gy * Kg * 2;
+    const int f = py_first[gy];
+    const float *col = tmp + (size_t)view * S * E + e;
+    float acc[RP_GY];
+#pragma unroll
+    for (int q = 0; q < RP_GY; ++q) acc[q] = 0.f;
 #pragma unroll 4
-    for (int m = 0; m < Kp; ++m) acc = fmaf(__ldg(w + m), __ldg(col + (size_t)m * E), acc);
-    coef[((size_t)view * S + y) * E + e] = acc;
+    for (int m = 0; m < Kg; ++m) {
+        const float4 wa = __ldg(w + 2 * m), wb = __ldg(w + 2 * m + 1);
+        const float v = __ldg(col + (size_t)min(f + m, S - 1) * E);
+        acc[0] = fmaf(wa.x, v, acc[0]); acc[1] = fmaf(wa.y, v, acc[1]);
+        acc[2] = fmaf(wa.z, v, acc[2]); acc[3] = fmaf(wa.w, v, acc[3]);
+        acc[4] = fmaf(wb.x, v, acc[4]); acc[5] = fmaf(wb.y, v, acc[5]);
+        acc[6] = fmaf(wb.z, v, acc[6]); acc[7] = fmaf(wb.w, v, acc[7]);
+    }
+#pragma unroll
+    for (int q = 0; q < RP_GY; ++q) {
+        const int y = gy * RP_GY + q;
+        if (y < S) coef[((size_t)view * S + y) * E + e] = acc[q];
+    }
 }
 
 // ---- horizontal pass ---------------------------------------------------------------------------------------------
-constexpr int RH_XC = 160;           // output pixels (= threads) per CTA
+constexpr int RH_XC = 160;           // output pixels per CTA
 constexpr int RH_ROWS = 3;           // image rows per CTA: the weights of a thread are reused for all of them
+constexpr int RH_SG = 4;             // thread groups per CTA, each RH_XC wide, sharing the staged windows and taking
+                                     //   every RH_SG-th slice: 4x the warps in flight for the same shared memory
+constexpr int RH_THREADS = RH_XC * RH_SG;
+constexpr int RH_MAX_IX = 1024;      // slice x view operator indices kept in shared memory per launch
 
 struct RefineHCtl {                  // per-launch control block, passed by value
     int32_t lo[RF_MAXM];             // per view column: smallest / largest coefficient offset (relative to the output
@@ -81,31 +101,39 @@ struct RefineHCtl {                  // per-launch control block, passed by valu
 };
 
 template <int K>
-__global__ void __launch_bounds__(RH_XC)
+__global__ void __launch_bounds__(RH_THREADS)
 refine_h_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, const float *__restrict__ dx_vals,
                 const int32_t *__restrict__ dx_first, const int32_t *__restrict__ ix, RefineHCtl ctl,
                 float *__restrict__ H) {
     extern __shared__ __align__(16) float s_win[];         // [view][row][width_i * 3]
     __shared__ int s_off[RF_MAXM];                         // float offset of view i's block in s_win
     __shared__ int s_x0[RF_MAXM];                          // first staged pixel of view i
+    __shared__ int s_wE[RF_MAXM];                          // staged floats per row of view i
+    __shared__ int s_act[RF_MAXM];                         // the unmasked view columns of this view-row
+    __shared__ int s_nact;
+    __shared__ int s_ix[RH_MAX_IX];                        // ix[n][i] of the batch
     const int j = blockIdx.z;
     const int r0 = blockIdx.y * RH_ROWS;
     const int xc0 = blockIdx.x * RH_XC;
     const int tid = threadIdx.x;
+    const int sg = tid / RH_XC, tx = tid - sg * RH_XC;
     const uint32_t act = ctl.active[j];
     if (act == 0u) return;
     const int nrow = min(RH_ROWS, S - r0);
     const int xcn = min(RH_XC, T - xc0);
 
     if (tid == 0) {
-        int off = 0;
+        int off = 0, na = 0;
         for (int i = 0; i < M; ++i) {
             const int a = max(xc0 + ctl.lo[i], 0), b = min(xc0 + xcn - 1 + ctl.hi[i], T - 1);
             s_x0[i] = a;
             s_off[i] = off;
-            if ((act >> i) & 1u) off += (b - a + 1) * 3 * RH_ROWS;
+            s_wE[i] = (b - a + 1) * 3;
+            if ((act >> i) & 1u) { off += (b - a + 1) * 3 * RH_ROWS; s_act[na++] = i; }
         }
+        s_nact = na;
     }
+    for (int e = tid; e < nb * M; e += RH_THREADS) s_ix[e] = __ldg(ix + e);
     __syncthreads();
     // ---- stage the coefficient windows (rows beyond S replicate nothing: they are never read)
     for (int i = 0; i < M; ++i) {
@@ -115,28 +143,28 @@ refine_h_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, con
         float *dst = s_win + s_off[i];
         for (int rr = 0; rr < nrow; ++rr) {
             const float *src = coef + (((size_t)(j * M + i) * S + r0 + rr) * T + a) * 3;
-            for (int e = tid; e < wE; e += RH_XC) dst[rr * wE + e] = __ldg(src + e);
+            for (int e = tid; e < wE; e += RH_THREADS) dst[rr * wE + e] = __ldg(src + e);
         }
     }
     __syncthreads();
-    if (tid >= xcn) return;
-    const int x = xc0 + tid;
+    if (tx >= xcn) return;
+    const int x = xc0 + tx;
+    const int nact = s_nact;
 
-    for (int n = 0; n < nb; ++n) {
+    for (int n = sg; n < nb; n += RH_SG) {                 // the RH_SG thread groups of a CTA take slices round-robin
         float acc[RH_ROWS][3];
 #pragma unroll
         for (int rr = 0; rr < RH_ROWS; ++rr) acc[rr][0] = acc[rr][1] = acc[rr][2] = 0.f;
-        const int32_t *ixn = ix + (size_t)n * M;
-        for (int i = 0; i < M; ++i) {
-            if (!((act >> i) & 1u)) continue;
-            const int sidx = __ldg(ixn + i);                               // uniform
+        const int *ixn = s_ix + n * M;
+        for (int ii = 0; ii < nact; ++ii) {
+            const int i = s_act[ii];
+            const int sidx = ixn[i];                                       // uniform, from shared memory
             const int f = __ldg(dx_first + (size_t)sidx * T + x);
             float w[K];
 #pragma unroll
             for (int m = 0; m < K; ++m) w[m] = __ldg(dx_vals + ((size_t)sidx * K + m) * T + x);
-            const int a = s_x0[i];
-            const int wE = (min(xc0 + xcn - 1 + ctl.hi[i], T - 1) - a + 1) * 3;
-            const float *px = s_win + s_off[i] + (f - a) * 3;
+            const int wE = s_wE[i];
+            const float *px = s_win + s_off[i] + (f - s_x0[i]) * 3;
 #pragma unroll
             for (int rr = 0; rr < RH_ROWS; ++rr) {
 #pragma unroll
@@ -215,8 +243,8 @@ static int launch_refi_prefilter(const void *vp, int M, int S, int T, const floa
     refi_prefilter_x_kernel<TIn><<<dim3(S, M * M), RP_THREADS, smem, st>>>((const TIn *)vp, S, T, px_vals, px_first, Kpx,
                                                                          view_zeroed, tmp);
     PCB_LAUNCH_OK();
-    refi_prefilter_y_kernel<<<dim3((E + 255) / 256, S, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
-                                                                           view_zeroed, coef);
+    refi_prefilter_y_kernel<<<dim3((E + 255) / 256, (S + RP_GY - 1) / RP_GY, M * M), 256, 0, st>>>(
+        tmp, S, E, py_vals, py_first, Kpy, view_zeroed, coef);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }
@@ -226,7 +254,7 @@ static int launch_refine_h(const float *coef, int M, int S, int T, int nb, const
                            const int32_t *ix, const RefineHCtl &ctl, size_t smem, float *H, cudaStream_t st) {
     PCB_CUDA(cudaFuncSetAttribute(refine_h_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((T + RH_XC - 1) / RH_XC, (S + RH_ROWS - 1) / RH_ROWS, M);
-    refine_h_kernel<K><<<grid, RH_XC, smem, st>>>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, H);
+    refine_h_kernel<K><<<grid, RH_THREADS, smem, st>>>(coef, M, S, T, nb, dx_vals, dx_first, ix, ctl, H);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }
@@ -250,7 +278,9 @@ static int launch_refine(const float *coef, int M, int S, int T, int nb, const f
     }
     for (int i = 0; i < M; ++i) { ctl.lo[i] = xlo_host[i]; ctl.hi[i] = xhi_host[i]; }
     const size_t smem = max_px * 3 * RH_ROWS * sizeof(float);
-    if (smem > 220 * 1024)
+    if (nb * M > RH_MAX_IX)
+        return fail(PCB_ERR_INVALID, "%s: at most %lld slice x view entries per call", "pcb_refocus_refi", RH_MAX_IX);
+    if (smem > 200 * 1024)
         return fail(PCB_ERR_UNSUPPORTED, "%s: coefficient windows of one view row do not fit shared memory", "pcb_refocus_refi");
     int rc;
     switch (Kx) {

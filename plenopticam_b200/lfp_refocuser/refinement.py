@@ -68,6 +68,29 @@ def _band(A, eps, kmin=1):
     return lo.astype(np.int32), vals
 
 
+def _group_band(first, vals, group):
+    """Band (first (n,), vals (n, K)) -> outputs in groups of `group` sharing one window: start (G,) int32 and
+    weights (G, Kg, group) float32, zero where an output's own band does not reach."""
+    n, K = vals.shape
+    G = (n + group - 1) // group
+    idx = np.minimum(np.arange(G * group).reshape(G, group), n - 1)
+    valid = np.arange(G * group).reshape(G, group) < n
+    fg = first[idx].astype(np.int64)
+    start = fg.min(axis=1)
+    off = fg - start[:, None]
+    Kg = K + int(off.max())
+    out = np.zeros((G, Kg, group), dtype=np.float32)
+    gi = np.arange(G)
+    for q in range(group):
+        for m in range(K):
+            sel = valid[:, q]
+            out[gi[sel], off[sel, q] + m, q] = vals[idx[sel, q], m]
+    return start.astype(np.int32), out, Kg
+
+
+PREFILTER_GROUP = 8     # output rows per thread in the vertical prefilter pass
+
+
 class AxisOperators(object):
     """All A_s (or B_s) of one axis in factorised band form:
 
@@ -119,6 +142,12 @@ class AxisOperators(object):
 
     def prefilter_tap_major(self):
         return np.ascontiguousarray(self.p_vals.T), self.p_first
+
+    def prefilter_grouped(self):
+        """Vertical prefilter pass: groups of PREFILTER_GROUP output rows share one window:
+        vals (G, Kg, PREFILTER_GROUP) float32, first (G,) int32, Kg."""
+        start, vals, Kg = _group_band(self.p_first, self.p_vals, PREFILTER_GROUP)
+        return vals, start, Kg
 
     def grouped(self):
         """Vertical pass: outputs in groups of GROUP share one window start (the minimum of their band starts),
@@ -191,9 +220,9 @@ class RefinementPlan(object):
             raise ValueError("view mask must have M*M entries")
         self.z_dev = t(self.z_host)
         # prefilter
-        pyv, pyf = Ay.p_vals, Ay.p_first                    # vertical: weights uniform per output row -> (S, Kp)
+        pyv, pyf, Kpy = Ay.prefilter_grouped()              # vertical: 8 output rows per thread, uniform weights
         pxv, pxf = Bx.prefilter_tap_major()                 # horizontal: lanes along x -> (Kp, T)
-        self.py_v, self.py_f, self.Kpy = t(pyv), t(pyf), int(Ay.Kp)
+        self.py_v, self.py_f, self.Kpy = t(pyv), t(pyf), int(Kpy)
         self.px_v, self.px_f, self.Kpx = t(pxv), t(pxf), int(Bx.Kp)
         # per-slice bands
         dyv, dyf, self.Kgy = Ay.grouped()
@@ -205,7 +234,7 @@ class RefinementPlan(object):
         self.iy_d, self.ix_d = t(self.iy), t(self.ix)
         self._xlo, self._xhi = xlo, xhi
         per_slice = M * S * T * 3 * 4                       # horizontal pass of one slice: (M, S, T, 3) float32
-        self.batch = int(max(1, min(self.N, tmp_budget_bytes // per_slice)))
+        self.batch = int(max(1, min(self.N, tmp_budget_bytes // per_slice, 1024 // M)))
         self.device = device
 
     def window(self, n0, nb):
@@ -214,6 +243,21 @@ class RefinementPlan(object):
         lo = self._xlo[sl].min(axis=0).astype(np.int32)
         hi = self._xhi[sl].max(axis=0).astype(np.int32)
         return np.ascontiguousarray(lo), np.ascontiguousarray(hi)
+
+
+_DEVICE_PLANS = {}
+
+
+def device_plan(S, T, M, a_list, view_zeroed, device):
+    """RefinementPlan of the configuration, kept for the next light field of the same camera (2 entries)."""
+    z = np.ascontiguousarray(np.asarray(view_zeroed, dtype=np.uint8).reshape(-1))
+    key = (int(S), int(T), int(M), tuple(int(a) for a in a_list), z.tobytes(), str(device))
+    plan = _DEVICE_PLANS.get(key)
+    if plan is None:
+        if len(_DEVICE_PLANS) >= 2:
+            _DEVICE_PLANS.pop(next(iter(_DEVICE_PLANS)))
+        plan = _DEVICE_PLANS[key] = RefinementPlan(S, T, M, a_list, view_zeroed, device)
+    return plan
 
 
 def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None):
@@ -225,7 +269,7 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None):
 
     M, M2, S, T, Cn = vp.shape
     if plan is None:
-        plan = RefinementPlan(S, T, M, a_list, view_zeroed, vp.device)
+        plan = device_plan(S, T, M, a_list, view_zeroed, vp.device)
     dev = vp.device
     N = plan.N
     L, p, st = nat.lib(), ops._ptr, ops._stream()

@@ -76,17 +76,25 @@ def gather_slices(local, n_total, group=None):
     return torch.cat(parts, dim=0)
 
 
-def sharded_refocus_stack(vp, a_list, group=None, postprocess=True):
+def sharded_refocus_stack(vp, a_list, group=None, postprocess=True, refi=False, view_zeroed=None):
     """Slice-sharded LfpRefocuser.shift_and_sum on device tensors: every rank passes the same light field
-    `vp` (M,M,S,T,3) and gets the full finished stack back.  One all-gather; two tiny broadcasts."""
+    `vp` (M,M,S,T,3) and gets the full finished stack back.  One all-gather; two tiny broadcasts.
+    refi=True: `a_list` are the up-sampled-pixel parameters of the refinement path (range(M*r0, M*r1));
+    each rank prefilters the light field itself (shift independent, ~3 ms) and evaluates its own slices."""
     from . import ops
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     a_list = list(a_list)
     _, mine = shard_slices(a_list, rank, world)
     mm = ops.new_minmax()
-    local = ops.refocus_int(vp, mine, mm=mm) if mine else \
-        torch.empty((0,) + tuple(vp.shape[2:]), dtype=torch.float32, device=vp.device)
+    if not mine:
+        local = torch.empty((0,) + tuple(vp.shape[2:]), dtype=torch.float32, device=vp.device)
+    elif refi:
+        from .lfp_refocuser.refinement import refocus_refi
+        mask = ops.aperture_mask(vp.shape[0]) if view_zeroed is None else view_zeroed
+        local = refocus_refi(vp, mine, mask, mm=mm)
+    else:
+        local = ops.refocus_int(vp, mine, view_zeroed=view_zeroed, mm=mm)
     if postprocess:
         src = owner_of(0, len(a_list), world)
         lohi = torch.empty(2, dtype=torch.float64, device=vp.device)
