@@ -8,6 +8,7 @@
 #include "refocus_pxp.cuh"
 #include "refine.cuh"
 #include "resample.cuh"
+#include "resample_col.cuh"
 #include "rotate.cuh"
 #include "viewpoints.cuh"
 
@@ -23,6 +24,13 @@ static inline int grid_for(int64_t n, int per_block) {
     int64_t b = (n + per_block - 1) / per_block;
     const int64_t cap = 148 * 16;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <int MODE>
+static int dispatch_resample(const ResampleArgs &a, int raw_dtype, float *out_f32, uint16_t *out_u16,
+                             pcb_minmax_t *mm_rw, const pcb_minmax_t *mm_ro, cudaStream_t st) {
+    if (resample_col_applies(a, raw_dtype)) return launch_resample_col<MODE>(a, out_f32, out_u16, mm_rw, mm_ro, st);
+    return launch_resample<MODE>(a, raw_dtype, out_f32, out_u16, mm_rw, mm_ro, st);
 }
 
 extern "C" {
@@ -71,7 +79,7 @@ int pcb_resample_minmax(const void *raw, int raw_dtype, int H, int W, int C, con
     int rc = make_resample_args(a, raw, H, W, C, lens, LY, LX, M, pattern, hexcol, Xs, hex_odd, flip);
     if (rc) return rc;
     PCB_REQUIRE(mm != nullptr, "mm");
-    return launch_resample<RS_MINMAX>(a, raw_dtype, nullptr, nullptr, mm, nullptr, as_stream(stream));
+    return dispatch_resample<RS_MINMAX>(a, raw_dtype, nullptr, nullptr, mm, nullptr, as_stream(stream));
 }
 
 int pcb_resample_f32(const void *raw, int raw_dtype, int H, int W, int C, const pcb_lens_t *lens, int LY, int LX,
@@ -81,7 +89,7 @@ int pcb_resample_f32(const void *raw, int raw_dtype, int H, int W, int C, const 
     int rc = make_resample_args(a, raw, H, W, C, lens, LY, LX, M, pattern, hexcol, Xs, hex_odd, flip);
     if (rc) return rc;
     PCB_REQUIRE(aligned != nullptr, "aligned");
-    return launch_resample<RS_F32>(a, raw_dtype, aligned, nullptr, mm, nullptr, as_stream(stream));
+    return dispatch_resample<RS_F32>(a, raw_dtype, aligned, nullptr, mm, nullptr, as_stream(stream));
 }
 
 int pcb_resample_u16(const void *raw, int raw_dtype, int H, int W, int C, const pcb_lens_t *lens, int LY, int LX,
@@ -91,7 +99,7 @@ int pcb_resample_u16(const void *raw, int raw_dtype, int H, int W, int C, const 
     int rc = make_resample_args(a, raw, H, W, C, lens, LY, LX, M, pattern, hexcol, Xs, hex_odd, flip);
     if (rc) return rc;
     PCB_REQUIRE(aligned != nullptr && mm != nullptr, "aligned, mm");
-    return launch_resample<RS_U16>(a, raw_dtype, nullptr, aligned, nullptr, mm, as_stream(stream));
+    return dispatch_resample<RS_U16>(a, raw_dtype, nullptr, aligned, nullptr, mm, as_stream(stream));
 }
 
 int pcb_quantize_u16(const float *in, int64_t n, const pcb_minmax_t *mm, uint16_t *out, void *stream) {
