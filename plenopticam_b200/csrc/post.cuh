@@ -154,22 +154,44 @@ select_hist_kernel(const float *__restrict__ data, int64_t n, int luma, SelectSt
     }
 }
 
+// One warp per rank: lane l owns bins 8l..8l+7; exclusive warp scan of the lane sums, then each lane looks for the
+// bucket holding the rank among its own eight bins.  (launched with PS_MAXR warps)
 template <int PASS>
-__global__ void select_scan_kernel(SelectState *st) {
-    // one warp per rank would do; sizes are tiny, so thread r scans row r serially
-    const int r = threadIdx.x;
-    if (r < st->nr) {
+__global__ void __launch_bounds__(PS_MAXR * 32)
+select_scan_kernel(SelectState *st) {
+    const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nr = st->nr;
+    if (r < nr) {
         const uint32_t *h = PASS == 0 ? st->hist[0] : st->hist[r];
-        unsigned long long k = st->rank[r], cum = 0;
-        int b = 0;
-        for (; b < 256; ++b) {
-            const unsigned long long c = h[b];
-            if (k < cum + c) break;
-            cum += c;
+        const uint4 lo4 = *reinterpret_cast<const uint4 *>(h + 8 * lane);
+        const uint4 hi4 = *reinterpret_cast<const uint4 *>(h + 8 * lane + 4);
+        const uint32_t c[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) sum += c[b];
+        unsigned long long incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        b = b > 255 ? 255 : b;
-        st->rank[r] = k - cum;
-        st->prefix[r] = (st->prefix[r] << 8) | (uint32_t)b;
+        unsigned long long cum = incl - sum;                    // counts below this lane's bins
+        const unsigned long long k = st->rank[r];
+        const bool mine = k >= cum && k < incl;
+        const unsigned found = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            int b = 0;
+#pragma unroll
+            for (; b < 7; ++b) {
+                if (k < cum + c[b]) break;
+                cum += c[b];
+            }
+            st->rank[r] = k - cum;
+            st->prefix[r] = (st->prefix[r] << 8) | (uint32_t)(8 * lane + b);
+        } else if (found == 0u && lane == 31) {                  // rank beyond the histogram (cannot happen): last bin
+            st->rank[r] = 0;
+            st->prefix[r] = (st->prefix[r] << 8) | 255u;
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
@@ -201,13 +223,13 @@ static int run_percentile(const float *data, int64_t n, int luma, const double *
     int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
     blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
     select_hist_kernel<0><<<blocks, 256, 0, st>>>(data, n, luma, ss);
-    select_scan_kernel<0><<<1, 256, 0, st>>>(ss);
+    select_scan_kernel<0><<<1, PS_MAXR * 32, 0, st>>>(ss);
     select_hist_kernel<1><<<blocks, 256, 0, st>>>(data, n, luma, ss);
-    select_scan_kernel<1><<<1, 256, 0, st>>>(ss);
+    select_scan_kernel<1><<<1, PS_MAXR * 32, 0, st>>>(ss);
     select_hist_kernel<2><<<blocks, 256, 0, st>>>(data, n, luma, ss);
-    select_scan_kernel<2><<<1, 256, 0, st>>>(ss);
+    select_scan_kernel<2><<<1, PS_MAXR * 32, 0, st>>>(ss);
     select_hist_kernel<3><<<blocks, 256, 0, st>>>(data, n, luma, ss);
-    select_scan_kernel<3><<<1, 256, 0, st>>>(ss);
+    select_scan_kernel<3><<<1, PS_MAXR * 32, 0, st>>>(ss);
     select_finish_kernel<<<1, 32, 0, st>>>(ss, n, result);
     PCB_LAUNCH_OK();
     return PCB_OK;
