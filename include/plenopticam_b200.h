@@ -32,6 +32,7 @@ extern "C" {
 #define PCB_U16 0
 #define PCB_F32 1
 #define PCB_U8  2
+#define PCB_F64 3   /* de-vignetting only (the reference works on float64 copies, lfp_aligner/top_level.py:39-40) */
 
 /* micro-lens arrangement: cfg.calibs['pat_type'] */
 #define PCB_REC 0
@@ -182,9 +183,31 @@ int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N,
 int64_t pcb_percentile_scratch_bytes(void);
 int pcb_percentile_f32(const float *data, int64_t n, int luma, const double *q_host, int nq,
                        double *result, void *scratch, void *stream);
+int pcb_percentile_f64(const double *data, int64_t n, int luma, const double *q_host, int nq,
+                       double *result, void *scratch, void *stream);   /* 8 x 8-bit passes over 64-bit keys */
 int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi,
                       const pcb_minmax_t *mm /* nullable: fallback for a bound that is exactly 0 */,
                       float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * De-vignetting (first "next" row of SURVEY §8f; runs immediately before the resampler) — replaces
+ * LfpDevignetter.__init__ / main / wht_img_divide / _estimate_noise_level
+ * (lfp_aligner/lfp_devignetter.py:33-57,59-93,160-176).  float64 like the reference; divisions are IEEE, so the
+ * de-vignetted image is bit-identical.
+ *   pcb_devig_white       : wgray[npx] = rgb2gry(wht) (C == 3: ((r*0.2126 + g*0.7152) + b*0.0722)) or channel 0
+ *   pcb_percentile_f64    : the 99.9th percentile of wgray (exact order statistics, see above)
+ *   pcb_devig_normalize   : wgray /= *divisor                     (divisor on the device: no host round trip)
+ *   pcb_devig_noise_level : std(wn - convolve2d(wn, g (x) g, 'same')) -> stats[2]  (stats: 3 doubles; tmp: H*W doubles)
+ *                           gauss_host: normalised 1-D Gaussian of odd length glen <= 64 (misc/data_proc.py:31-42)
+ *   pcb_devig_divide      : out[i,c] = wn[i] != 0 ? lfp[i,c] / wn[i] : 0;  out_dtype PCB_F64 (API parity) or
+ *                           PCB_F32 (input of the resampler when the image stays on the device)
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_devig_white(const void *wht, int dtype, int64_t npx, int C, double *wgray, void *stream);
+int pcb_devig_normalize(double *wgray, int64_t npx, const double *divisor, void *stream);
+int pcb_devig_noise_level(const double *wn, int H, int W, const double *gauss_host, int glen,
+                          double *tmp, double *stats, void *stream);
+int pcb_devig_divide(const void *lfp, int dtype, int64_t npx, int C, const double *wn,
+                     void *out, int out_dtype, void *stream);
 
 #ifdef __cplusplus
 }

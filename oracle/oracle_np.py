@@ -509,3 +509,34 @@ def synth_raw(H, W, C=3, seed=0, dtype=np.uint16):
     if np.issubdtype(dtype, np.integer):
         return np.round(img * 65535.0).astype(dtype)
     return img.astype(dtype)
+
+
+# ------------------------------------------------------------------------------------------------------
+# de-vignetting (lfp_aligner/lfp_devignetter.py:33-93,160-176; misc/data_proc.py:31-42)
+# ------------------------------------------------------------------------------------------------------
+def gauss_kernel_1d(length, sigma=1.0):
+    """1-D factor g of misc.create_gauss_kernel: kernel2d = outer(g, g) with g normalised to sum 1
+    (exp(-(x^2+y^2)/2s^2) / sum is separable).  `length` is made odd like data_proc.py:34."""
+    length = (length - 1) // 2 + (length + 1) // 2
+    xs = np.arange(-length // 2 + 1, length // 2 + 1)
+    g = np.exp(-(xs.astype(np.float64) ** 2) / (2 * sigma ** 2))
+    return g / g.sum()
+
+
+def devignette(lfp_img, wht_img, pitch_mean):
+    """LfpDevignetter(lfp_img=..., wht_img=...).main() with patch_mode False (the reference's only reachable
+    mode, lfp_devignetter.py:43): returns (lfp_img float64, wht_img float64 normalised, noise_lev)."""
+    from scipy.signal import convolve2d
+    lfp = np.asarray(lfp_img).astype('float64')
+    wht = np.ones(lfp.shape) if wht_img is None else np.asarray(wht_img).astype('float64')
+    if wht.ndim == 3 and wht.shape[2] == 3:
+        wht = rgb2gry(wht)                                           # :53  -> (H, W, 1)
+    if wht.ndim != lfp.ndim:
+        wht = rgb2gry(wht)                                           # :56
+    wht = wht / np.percentile(wht, q=99.9)                           # :64
+    g = gauss_kernel_1d(int(pitch_mean))
+    bw = wht[..., 0] if wht.ndim == 3 else wht                       # :165-168
+    flt = convolve2d(bw, np.outer(g, g) / np.outer(g, g).sum(), 'same')
+    noise = float(np.std(bw - flt))
+    out = np.divide(lfp, wht, out=np.zeros_like(lfp), where=wht != 0)    # :87
+    return out, wht, noise

@@ -19,7 +19,7 @@ HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "plenopticam_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
-PCB_U16, PCB_F32, PCB_U8 = 0, 1, 2
+PCB_U16, PCB_F32, PCB_U8, PCB_F64 = 0, 1, 2, 3
 PCB_REC, PCB_HEX = 0, 1
 PCB_LENS_INVALID = -2 ** 31
 
@@ -93,7 +93,12 @@ _SIGNATURES = {
                               _vp, _vp, _vp]),
     "pcb_percentile_scratch_bytes": (_i64, []),
     "pcb_percentile_f32": (_i, [_vp, _i64, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
+    "pcb_percentile_f64": (_i, [_vp, _i64, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
     "pcb_contrast_srgb": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "pcb_devig_white": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "pcb_devig_normalize": (_i, [_vp, _i64, _vp, _vp]),
+    "pcb_devig_noise_level": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
+    "pcb_devig_divide": (_i, [_vp, _i, _i64, _i, _vp, _vp, _i, _vp]),
 }
 
 

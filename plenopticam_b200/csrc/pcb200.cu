@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC
 #include "common.cuh"
 #include "post.cuh"
+#include "devignette.cuh"
 #include "refocus.cuh"
 #include "refocus_rows.cuh"
 #include "refocus_px.cuh"
@@ -31,6 +32,20 @@ static int dispatch_resample(const ResampleArgs &a, int raw_dtype, float *out_f3
                              pcb_minmax_t *mm_rw, const pcb_minmax_t *mm_ro, cudaStream_t st) {
     if (resample_col_applies(a, raw_dtype)) return launch_resample_col<MODE>(a, out_f32, out_u16, mm_rw, mm_ro, st);
     return launch_resample<MODE>(a, raw_dtype, out_f32, out_u16, mm_rw, mm_ro, st);
+}
+
+template <typename TIn>
+static int devig_divide_out(const void *lfp, int64_t npx, int C, const double *wn, void *out, int out_dtype,
+                            cudaStream_t st) {
+    const int g = devig_grid(npx * C);
+    if (out_dtype == PCB_F64)
+        devig_divide_kernel<TIn, double><<<g, 256, 0, st>>>((const TIn *)lfp, npx, C, wn, (double *)out);
+    else if (out_dtype == PCB_F32)
+        devig_divide_kernel<TIn, float><<<g, 256, 0, st>>>((const TIn *)lfp, npx, C, wn, (float *)out);
+    else
+        return fail(PCB_ERR_INVALID, "%s: output dtype %lld (float32 / float64)", "pcb_devig_divide", out_dtype);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
 }
 
 extern "C" {
@@ -293,7 +308,68 @@ int pcb_percentile_f32(const float *data, int64_t n, int luma, const double *q_h
     PCB_REQUIRE(data != nullptr && q_host != nullptr && result != nullptr && scratch != nullptr, "pointers");
     PCB_REQUIRE(n > 0 && nq > 0 && nq <= PS_MAXQ, "n > 0, 1 <= nq <= 4");
     for (int k = 0; k < nq; ++k) PCB_REQUIRE(q_host[k] >= 0.0 && q_host[k] <= 100.0, "0 <= q <= 100");
-    return run_percentile(data, n, luma, q_host, nq, result, scratch, as_stream(stream));
+    return run_percentile<float>(data, n, luma, q_host, nq, result, scratch, as_stream(stream));
+}
+
+int pcb_percentile_f64(const double *data, int64_t n, int luma, const double *q_host, int nq, double *result,
+                       void *scratch, void *stream) {
+    PCB_REQUIRE(data != nullptr && q_host != nullptr && result != nullptr && scratch != nullptr, "pointers");
+    PCB_REQUIRE(n > 0 && nq > 0 && nq <= PS_MAXQ, "n > 0, 1 <= nq <= 4");
+    for (int k = 0; k < nq; ++k) PCB_REQUIRE(q_host[k] >= 0.0 && q_host[k] <= 100.0, "0 <= q <= 100");
+    return run_percentile<double>(data, n, luma, q_host, nq, result, scratch, as_stream(stream));
+}
+
+int pcb_devig_white(const void *wht, int dtype, int64_t npx, int C, double *wgray, void *stream) {
+    PCB_REQUIRE(wht != nullptr && wgray != nullptr && npx > 0 && C >= 1, "wht, wgray, npx > 0, C >= 1");
+    cudaStream_t st = as_stream(stream);
+    const int g = devig_grid(npx);
+    switch (dtype) {
+    case PCB_U16: devig_white_kernel<uint16_t><<<g, 256, 0, st>>>((const uint16_t *)wht, npx, C, wgray); break;
+    case PCB_F32: devig_white_kernel<float><<<g, 256, 0, st>>>((const float *)wht, npx, C, wgray); break;
+    case PCB_U8:  devig_white_kernel<uint8_t><<<g, 256, 0, st>>>((const uint8_t *)wht, npx, C, wgray); break;
+    case PCB_F64: devig_white_kernel<double><<<g, 256, 0, st>>>((const double *)wht, npx, C, wgray); break;
+    default: return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+    }
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+int pcb_devig_normalize(double *wgray, int64_t npx, const double *divisor, void *stream) {
+    PCB_REQUIRE(wgray != nullptr && divisor != nullptr && npx > 0, "wgray, divisor, npx > 0");
+    devig_normalize_kernel<<<devig_grid(npx), 256, 0, as_stream(stream)>>>(wgray, npx, divisor);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+int pcb_devig_noise_level(const double *wn, int H, int W, const double *gauss_host, int glen, double *tmp,
+                          double *stats, void *stream) {
+    PCB_REQUIRE(wn != nullptr && gauss_host != nullptr && tmp != nullptr && stats != nullptr, "pointers");
+    PCB_REQUIRE(H > 0 && W > 0 && H <= 65535 && glen >= 1 && glen <= DV_MAXG && (glen & 1), "sizes, odd glen <= 64");
+    cudaStream_t st = as_stream(stream);
+    DevigGauss gk;
+    memset(&gk, 0, sizeof(gk));
+    gk.len = glen;
+    for (int k = 0; k < glen; ++k) gk.g[k] = gauss_host[k];
+    PCB_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(double), st));
+    dim3 grid((W + 255) / 256, H);
+    devig_blur_rows_kernel<<<grid, 256, 0, st>>>(wn, H, W, gk, tmp);
+    devig_blur_cols_stats_kernel<<<grid, 256, 0, st>>>(wn, tmp, H, W, gk, stats);
+    devig_stats_finish_kernel<<<1, 1, 0, st>>>(stats, (double)H * (double)W);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+int pcb_devig_divide(const void *lfp, int dtype, int64_t npx, int C, const double *wn, void *out, int out_dtype,
+                     void *stream) {
+    PCB_REQUIRE(lfp != nullptr && wn != nullptr && out != nullptr && npx > 0 && C >= 1, "pointers, npx > 0, C >= 1");
+    cudaStream_t st = as_stream(stream);
+    switch (dtype) {
+    case PCB_U16: return devig_divide_out<uint16_t>(lfp, npx, C, wn, out, out_dtype, st);
+    case PCB_F32: return devig_divide_out<float>(lfp, npx, C, wn, out, out_dtype, st);
+    case PCB_U8:  return devig_divide_out<uint8_t>(lfp, npx, C, wn, out, out_dtype, st);
+    case PCB_F64: return devig_divide_out<double>(lfp, npx, C, wn, out, out_dtype, st);
+    }
+    return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
 
 int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, const pcb_minmax_t *mm, float *out,

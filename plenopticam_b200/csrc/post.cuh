@@ -84,25 +84,49 @@ contrast_srgb_kernel(const float *__restrict__ in, int64_t n, const double *__re
 
 // ---- exact percentiles by radix select -------------------------------------------------------------
 // np.percentile(x, q) (default 'linear'): vidx = q/100*(n-1); lo = floor(vidx); t = vidx-lo;
-// result = lerp(sorted[lo], sorted[lo+1], t).  We find the needed order statistics exactly with four
-// 8-bit histogram passes over order-preserving keys; up to PS_MAXR ranks are resolved together.
+// result = lerp(sorted[lo], sorted[lo+1], t).  We find the needed order statistics exactly with 8-bit
+// histogram passes over order-preserving keys (4 passes for float32 data, 8 for float64); up to PS_MAXR ranks
+// are resolved together.
 constexpr int PS_MAXQ = 4;
 constexpr int PS_MAXR = 2 * PS_MAXQ;
 
 struct SelectState {
     uint32_t hist[PS_MAXR][256];
-    uint32_t prefix[PS_MAXR];     // key bits resolved so far (high bits)
-    unsigned long long rank[PS_MAXR];   // remaining rank inside the current prefix bucket
+    unsigned long long prefix[PS_MAXR];   // key bits resolved so far (high bits)
+    unsigned long long rank[PS_MAXR];     // remaining rank inside the current prefix bucket
     int nr;
     int pad;
     double q[PS_MAXQ];
 };
 
+template <typename T> struct SelKey;
+template <> struct SelKey<float> {
+    static constexpr int PASSES = 4;
+    __device__ static __forceinline__ unsigned long long key(float v) { return float_to_key(v); }
+    __device__ static __forceinline__ double value(unsigned long long k) { return (double)key_to_float((uint32_t)k); }
+};
+template <> struct SelKey<double> {
+    static constexpr int PASSES = 8;
+    __device__ static __forceinline__ unsigned long long key(double v) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+        return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    }
+    __device__ static __forceinline__ double value(unsigned long long k) {
+        const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        return __longlong_as_double((long long)u);
+    }
+};
+
+// rgb2gry (color_space_converter, third party, unpinned): BT.709 luma
 __device__ __forceinline__ float select_value(const float *data, int64_t i, int luma) {
     if (!luma) return __ldg(data + i);
-    // rgb2gry (color_space_converter, third party, unpinned): BT.709 luma
     const float r = __ldg(data + 3 * i), g = __ldg(data + 3 * i + 1), b = __ldg(data + 3 * i + 2);
     return (float)(0.2126 * (double)r + 0.7152 * (double)g + 0.0722 * (double)b);
+}
+__device__ __forceinline__ double select_value(const double *data, int64_t i, int luma) {
+    if (!luma) return __ldg(data + i);
+    const double r = __ldg(data + 3 * i), g = __ldg(data + 3 * i + 1), b = __ldg(data + 3 * i + 2);
+    return __dadd_rn(__dadd_rn(__dmul_rn(r, 0.2126), __dmul_rn(g, 0.7152)), __dmul_rn(b, 0.0722));
 }
 
 __global__ void select_init_kernel(SelectState *st, int64_t n, int nq, double q0, double q1, double q2, double q3) {
@@ -123,31 +147,31 @@ __global__ void select_init_kernel(SelectState *st, int64_t n, int nq, double q0
     for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
 }
 
-template <int PASS>
+// pass 0 looks at the most significant byte; all ranks share the first-level histogram
+template <typename T>
 __global__ void __launch_bounds__(256)
-select_hist_kernel(const float *__restrict__ data, int64_t n, int luma, SelectState *st) {
+select_hist_kernel(const T *__restrict__ data, int64_t n, int luma, int pass, SelectState *st) {
     __shared__ uint32_t sh[PS_MAXR][256];
-    __shared__ uint32_t s_prefix[PS_MAXR];
+    __shared__ unsigned long long s_prefix[PS_MAXR];
     const int nr = st->nr;
     for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
     if (threadIdx.x < PS_MAXR) s_prefix[threadIdx.x] = st->prefix[threadIdx.x];
     __syncthreads();
-    constexpr int shift = 24 - 8 * PASS;
+    const int shift = (SelKey<T>::PASSES - 1 - pass) * 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t key = float_to_key(select_value(data, i, luma));
-        const uint32_t bin = (key >> shift) & 0xffu;
-        if constexpr (PASS == 0) {
-            // all ranks share the first-level histogram
+        const unsigned long long key = SelKey<T>::key(select_value(data, i, luma));
+        const uint32_t bin = (uint32_t)(key >> shift) & 0xffu;
+        if (pass == 0) {
             atomicAdd(&sh[0][bin], 1u);
         } else {
-            const uint32_t hi = key >> (shift + 8);
+            const unsigned long long hi = key >> (shift + 8);
             for (int r = 0; r < nr; ++r)
                 if (hi == s_prefix[r]) atomicAdd(&sh[r][bin], 1u);
         }
     }
     __syncthreads();
-    const int rows = PASS == 0 ? 1 : nr;
+    const int rows = pass == 0 ? 1 : nr;
     for (int i = threadIdx.x; i < rows * 256; i += blockDim.x) {
         const uint32_t v = (&sh[0][0])[i];
         if (v) atomicAdd(&(&st->hist[0][0])[i], v);
@@ -156,13 +180,12 @@ select_hist_kernel(const float *__restrict__ data, int64_t n, int luma, SelectSt
 
 // One warp per rank: lane l owns bins 8l..8l+7; exclusive warp scan of the lane sums, then each lane looks for the
 // bucket holding the rank among its own eight bins.  (launched with PS_MAXR warps)
-template <int PASS>
 __global__ void __launch_bounds__(PS_MAXR * 32)
-select_scan_kernel(SelectState *st) {
+select_scan_kernel(SelectState *st, int pass) {
     const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nr = st->nr;
     if (r < nr) {
-        const uint32_t *h = PASS == 0 ? st->hist[0] : st->hist[r];
+        const uint32_t *h = pass == 0 ? st->hist[0] : st->hist[r];
         const uint4 lo4 = *reinterpret_cast<const uint4 *>(h + 8 * lane);
         const uint4 hi4 = *reinterpret_cast<const uint4 *>(h + 8 * lane + 4);
         const uint32_t c[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
@@ -187,21 +210,22 @@ select_scan_kernel(SelectState *st) {
                 cum += c[b];
             }
             st->rank[r] = k - cum;
-            st->prefix[r] = (st->prefix[r] << 8) | (uint32_t)(8 * lane + b);
+            st->prefix[r] = (st->prefix[r] << 8) | (unsigned long long)(8 * lane + b);
         } else if (found == 0u && lane == 31) {                  // rank beyond the histogram (cannot happen): last bin
             st->rank[r] = 0;
-            st->prefix[r] = (st->prefix[r] << 8) | 255u;
+            st->prefix[r] = (st->prefix[r] << 8) | 255ull;
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
 }
 
+template <typename T>
 __global__ void select_finish_kernel(const SelectState *st, int64_t n, double *result) {
     const int k = threadIdx.x;
     if (2 * k < st->nr) {
-        const double a = (double)key_to_float(st->prefix[2 * k]);
-        const double b = (double)key_to_float(st->prefix[2 * k + 1]);
+        const double a = SelKey<T>::value(st->prefix[2 * k]);
+        const double b = SelKey<T>::value(st->prefix[2 * k + 1]);
         const double vidx = st->q[k] / 100.0 * (double)(n - 1);
         const double t = vidx - floor(vidx);
         // numpy _lerp: a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
@@ -213,7 +237,8 @@ __global__ void select_finish_kernel(const SelectState *st, int64_t n, double *r
     }
 }
 
-static int run_percentile(const float *data, int64_t n, int luma, const double *q_host, int nq, double *result,
+template <typename T>
+static int run_percentile(const T *data, int64_t n, int luma, const double *q_host, int nq, double *result,
                           void *scratch, cudaStream_t st) {
     SelectState *ss = reinterpret_cast<SelectState *>(scratch);
     double q[PS_MAXQ] = {0, 0, 0, 0};
@@ -222,15 +247,11 @@ static int run_percentile(const float *data, int64_t n, int luma, const double *
     PCB_LAUNCH_OK();
     int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
     blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
-    select_hist_kernel<0><<<blocks, 256, 0, st>>>(data, n, luma, ss);
-    select_scan_kernel<0><<<1, PS_MAXR * 32, 0, st>>>(ss);
-    select_hist_kernel<1><<<blocks, 256, 0, st>>>(data, n, luma, ss);
-    select_scan_kernel<1><<<1, PS_MAXR * 32, 0, st>>>(ss);
-    select_hist_kernel<2><<<blocks, 256, 0, st>>>(data, n, luma, ss);
-    select_scan_kernel<2><<<1, PS_MAXR * 32, 0, st>>>(ss);
-    select_hist_kernel<3><<<blocks, 256, 0, st>>>(data, n, luma, ss);
-    select_scan_kernel<3><<<1, PS_MAXR * 32, 0, st>>>(ss);
-    select_finish_kernel<<<1, 32, 0, st>>>(ss, n, result);
+    for (int pass = 0; pass < SelKey<T>::PASSES; ++pass) {
+        select_hist_kernel<T><<<blocks, 256, 0, st>>>(data, n, luma, pass, ss);
+        select_scan_kernel<<<1, PS_MAXR * 32, 0, st>>>(ss, pass);
+    }
+    select_finish_kernel<T><<<1, 32, 0, st>>>(ss, n, result);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }

@@ -1,8 +1,9 @@
-"""`LfpAligner` restricted to the hot path: (opt) LfpRotator -> LfpResampler
-(lfp_aligner/top_level.py:32-83).  The pre-processing stages that precede them in the reference
-(CfaOutliers, LfpDevignetter, CfaProcessor; top_level.py:44-64) are out of scope — feed this
-class the RGB image those stages produce.  The rotated image stays on the device between the two stages."""
+"""`LfpAligner` for RGB exposures: (opt) LfpDevignetter -> (opt) LfpRotator -> LfpResampler
+(lfp_aligner/top_level.py:32-83).  The Bayer stages of Lytro files (CfaOutliers, CfaProcessor; top_level.py:44-49,
+59-64) are out of scope — feed this class the RGB image they produce.  The image stays on the device
+between the stages."""
 from ..misc import PlenopticamStatus
+from .lfp_devignetter import LfpDevignetter
 from .lfp_resampler import LfpResampler
 from .lfp_rotator import LfpRotator
 
@@ -20,6 +21,12 @@ class LfpAligner(object):
 
     def main(self):
         img = self._lfp_img
+        if self.cfg.params[self.cfg.opt_vign] and self._wht_img is not None and img is not None:
+            obj = LfpDevignetter(lfp_img=img, wht_img=self._wht_img, cfg=self.cfg, sta=self.sta)
+            obj.main()
+            img = obj.lfp_img_device
+            self._wht_dev = obj._dev_wn
+            del obj
         if self.cfg.params[self.cfg.opt_rota] and img is not None:
             obj = LfpRotator(img, self.cfg.calibs[self.cfg.mic_list], rad=None, cfg=self.cfg, sta=self.sta)
             obj.main()

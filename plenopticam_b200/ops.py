@@ -331,3 +331,67 @@ def refocuser_postprocess(stack, mm=None, out=None):
     if mm is None:
         mm = minmax_f32(stack)
     return contrast_srgb(stack, lohi, mm=mm, out=out)
+
+
+# ------------------------------------------------------------------------------------------------------
+# de-vignetting (lfp_aligner/lfp_devignetter.py)
+# ------------------------------------------------------------------------------------------------------
+_TORCH2PCB_F64 = dict(_TORCH2PCB)
+_TORCH2PCB_F64[torch.float64] = nat.PCB_F64
+
+
+def to_device_any(arr):
+    """numpy -> CUDA tensor keeping uint8 / uint16 / float32 / float64 as they are (other dtypes -> float64)."""
+    dev = require_cuda()
+    arr = np.asarray(arr)
+    if arr.dtype in (np.dtype("uint8"), np.dtype("uint16"), np.dtype("float32")):
+        return to_device(arr, dtype=arr.dtype)
+    host = np.ascontiguousarray(arr, dtype=np.float64)
+    pinned = torch.empty(host.shape, dtype=torch.float64, pin_memory=True)
+    pinned.numpy()[...] = host
+    return pinned.to(dev, non_blocking=True)
+
+
+def percentile_f64(data, q):
+    """np.percentile of a float64 CUDA tensor (exact order statistics, 8 radix passes) -> float64 tensor of len(q)."""
+    _chk_dev(data)
+    if data.dtype != torch.float64:
+        raise TypeError("float64 expected")
+    L = nat.lib()
+    q = [float(v) for v in np.atleast_1d(q)]
+    scratch = torch.empty(int(L.pcb_percentile_scratch_bytes()), dtype=torch.uint8, device=data.device)
+    res = torch.empty(len(q), dtype=torch.float64, device=data.device)
+    qarr = (C.c_double * len(q))(*q)
+    nat.check(L.pcb_percentile_f64(_ptr(data), data.numel(), 0, qarr, len(q), _ptr(res), _ptr(scratch), _stream()))
+    return res
+
+
+def devignette(lfp, wht, gauss_1d, out_dtype=torch.float64):
+    """White-image division on the device.
+
+    lfp: (H,W[,C]) CUDA tensor (uint8/uint16/float32/float64); wht: (H,W[,Cw]) CUDA tensor, Cw in (1, 3);
+    gauss_1d: normalised odd-length 1-D Gaussian (numpy float64) of the noise-level estimate.
+    Returns (out (same shape as lfp, out_dtype), wn (H,W) float64 normalised gray white image, stats) where
+    stats[2] is the noise level (float64 CUDA tensor of 3; no synchronisation here)."""
+    _chk_dev(lfp, wht)
+    L, st = nat.lib(), _stream()
+    H, W = int(lfp.shape[0]), int(lfp.shape[1])
+    Cl = int(lfp.shape[2]) if lfp.dim() == 3 else 1
+    Cw = int(wht.shape[2]) if wht.dim() == 3 else 1
+    if tuple(wht.shape[:2]) != (H, W) or Cw not in (1, 3):
+        raise ValueError("white image must be (H, W), (H, W, 1) or (H, W, 3) with the light-field image's H, W")
+    npx = H * W
+    dev = lfp.device
+    wn = torch.empty((H, W), dtype=torch.float64, device=dev)
+    nat.check(L.pcb_devig_white(_ptr(wht), _TORCH2PCB_F64[wht.dtype], npx, Cw, _ptr(wn), st))
+    p = percentile_f64(wn, [99.9])
+    nat.check(L.pcb_devig_normalize(_ptr(wn), npx, _ptr(p), st))
+    g = np.ascontiguousarray(gauss_1d, dtype=np.float64)
+    tmp = torch.empty((H, W), dtype=torch.float64, device=dev)
+    stats = torch.empty(3, dtype=torch.float64, device=dev)
+    nat.check(L.pcb_devig_noise_level(_ptr(wn), H, W, g.ctypes.data_as(C.POINTER(C.c_double)), int(g.size), _ptr(tmp),
+                                      _ptr(stats), st))
+    out = torch.empty(tuple(lfp.shape), dtype=out_dtype, device=dev)
+    nat.check(L.pcb_devig_divide(_ptr(lfp), _TORCH2PCB_F64[lfp.dtype], npx, Cl, _ptr(wn), _ptr(out),
+                                 _TORCH2PCB_F64[out_dtype], st))
+    return out, wn, stats
