@@ -190,6 +190,16 @@ int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi,
                       float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Scheimpflug composite ("next" row) — replaces LfpScheimpflug.scheimpflug_from_stack
+ * (lfp_refocuser/lfp_scheimpflug.py:68-114): out[y,x,:] = stack[a_map[y,x]][y,x,:] with
+ *   mode 0: a_map = a_y[y]   mode 1: a_map = a_x[x]   mode 2: a_map = (a_x[x] + a_y[y]) / 2  (integer mean, :94)
+ * stack (N,S,T,C) float32, a_y[S], a_x[T] int32 (device), out (S,T,C) float32.  The uint16 image the reference
+ * saves is pcb_minmax_f32 + pcb_quantize_u16 of `out` (misc/normalizer.py:43-46).
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_scheimpflug(const float *stack, int N, int S, int T, int C, const int32_t *a_y, const int32_t *a_x,
+                    int mode, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * De-vignetting (first "next" row of SURVEY §8f; runs immediately before the resampler) — replaces
  * LfpDevignetter.__init__ / main / wht_img_divide / _estimate_noise_level
  * (lfp_aligner/lfp_devignetter.py:33-57,59-93,160-176).  float64 like the reference; divisions are IEEE, so the

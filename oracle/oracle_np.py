@@ -540,3 +540,34 @@ def devignette(lfp_img, wht_img, pitch_mean):
     noise = float(np.std(bw - flt))
     out = np.divide(lfp, wht, out=np.zeros_like(lfp), where=wht != 0)    # :87
     return out, wht, noise
+
+
+# ------------------------------------------------------------------------------------------------------
+# Scheimpflug composite (lfp_refocuser/lfp_scheimpflug.py:68-114)
+# ------------------------------------------------------------------------------------------------------
+PFLU_VALS = ('vertical', 'horizontal', 'skew up', 'skew down')
+
+
+def scheimpflug_from_stack(stack, direction):
+    """(float composite, Normalizer(composite).uint16_norm()) for one direction, including the reference's
+    `== (PFLU_VALS[2] or PFLU_VALS[3])` quirk (:91: only 'skew up' takes the diagonal map)."""
+    stack = np.asarray(stack)
+    N = len(stack)
+    m, n = stack[0].shape[:2]
+    p = stack[0].shape[2] if stack[0].ndim == 3 else 1
+    a_x = np.linspace(0, N, n + 2, dtype='int')[1:-1]
+    a_y = np.linspace(0, N, m + 2, dtype='int')[1:-1]
+    a_map_x = np.outer(np.ones(m, dtype='int'), a_x)
+    a_map_y = np.outer(a_y, np.ones(n, dtype='int'))
+    a_map = a_map_y
+    if direction == PFLU_VALS[1]:
+        a_map = a_map_x
+    elif direction == (PFLU_VALS[2] or PFLU_VALS[3]):
+        a_map = np.mean(np.stack([a_map_x, a_map_y]), dtype='int', axis=0)
+    yy, xx = np.mgrid[0:m, 0:n]
+    img = np.zeros([m, n, p])
+    img[...] = stack[a_map, yy, xx].reshape(m, n, p)
+    x32 = img.astype('float32')
+    mn, mx = x32.min(), x32.max()
+    q = np.asarray(np.round(norm_fun(x32, mn, mx) * 65535), dtype=np.uint16)
+    return img, q

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "post.cuh"
 #include "devignette.cuh"
+#include "scheimpflug.cuh"
 #include "refocus.cuh"
 #include "refocus_rows.cuh"
 #include "refocus_px.cuh"
@@ -370,6 +371,16 @@ int pcb_devig_divide(const void *lfp, int dtype, int64_t npx, int C, const doubl
     case PCB_F64: return devig_divide_out<double>(lfp, npx, C, wn, out, out_dtype, st);
     }
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
+int pcb_scheimpflug(const float *stack, int N, int S, int T, int C, const int32_t *a_y, const int32_t *a_x, int mode,
+                    float *out, void *stream) {
+    PCB_REQUIRE(stack != nullptr && a_y != nullptr && a_x != nullptr && out != nullptr, "pointers");
+    PCB_REQUIRE(N > 0 && S > 0 && S <= 65535 && T > 0 && C > 0 && mode >= 0 && mode <= 2, "sizes, mode in 0..2");
+    const int E = T * C;
+    scheimpflug_kernel<<<dim3((E + 255) / 256, S), 256, 0, as_stream(stream)>>>(stack, N, S, E, C, a_y, a_x, mode, out);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
 }
 
 int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, const pcb_minmax_t *mm, float *out,

@@ -1,6 +1,6 @@
-"""`LfpRefocuser` restricted to the hot path (lfp_refocuser/top_level.py:32-79): shift-and-sum stack, then
-percentile contrast alignment against slice 0 and the sRGB transfer, all on the device.  PNG/GIF export and
-the Scheimpflug composite (top_level.py:72-87) are out of scope."""
+"""`LfpRefocuser` (lfp_refocuser/top_level.py:32-87): shift-and-sum stack, percentile contrast alignment against
+slice 0 and the sRGB transfer, then (opt) the Scheimpflug composites, all on the device.  PNG/GIF export of the
+stack (top_level.py:72-77) is out of scope."""
 from .. import ops
 from ..lfp_extractor.lfp_viewpoints import LfpViewpoints
 from .lfp_shiftandsum import LfpShiftAndSum
@@ -19,9 +19,17 @@ class LfpRefocuser(LfpViewpoints):
             return False
         if self.cfg.params[self.cfg.opt_refo]:
             self.shift_and_sum()
-        if self.cfg.params[self.cfg.opt_pflu]:
-            raise NotImplementedError('Scheimpflug rendering (lfp_refocuser/lfp_scheimpflug.py) is outside the '
-                                      'B200 hot path')
+        if self.cfg.params[self.cfg.opt_pflu]:                    # lfp_refocuser/top_level.py:54
+            self.scheimpflug()
+        return True
+
+    def scheimpflug(self):
+        from .lfp_scheimpflug import LfpScheimpflug
+        stack = self.refo_stack_device if self.refo_stack_device is not None else self.refo_stack
+        obj = LfpScheimpflug(refo_stack=stack, cfg=self.cfg, sta=self.sta)
+        obj.main()
+        self.scheimpflug_images = obj.images
+        del obj
         return True
 
     def shift_and_sum(self):

@@ -395,3 +395,41 @@ def devignette(lfp, wht, gauss_1d, out_dtype=torch.float64):
     nat.check(L.pcb_devig_divide(_ptr(lfp), _TORCH2PCB_F64[lfp.dtype], npx, Cl, _ptr(wn), _ptr(out),
                                  _TORCH2PCB_F64[out_dtype], st))
     return out, wn, stats
+
+
+# ------------------------------------------------------------------------------------------------------
+# Scheimpflug composite (lfp_refocuser/lfp_scheimpflug.py:68-114)
+# ------------------------------------------------------------------------------------------------------
+PFLU_VALS = ('vertical', 'horizontal', 'skew up', 'skew down')
+
+
+def scheimpflug_maps(n_slices, S, T):
+    """a_y (S,), a_x (T,) of lfp_scheimpflug.py:81-82: integer-typed linspace without its end points."""
+    a_x = np.linspace(0, n_slices, T + 2, dtype='int')[1:-1]
+    a_y = np.linspace(0, n_slices, S + 2, dtype='int')[1:-1]
+    return a_y.astype(np.int32), a_x.astype(np.int32)
+
+
+def scheimpflug_mode(direction):
+    """Which map the reference ends up using (:86-94).  Its test `== (PFLU_VALS[2] or PFLU_VALS[3])` only ever
+    matches 'skew up'; 'skew down' therefore keeps the default vertical map."""
+    if direction == PFLU_VALS[1]:
+        return 1
+    if direction == PFLU_VALS[2]:
+        return 2
+    return 0
+
+
+def scheimpflug(stack, direction):
+    """(S,T,C) float32 composite and its Normalizer.uint16_norm (uint16 CUDA tensors stay on the device)."""
+    _chk_dev(stack)
+    if stack.dtype != torch.float32 or stack.dim() != 4:
+        raise TypeError("float32 (N,S,T,C) stack expected")
+    N, S, T, Cn = (int(v) for v in stack.shape)
+    a_y, a_x = scheimpflug_maps(N, S, T)
+    ay_d, ax_d = torch.from_numpy(a_y).to(stack.device), torch.from_numpy(a_x).to(stack.device)
+    out = torch.empty((S, T, Cn), dtype=torch.float32, device=stack.device)
+    nat.check(nat.lib().pcb_scheimpflug(_ptr(stack), N, S, T, Cn, _ptr(ay_d), _ptr(ax_d), scheimpflug_mode(direction),
+                                        _ptr(out), _stream()))
+    mm = minmax_f32(out)
+    return out, quantize_u16(out, mm)
