@@ -190,6 +190,13 @@ int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi,
                       float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Lytro raw bit-unpacking ("next" row) — replaces LfpDecoder.comp_bayer
+ * (lfp_reader/lfp_decoder.py:273-326).  buf: packed bytes on the device; bits = cfg.lfpimg['bit'] (10: 5 bytes ->
+ * 4 pixels, 12: 3 bytes -> 2 pixels); out: floor(nbytes/5)*4 or floor(nbytes/3)*2 uint16 pixels in file order.
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_unpack_bayer(const uint8_t *buf, int64_t nbytes, int bits, uint16_t *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Scheimpflug composite ("next" row) — replaces LfpScheimpflug.scheimpflug_from_stack
  * (lfp_refocuser/lfp_scheimpflug.py:68-114): out[y,x,:] = stack[a_map[y,x]][y,x,:] with
  *   mode 0: a_map = a_y[y]   mode 1: a_map = a_x[x]   mode 2: a_map = (a_x[x] + a_y[y]) / 2  (integer mean, :94)

@@ -571,3 +571,19 @@ def scheimpflug_from_stack(stack, direction):
     mn, mx = x32.min(), x32.max()
     q = np.asarray(np.round(norm_fun(x32, mn, mx) * 65535), dtype=np.uint16)
     return img, q
+
+
+# ------------------------------------------------------------------------------------------------------
+# Lytro raw bit-unpacking (lfp_reader/lfp_decoder.py:273-326)
+# ------------------------------------------------------------------------------------------------------
+def comp_bayer(img_buf, shape, bit_pac=10):
+    buf = np.frombuffer(bytes(img_buf), dtype=np.uint8).astype(np.uint16)
+    if bit_pac == 10:
+        b = buf[:buf.size // 5 * 5].reshape(-1, 5)
+        px = (b[:, :4] << 2) + ((b[:, 4:5] >> (2 * np.arange(4, dtype=np.uint16))) & 3)
+    elif bit_pac == 12:
+        b = buf[:buf.size // 3 * 3].reshape(-1, 3)
+        px = np.stack([(b[:, 0] << 4) + (b[:, 1] >> 4), ((b[:, 1] & 15) << 8) + b[:, 2]], axis=1)
+    else:
+        raise ValueError(bit_pac)
+    return px.reshape(shape[1], shape[0]).astype('float')

@@ -4,6 +4,7 @@
 #include "post.cuh"
 #include "devignette.cuh"
 #include "scheimpflug.cuh"
+#include "unpack.cuh"
 #include "refocus.cuh"
 #include "refocus_rows.cuh"
 #include "refocus_px.cuh"
@@ -371,6 +372,24 @@ int pcb_devig_divide(const void *lfp, int dtype, int64_t npx, int C, const doubl
     case PCB_F64: return devig_divide_out<double>(lfp, npx, C, wn, out, out_dtype, st);
     }
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
+int pcb_unpack_bayer(const uint8_t *buf, int64_t nbytes, int bits, uint16_t *out, void *stream) {
+    PCB_REQUIRE(buf != nullptr && out != nullptr && nbytes > 0, "buf, out, nbytes > 0");
+    PCB_REQUIRE(bits == 10 || bits == 12, "10- or 12-bit packing (lfp_decoder.py:280-312)");
+    PCB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7) == 0, "out 8-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    if (bits == 10) {
+        const int64_t ng = nbytes / 5;
+        PCB_REQUIRE(ng > 0, "at least one 5-byte group");
+        unpack10_kernel<<<grid_for(ng, 256 * 4), 256, 0, st>>>(buf, ng, out);
+    } else {
+        const int64_t ng = nbytes / 3;
+        PCB_REQUIRE(ng > 0, "at least one 3-byte group");
+        unpack12_kernel<<<grid_for(ng, 256 * 4), 256, 0, st>>>(buf, ng, out);
+    }
+    PCB_LAUNCH_OK();
+    return PCB_OK;
 }
 
 int pcb_scheimpflug(const float *stack, int N, int S, int T, int C, const int32_t *a_y, const int32_t *a_x, int mode,
