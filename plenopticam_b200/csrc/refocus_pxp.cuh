@@ -285,7 +285,7 @@ static PxpPlan plan_refocus_pxp(const PxPlan &px, int M, int S, int T, int N, in
     const int c0 = M / 2;
     pl.ppt = T <= 1024 ? 1 : 2;
     pl.threads = ((((T + pl.ppt - 1) / pl.ppt) + 31) & ~31);
-    pl.maxt = pl.threads <= 640 ? 640 : 1024;
+    pl.maxt = (pl.threads <= 640 && pl.ppt == 1) ? 640 : 1024;      // the 640-thread build only exists for PPT = 1
     const int W = pl.threads * pl.ppt;
     PxpCtl &c = pl.ctl;
     int max_nact = 0;

@@ -268,6 +268,7 @@ def test_interrupt_returns_false(cuda):
 @pytest.mark.parametrize("M,S,T,a_list", [
     (15, 37, 61, list(range(-32, 32))),          # Illum-like angular size, shifts far larger than the image
     (7, 19, 1300, [-3, 0, 2, 5]),                # wide rows -> several x chunks, several words per thread
+    (7, 5, 1100, [-3, 0, 2, 5]),                 # two pixels per thread with <= 640 threads (found by tools/stress_parity.py)
     (5, 3, 4, list(range(-40, 40))),             # tiny image, N > 64 -> two launches, shift >> T
     (9, 1, 33, [-2, -1, 0, 1, 2]),               # single row: top and bottom edge are the same row
     (3, 40, 7, [100, -100, 1]),                  # |a| huge
