@@ -117,8 +117,60 @@ def main():
                                            info=got if isinstance(got, str) else float(np.abs(got - ref).max())))
         os.environ.pop("PCB_REFOCUS_KERNEL", None)
     print("refocus: %d cases x 4 kernel forms, %d failures" % (args.cases, bad_r))
+    # ---------------------------------------------------------------- refinement, viewpoints, post-processing
+    from plenopticam_b200.lfp_refocuser.refinement import refocus_refi
+    bad_o = 0
+    for case in range(max(4, args.cases // 6)):
+        M = int(rng.choice([3, 5, 7, 9]))
+        S, T = int(rng.integers(6, 70)), int(rng.integers(6, 200))
+        r0 = int(rng.integers(-2, 1)); ran = (r0, r0 + int(rng.integers(1, 3)))
+        dt = rng.choice([np.uint16, np.float32])
+        vp = (rng.random((M, M, S, T, 3)) * (65535 if dt == np.uint16 else 1)).astype(dt)
+        try:
+            got = ops.to_host(refocus_refi(ops.to_device(vp), range(M * ran[0], M * ran[1]), ops.aperture_mask(M)))
+            ref = onp.refocus_refi(vp, ran, M)
+            err = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-12))
+            ok = err <= 2e-5
+        except Exception as e:                                   # noqa: BLE001
+            ok, err = False, repr(e)
+        if not ok:
+            bad_o += 1
+            print("REFI FAIL", dict(case=case, M=M, S=S, T=T, ran=ran, dt=np.dtype(dt).name, err=err))
+    for case in range(args.cases):
+        M_in = int(rng.choice([3, 5, 7, 9, 11, 15])); M_out = int(rng.choice([m for m in (3, 5, 7, 9, 11, 15) if m <= M_in]))
+        S, T, Cn = int(rng.integers(1, 40)), int(rng.integers(1, 300)), int(rng.choice([1, 3, 4]))
+        dt = rng.choice([np.uint8, np.uint16, np.float32])
+        al = (rng.random((S * M_in, T * M_in, Cn)) * 255).astype(dt)
+        try:
+            vpd = ops.viewpoints(ops.to_device(al), M_in, M_out)
+            ref = onp.compose_viewpoints(onp.crop_micro_images(al, M_in, M_out), M_out)
+            ok = np.array_equal(ops.to_host(vpd), ref)
+            back = ops.to_host(ops.viewpoints_inverse(vpd))
+            ok = ok and np.array_equal(back, onp.crop_micro_images(al, M_in, M_out))
+        except Exception as e:                                   # noqa: BLE001
+            ok = False
+            print(repr(e))
+        if not ok:
+            bad_o += 1
+            print("VIEWPOINTS FAIL", dict(case=case, M_in=M_in, M_out=M_out, S=S, T=T, C=Cn, dt=np.dtype(dt).name))
+    for case in range(max(4, args.cases // 4)):
+        N, S, T = int(rng.integers(1, 9)), int(rng.integers(2, 60)), int(rng.integers(2, 200))
+        stack = (rng.random((N, S, T, 3)) ** 2 * float(rng.choice([1.0, 300.0, 70000.0]))).astype(np.float64)
+        if rng.integers(0, 3) == 0:
+            stack[0, : S // 2] = 0.0                            # zero lower percentile -> Normalizer's min fallback
+        try:
+            got = ops.to_host(ops.refocuser_postprocess(ops.to_device(stack.astype(np.float32))))
+            ref = onp.refocuser_postprocess(stack.astype(np.float32).astype(np.float64))
+            err = float(np.abs(got.astype(np.float64) - ref).max())
+            ok = err <= 1e-5
+        except Exception as e:                                   # noqa: BLE001
+            ok, err = False, repr(e)
+        if not ok:
+            bad_o += 1
+            print("POST FAIL", dict(case=case, N=N, S=S, T=T, err=err))
+    print("refinement / viewpoints / post: %d failures" % bad_o)
     torch.cuda.synchronize()
-    sys.exit(1 if bad or bad_r else 0)
+    sys.exit(1 if bad or bad_r or bad_o else 0)
 
 
 if __name__ == "__main__":
