@@ -42,6 +42,18 @@ inline int fail(int code, const char *fmt, const char *a = "", long long b = 0) 
         }                                                                                         \
     } while (0)
 
+// SM count of the current device (persistent / strip-mined grids)
+static inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
 // ---- order-preserving float <-> uint32 keys (for atomic min/max and radix select) -----------------
 __host__ __device__ __forceinline__ uint32_t float_to_key(float f) {
 #ifdef __CUDA_ARCH__

@@ -265,15 +265,7 @@ struct PxpPlan {
     bool clamp, exact24;
 };
 
-static int pxp_sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            n = 148;
-    }
-    return n;
-}
+static int pxp_sm_count() { return sm_count(); }
 
 // Host-side planning (no device access).  `px` supplies the accumulator / edge-table geometry.
 static PxpPlan plan_refocus_pxp(const PxPlan &px, int M, int S, int T, int N, int max_abs_a,
