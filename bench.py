@@ -390,6 +390,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stage_gbs[dom], "peak": peak, "unit": "GB/s",
                 "frac": stage_gbs[dom] / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes[dom], "ms_per_launch": stage_ms[dom]}
+    if dom == "refocus_int":
+        # the stage is not HBM-limited: one shared-memory read per (pixel, view, slice) is what bounds it
+        roofline["on_chip_limiter"] = ("shared-memory wavefronts: LSU data pipe 80-84 % busy in refocus_pxp_kernel "
+                                       "(ncu, profiles/r01b_prof_step.txt; DESIGN.md 4.3)")
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
         with open(tr_path) as f:
@@ -397,9 +401,9 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        t_full, info = cpu_pipeline_sample(w, min(8, n_slices), 1)
+        t_full, info = cpu_pipeline_sample(w, min(8, n_slices), 1, area_div=2)
         cpu_baseline = {"value": n_slices / t_full, "unit": "slices/s", "cores": 1, "kind": "port",
-                        "sample": "numpy oracle, 1 core: 1/4-area crop (%dx%d lenslets), %d of %d slices, extrapolated "
+                        "sample": "numpy oracle, 1 core: 1/2-area crop (%dx%d lenslets), %d of %d slices, extrapolated "
                                   "linearly in lenslets x slices" % (info["lens_grid"][0], info["lens_grid"][1],
                                                                      info["slices"], n_slices),
                         "detail": info}
