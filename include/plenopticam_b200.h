@@ -190,6 +190,28 @@ int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi,
                       float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Global rectification ("next" row; the reference's default smp_meth) — device side of
+ * LfpGlobalResampler (lfp_aligner/lfp_global_resampler.py:32-167).  Matrices and spline operators come from
+ * plenopticam_b200/lfp_aligner/lfp_global_resampler.py (host, float64).
+ *   pcb_image_minmax    : min / max of an image of any element type (clip range of the warp)
+ *   pcb_warp_projective : skimage.transform.warp(img, ProjectiveTransform(tra_mat).inverse, output_shape) (:81-82):
+ *                         (x,y,z) = inv_matrix @ (col,row,1), bilinear, outside = 0, clipped to the input range.
+ *                         inv_matrix_host: 9 doubles, row major.  out: float32 (rows, cols, C).
+ *                         skimage is not installed in the build container: parity of this call is UNPINNED.
+ *   pcb_hex_align       : hexagonal_alignment + hex_stretch + per-strip misc.img_resize (:84-167) for even (py, px):
+ *                         i0/i1/w[nk]: stretch lerp; wx_vals[K][x_len] / wx_first[x_len]: banded x resize of a strip of
+ *                         nk*px samples; wy[y_len][py]: dense y resize; kept columns [crop_lo, crop_lo + out_cols).
+ *                         tmpx: float32 (strips*py, out_cols, C) scratch; out: float32 (strips*y_len, out_cols, C).
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_image_minmax(const void *img, int dtype, int64_t n, pcb_minmax_t *mm, void *stream);
+int pcb_warp_projective(const void *img, int dtype, int H, int W, int C, const double *inv_matrix_host,
+                        int rows, int cols, const pcb_minmax_t *mm, float *out, void *stream);
+int pcb_hex_align(const float *prj, int prows, int pcols, int C, int strips, int py, int px, int hex_odd, int nk,
+                  const int32_t *i0, const int32_t *i1, const float *w,
+                  const float *wx_vals, const int32_t *wx_first, int K, int x_len, int crop_lo, int out_cols,
+                  const float *wy, int y_len, float *tmpx, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Lytro raw bit-unpacking ("next" row) — replaces LfpDecoder.comp_bayer
  * (lfp_reader/lfp_decoder.py:273-326).  buf: packed bytes on the device; bits = cfg.lfpimg['bit'] (10: 5 bytes ->
  * 4 pixels, 12: 3 bytes -> 2 pixels); out: floor(nbytes/5)*4 or floor(nbytes/3)*2 uint16 pixels in file order.

@@ -587,3 +587,190 @@ def comp_bayer(img_buf, shape, bit_pac=10):
     else:
         raise ValueError(bit_pac)
     return px.reshape(shape[1], shape[0]).astype('float')
+
+
+# ------------------------------------------------------------------------------------------------------
+# global resampling (lfp_aligner/lfp_global_resampler.py:32-167, lfp_calibrator/grid_fitter.py)
+# ------------------------------------------------------------------------------------------------------
+def warp_projective(image, inv_matrix, output_shape, cval=0.0):
+    """Restatement of skimage.transform.warp(image, ProjectiveTransform(m).inverse, output_shape=...) with its
+    defaults (order=1, mode='constant', cval=0, clip=True, preserve_range=False) for float64 images.
+
+    scikit-image is an unpinned requirement (`scikit-image>=0.18.0`) that is NOT installed here: PARITY UNPINNED.
+    Published algorithm (skimage/transform/_warps.py, _warps_cy.pyx `_warp_fast`): for output pixel (r, c) the
+    input position is (x, y, z) = inv_matrix @ (c, r, 1), (x/z, y/z); bilinear interpolation between
+    floor/ceil neighbours, neighbours outside the image read `cval`; the result is clipped to the input's value
+    range except pixels that are exactly `cval` when cval lies outside that range (`_clip_warp_output`)."""
+    img = np.asarray(image, dtype=np.float64)
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[..., None]
+    H, W, C = img.shape
+    rows, cols = int(output_shape[0]), int(output_shape[1])
+    rr, cc = np.mgrid[0:rows, 0:cols].astype(np.float64)
+    m = np.asarray(inv_matrix, dtype=np.float64)
+    z = m[2, 0] * cc + m[2, 1] * rr + m[2, 2]
+    x = (m[0, 0] * cc + m[0, 1] * rr + m[0, 2]) / z
+    y = (m[1, 0] * cc + m[1, 1] * rr + m[1, 2]) / z
+    r0, c0 = np.floor(y), np.floor(x)
+    r1, c1 = np.ceil(y), np.ceil(x)
+    dr, dc = y - r0, x - c0
+
+    def get(ri, ci):
+        ok = (ri >= 0) & (ri < H) & (ci >= 0) & (ci < W)
+        v = img[np.clip(ri, 0, H - 1).astype(np.int64), np.clip(ci, 0, W - 1).astype(np.int64)]
+        return np.where(ok[..., None], v, cval)
+
+    top = (1 - dc)[..., None] * get(r0, c0) + dc[..., None] * get(r0, c1)
+    bot = (1 - dc)[..., None] * get(r1, c0) + dc[..., None] * get(r1, c1)
+    out = (1 - dr)[..., None] * top + dr[..., None] * bot
+    mn, mx = img.min(), img.max()
+    preserve = not (mn <= cval <= mx)
+    mask = out == cval
+    out = np.clip(out, mn, mx)
+    if preserve:
+        out[mask] = cval
+    return out[..., 0] if squeeze else out
+
+
+def grid_gen(dims, pat_type='rec', hex_odd=0):
+    """GridFitter.grid_gen (grid_fitter.py:215-256) without normalisation: rows [y, x, ly, lx], centred on 0."""
+    y_range = np.linspace(0, dims[0] - 1, dims[0])
+    x_range = np.linspace(0, dims[1] - 1, dims[1])
+    y_grid, x_grid = np.meshgrid(y_range, x_range)
+    y_idcs, x_idcs = np.meshgrid(y_range.copy(), x_range.copy())
+    if pat_type == 'hex':
+        y_grid = y_grid * (np.sqrt(3) / 2)
+        x_grid[:, int(hex_odd)::2] += .5
+    y_grid = y_grid - y_grid.max() / 2
+    x_grid = x_grid - x_grid.max() / 2
+    return np.vstack(np.dstack([y_grid.T, x_grid.T, y_idcs.T, x_idcs.T]))
+
+
+def apply_projective(p, grid, flip_xy=False):
+    """GridFitter.apply_transform (grid_fitter.py:166-194): returns the grid with projected (y, x) columns."""
+    p = np.array([*p, 1.0]) if len(np.ravel(p)) == 8 else np.array(p, dtype=np.float64)
+    pmat = p.reshape(3, 3).copy()
+    pmat[-1, :] = np.array([*pmat[-1, :2], 1])
+    grid = np.array(grid, dtype=np.float64)
+    pts = np.concatenate((grid[:, :2].T, np.ones(len(grid))[np.newaxis, :]), axis=0)
+    if flip_xy:
+        pts[:2, :] = pts[:2, :][::-1]
+    prj = np.dot(pmat, pts)
+    if flip_xy:
+        prj[:2, :] = prj[:2, :][::-1]
+    grid[:, :2] = np.divide(prj[:2, :], prj[2, :], out=np.zeros(prj[:2, :].shape), where=prj[2, :] != 0).T[:, :2]
+    return grid
+
+
+def grid_fit_pmat(coords, pat_type='rec', hex_odd=0, flip_xy=True):
+    """GridFitter(coords, flip_xy=True).main(); .pmat (grid_fitter.py:88-131,333-340) as used by the global resampler
+    (lfp_global_resampler.py:35-37,72-75): MINPACK Levenberg-Marquardt on the per-point Euclidean distances between
+    the centroids and the projected unit grid.  NOTE the reference constructs GridFitter without pat_type / hex_odd,
+    so the fitted model grid is always RECTANGULAR, also for hexagonal MLAs (:35, :72)."""
+    from scipy.optimize import leastsq
+    coords = np.asarray(coords, dtype=np.float64)
+    dims = [int(max(coords[:, 2]) + 1), int(max(coords[:, 3]) + 1)]
+    if not (dims[0] > 3 and dims[1] > 3):
+        return np.identity(3)
+
+    def cost(p):
+        g = apply_projective(p, grid_gen(dims, 'rec', 0), flip_xy)
+        return np.sqrt(np.sum((coords[:, :2] - g[:, :2]) ** 2, axis=1)).flatten()
+
+    p_init = np.diag([1.0, 1.0, 1.0])
+    p_init[:2, -1] = np.array([0.0, 0.0])
+    coeffs = leastsq(cost, p_init.flatten()[:8])[0]
+    return np.array([*coeffs, 1.0]).reshape(3, 3)
+
+
+def qr_decompose(pmat):
+    """GridFitter.decompose (grid_fitter.py:310-331): (rmat, kmat) from numpy's QR, K scaled to K[2,2] = 1."""
+    rmat, kmat = np.linalg.qr(np.asarray(pmat, dtype=np.float64).reshape(3, -1), mode='reduced')
+    kmat = kmat / kmat[2, 2]
+    if kmat[0, 0] < 0:
+        D = np.diag([-1, -1, 1.0])
+        kmat = np.dot(D, kmat)
+        rmat = np.dot(rmat, D)
+    return rmat, kmat
+
+
+def global_projective_plan(centroids, img_shape, pat_type, hex_odd):
+    """Host part of LfpGlobalResampler.projective_alignment (lfp_global_resampler.py:32-79):
+    (tra_mat, oshape, limg_pitch)."""
+    cent = np.asarray(centroids, dtype=np.float64)
+    pmat_cent = grid_fit_pmat(cent.copy())
+    _, K = qr_decompose(pmat_cent)
+    target = np.array([np.floor(K[1, 1]), np.floor(K[0, 0])])
+    if pat_type == 'rec':
+        target += np.mod(target + 1, 2)
+    elif pat_type == 'hex':
+        target += np.mod(target, 2)
+    pitch = target.astype('int')
+    scales = np.array([pitch[0] / K[1, 1], pitch[1] / K[0, 0]])
+    oshape = np.round(np.array(img_shape[:2]) * scales).astype('int')
+    Kpts = np.diag([pitch[0], pitch[1], K[2, 2]]).astype(np.float64)
+    if pat_type == 'hex':
+        Kpts[0, 0] = Kpts[0, 0] * 2 / np.sqrt(3)
+    dims = [int(max(cent[:, 2]) + 1), int(max(cent[:, 3]) + 1)]
+    grid = apply_projective(Kpts.flatten(), grid_gen(dims, pat_type, hex_odd))
+    shifts = np.zeros(2)
+    crop = pitch // 2
+    shifts[0] = min(grid[:, 0]) - crop[0] if min(grid[:, 0]) - crop[0] < 0 else 0
+    shifts[1] = min(grid[:, 1]) - crop[1] if min(grid[:, 1]) - crop[1] < 0 else 0
+    grid[:, :2] = grid[:, :2] - shifts
+    pmat_grid = grid_fit_pmat(grid.copy())
+    tra_mat = np.dot(pmat_grid, np.linalg.inv(pmat_cent))
+    return tra_mat, oshape, pitch
+
+
+def global_hex_alignment(prj, pitch, LY, LX, hex_odd):
+    """LfpGlobalResampler.hexagonal_alignment + hex_stretch (lfp_global_resampler.py:84-167) for pat_type 'hex':
+    returns (aligned float64, new odd pitch)."""
+    prj = np.asarray(prj, dtype=np.float64)
+    py, px = int(pitch[0]), int(pitch[1])
+    C = prj.shape[2]
+    lens_new_x = int(round(LX * 2 / np.sqrt(3)))
+    pad_zro = np.zeros([py, px, C])
+    pad_hlf = np.zeros([py, px // 2, C])
+    lnew = np.array([py, px]) + np.mod(np.array([py, px]) + 1, 2)
+    out = np.zeros([int((LY - 1) * (py + 1)), int(lens_new_x * (px + 1)), C])
+    sw = bool(hex_odd)
+    cut = (-px) // 2                                         # `:-self._limg_pitch[1]//2` (:113, :122)
+    coords = np.linspace(0, LX, lens_new_x)
+    Wy = spline_resize_matrix(py, int(round(py * (lnew[0] / py))))
+    Wx = None
+    for ly in range(LY - 1):
+        if sw:
+            row_a = np.hstack([pad_hlf, prj[ly * py:(ly + 1) * py, :cut, :]])
+            row_b = prj[(ly + 1) * py:(ly + 2) * py, ...]
+            row_c = np.hstack([row_a[:, px:, :], pad_zro])
+        else:
+            row_a = prj[ly * py:(ly + 1) * py, ...]
+            row_b = np.hstack([pad_hlf, prj[(ly + 1) * py:(ly + 2) * py, :cut, :]])
+            row_c = np.hstack([row_b[:, px:, :], pad_zro])
+        row = np.mean(np.concatenate([row_a[..., None], row_b[..., None], row_c[..., None]], axis=-1), axis=-1)
+        stack = np.zeros([py, lens_new_x * px, C])
+        for y in range(py):
+            for x in range(px):
+                pos = row[y, x::px, :]
+                for c in range(C):
+                    stack[y, x::px, c] = np.interp(coords, range(LX), pos[:LX, c])
+        if Wx is None:
+            Wx = spline_resize_matrix(stack.shape[1], int(round(stack.shape[1] * (lnew[1] / px))))
+        out[ly * (py + 1):(ly + 1) * (py + 1), ...] = np.einsum('yn,nmc,xm->yxc', Wy, stack, Wx, optimize=True)
+        sw = not sw
+    return out[:, lnew[1] // 2 + 1:(-lnew[1]) // 2, :], lnew
+
+
+def resample_global(raw, centroids, pat_type, hex_odd=None):
+    """LfpResampler with smp_meth='global' before the uint16 quantisation: (aligned float64, micro-image pitch)."""
+    cent = np.asarray(centroids, dtype=np.float64)
+    if hex_odd is None:
+        hex_odd = get_hex_direction(cent)
+    LY, LX = int(cent[:, 2].max() + 1), int(cent[:, 3].max() + 1)
+    tra, oshape, pitch = global_projective_plan(cent, np.asarray(raw).shape, pat_type, hex_odd)
+    prj = warp_projective(np.asarray(raw).astype('float64'), np.linalg.inv(tra), oshape)
+    if pat_type == 'rec':
+        return prj, pitch
+    return global_hex_alignment(prj, pitch, LY, LX, hex_odd)

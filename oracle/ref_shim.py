@@ -111,6 +111,26 @@ def load_reference():
     import scipy.interpolate as si
     si.interp2d = _interp2d_replacement
 
+    # skimage is absent: the global resampler's only use of it (lfp_global_resampler.py:81-82) gets the oracle's
+    # restatement of transform.warp / ProjectiveTransform (PARITY UNPINNED for that one call, see oracle_np.py)
+    sk = sys.modules.get("skimage.transform")
+    if sk is not None and "_pcb_standin" not in vars(sk) and type(sk).__name__ == "_Anything":
+        from oracle import oracle_np as _onp
+
+        class _Projective(object):
+            def __init__(self, matrix=None):
+                self.params = np.eye(3) if matrix is None else np.asarray(matrix, dtype=np.float64)
+
+            @property
+            def inverse(self):
+                return _Projective(np.linalg.inv(self.params))
+
+        sk.ProjectiveTransform = _Projective
+        sk.warp = lambda image, inverse_map, output_shape=None, **k: _onp.warp_projective(
+            image, inverse_map.params, output_shape if output_shape is not None else image.shape[:2])
+        sk._pcb_standin = True
+        sys.modules["skimage"].transform = sk
+
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import warnings

@@ -1,0 +1,152 @@
+// Global light-field rectification ("next" row; the reference's default smp_meth) —
+// device side of LfpGlobalResampler (lfp_aligner/lfp_global_resampler.py:32-167):
+//
+//   warp_projective_kernel   skimage.transform.warp(img, ProjectiveTransform(tra_mat).inverse, output_shape)   (:81-82)
+//                            order 1, mode 'constant', cval 0, clip to the input range (published algorithm,
+//                            skimage is not installed here: PARITY UNPINNED, see oracle_np.py::warp_projective)
+//   hex_strip_x_kernel       per lens-row strip: mean of the three half-pitch-shifted rows (:108-128), the
+//                            2/sqrt(3) stretch along the lens axis (np.interp, :151-167) and the x half of the bicubic
+//                            strip resize (misc.img_resize, :134-137) as a banded operator, cropped (:146)
+//   hex_strip_y_kernel       the y half of the strip resize (py -> py+1 rows)
+// The matrices and spline operators are prepared on the host in float64 (lfp_aligner/lfp_global_resampler.py).
+#pragma once
+#include "common.cuh"
+
+namespace pcb {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+image_minmax_kernel(const T *__restrict__ data, int64_t n, pcb_minmax_t *mm) {
+    float mn = INFINITY, mx = -INFINITY;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = ld_as_float(data + i);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    block_minmax_commit(mn, mx, mm);
+}
+
+struct WarpMat { double m[9]; };     // inverse map: (x, y, z) = m @ (col, row, 1) of the OUTPUT pixel
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+warp_projective_kernel(const T *__restrict__ img, int H, int W, int C, WarpMat wm, int rows, int cols,
+                       const pcb_minmax_t *__restrict__ mm, float *__restrict__ out) {
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const float lo = key_to_float(mm->kmin), hi = key_to_float(mm->kmax);
+    const bool preserve = !(lo <= 0.f && 0.f <= hi);          // cval = 0 outside the input range stays 0
+    const double z = wm.m[6] * c + wm.m[7] * r + wm.m[8];
+    const double x = (wm.m[0] * c + wm.m[1] * r + wm.m[2]) / z;
+    const double y = (wm.m[3] * c + wm.m[4] * r + wm.m[5]) / z;
+    const double fr = floor(y), fc = floor(x);
+    const int r0 = (int)fr, c0 = (int)fc, r1 = (int)ceil(y), c1 = (int)ceil(x);
+    const float dr = (float)(y - fr), dc = (float)(x - fc);
+    const bool okr0 = r0 >= 0 && r0 < H, okr1 = r1 >= 0 && r1 < H, okc0 = c0 >= 0 && c0 < W, okc1 = c1 >= 0 && c1 < W;
+    float *o = out + ((size_t)r * cols + c) * C;
+    for (int ch = 0; ch < C; ++ch) {
+        const float v00 = okr0 && okc0 ? ld_as_float(img + ((size_t)r0 * W + c0) * C + ch) : 0.f;
+        const float v01 = okr0 && okc1 ? ld_as_float(img + ((size_t)r0 * W + c1) * C + ch) : 0.f;
+        const float v10 = okr1 && okc0 ? ld_as_float(img + ((size_t)r1 * W + c0) * C + ch) : 0.f;
+        const float v11 = okr1 && okc1 ? ld_as_float(img + ((size_t)r1 * W + c1) * C + ch) : 0.f;
+        const float top = (1.f - dc) * v00 + dc * v01;
+        const float bot = (1.f - dc) * v10 + dc * v11;
+        float v = (1.f - dr) * top + dr * bot;
+        if (!(preserve && v == 0.f)) v = fminf(fmaxf(v, lo), hi);
+        o[ch] = v;
+    }
+}
+
+// ---- hexagonal alignment -----------------------------------------------------------------------------------------
+struct HexArgs {
+    const float *prj;      // (prows, pcols, C) rectified image
+    int prows, pcols, C;
+    int strips;            // LY - 1
+    int py, px;            // even micro-image pitch of the rectified image
+    int hex_odd;
+    int nk;                // lens_new_x: lens columns after the stretch
+    const int32_t *i0, *i1;   // [nk] source lens columns of stretched column k
+    const float *w;        // [nk] lerp weight
+    const float *wx_vals;  // [K][x_len] banded x-resize operator, tap major
+    const int32_t *wx_first;  // [x_len]
+    int K, x_len;
+    int crop_lo, out_cols; // kept columns [crop_lo, crop_lo + out_cols) of the resized strip
+    const float *wy;       // [y_len][py] dense y-resize operator
+    int y_len;             // py + 1
+};
+
+// merged lens row: mean of row a, row b (one of them shifted right by half a pitch) and the shifted one a full
+// pitch further (lfp_global_resampler.py:108-128)
+__device__ __forceinline__ float hex_merged(const float *A, const float *B, bool sw, int X, int h, int px, int Wp, int C,
+                                            int ch) {
+    const float *S = sw ? A : B;       // the row that is shifted right by h pixels
+    const float *U = sw ? B : A;       // the unshifted row
+    const float s0 = (X >= h && X < Wp) ? S[(size_t)(X - h) * C + ch] : 0.f;
+    const float u0 = X < Wp ? U[(size_t)X * C + ch] : 0.f;
+    const int X2 = X + px;
+    const float s1 = (X2 < Wp && X2 >= h) ? S[(size_t)(X2 - h) * C + ch] : 0.f;
+    return (s0 + u0 + s1) / 3.f;
+}
+
+constexpr int HX_THREADS = 512;
+
+// grid (py, strips): one CTA per image row of a strip
+__global__ void __launch_bounds__(HX_THREADS)
+hex_strip_x_kernel(HexArgs p, float *__restrict__ tmpx /* (strips*py, out_cols, C) */) {
+    extern __shared__ __align__(16) float s_row[];            // [nk*px*C] merged + stretched row
+    const int y = blockIdx.x, ly = blockIdx.y;
+    const int C = p.C;
+    const bool sw = ((p.hex_odd + ly) & 1) != 0;
+    const int ra = ly * p.py + y, rb = (ly + 1) * p.py + y;
+    const float *A = p.prj + (size_t)min(ra, p.prows - 1) * p.pcols * C;
+    const float *B = p.prj + (size_t)min(rb, p.prows - 1) * p.pcols * C;
+    const bool rows_ok = rb < p.prows;
+    const int h = p.px / 2;
+    const int mE = p.nk * p.px * C;
+    for (int e = threadIdx.x; e < mE; e += HX_THREADS) {
+        const int X = e / C, ch = e - X * C;
+        const int k = X / p.px, x = X - k * p.px;
+        const int xa = x + __ldg(p.i0 + k) * p.px, xb = x + __ldg(p.i1 + k) * p.px;
+        const float wk = __ldg(p.w + k);
+        float va = 0.f, vb = 0.f;
+        if (rows_ok) {
+            va = hex_merged(A, B, sw, xa, h, p.px, p.pcols, C, ch);
+            vb = hex_merged(A, B, sw, xb, h, p.px, p.pcols, C, ch);
+        }
+        s_row[e] = va + (vb - va) * wk;                        // np.interp
+    }
+    __syncthreads();
+    float *dst = tmpx + (size_t)(ly * p.py + y) * p.out_cols * C;
+    for (int xo = threadIdx.x; xo < p.out_cols; xo += HX_THREADS) {
+        const int X = xo + p.crop_lo;
+        const float *px_ = s_row + (size_t)__ldg(p.wx_first + X) * C;
+        for (int ch = 0; ch < C; ++ch) {
+            float acc = 0.f;
+            for (int k = 0; k < p.K; ++k) acc = fmaf(__ldg(p.wx_vals + (size_t)k * p.x_len + X), px_[k * C + ch], acc);
+            dst[(size_t)xo * C + ch] = acc;
+        }
+    }
+}
+
+// grid (ceil(out_cols*C / 256), strips): thread = one (x, c) element of a strip, all y_len output rows
+constexpr int HX_MAXPY = 64;
+__global__ void __launch_bounds__(256)
+hex_strip_y_kernel(HexArgs p, const float *__restrict__ tmpx, float *__restrict__ out /* (strips*y_len, out_cols, C) */) {
+    const int ly = blockIdx.y;
+    const int E = p.out_cols * p.C;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    float v[HX_MAXPY];
+#pragma unroll 4
+    for (int y = 0; y < p.py; ++y) v[y] = __ldg(tmpx + (size_t)(ly * p.py + y) * E + e);
+    for (int yo = 0; yo < p.y_len; ++yo) {
+        const float *wrow = p.wy + (size_t)yo * p.py;
+        float acc = 0.f;
+        for (int y = 0; y < p.py; ++y) acc = fmaf(__ldg(wrow + y), v[y], acc);
+        out[(size_t)(ly * p.y_len + yo) * E + e] = acc;
+    }
+}
+
+}  // namespace pcb

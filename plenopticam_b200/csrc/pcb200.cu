@@ -12,6 +12,7 @@
 #include "refine.cuh"
 #include "resample.cuh"
 #include "resample_col.cuh"
+#include "global_resample.cuh"
 #include "rotate.cuh"
 #include "viewpoints.cuh"
 
@@ -372,6 +373,61 @@ int pcb_devig_divide(const void *lfp, int dtype, int64_t npx, int C, const doubl
     case PCB_F64: return devig_divide_out<double>(lfp, npx, C, wn, out, out_dtype, st);
     }
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
+int pcb_image_minmax(const void *img, int dtype, int64_t n, pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(img != nullptr && mm != nullptr && n > 0, "img, mm, n > 0");
+    cudaStream_t st = as_stream(stream);
+    const int g = grid_for(n, 256 * 8);
+    switch (dtype) {
+    case PCB_U16: image_minmax_kernel<uint16_t><<<g, 256, 0, st>>>((const uint16_t *)img, n, mm); break;
+    case PCB_F32: image_minmax_kernel<float><<<g, 256, 0, st>>>((const float *)img, n, mm); break;
+    case PCB_U8:  image_minmax_kernel<uint8_t><<<g, 256, 0, st>>>((const uint8_t *)img, n, mm); break;
+    default: return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+    }
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+int pcb_warp_projective(const void *img, int dtype, int H, int W, int C, const double *inv_matrix_host, int rows,
+                        int cols, const pcb_minmax_t *mm, float *out, void *stream) {
+    PCB_REQUIRE(img != nullptr && inv_matrix_host != nullptr && mm != nullptr && out != nullptr, "pointers");
+    PCB_REQUIRE(H > 0 && W > 0 && C > 0 && rows > 0 && rows <= 65535 && cols > 0, "sizes");
+    cudaStream_t st = as_stream(stream);
+    WarpMat wm;
+    for (int k = 0; k < 9; ++k) wm.m[k] = inv_matrix_host[k];
+    dim3 grid((cols + 255) / 256, rows);
+    switch (dtype) {
+    case PCB_U16: warp_projective_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)img, H, W, C, wm, rows, cols, mm, out); break;
+    case PCB_F32: warp_projective_kernel<float><<<grid, 256, 0, st>>>((const float *)img, H, W, C, wm, rows, cols, mm, out); break;
+    case PCB_U8:  warp_projective_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)img, H, W, C, wm, rows, cols, mm, out); break;
+    default: return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+    }
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+int pcb_hex_align(const float *prj, int prows, int pcols, int C, int strips, int py, int px, int hex_odd, int nk,
+                  const int32_t *i0, const int32_t *i1, const float *w, const float *wx_vals, const int32_t *wx_first,
+                  int K, int x_len, int crop_lo, int out_cols, const float *wy, int y_len, float *tmpx, float *out,
+                  void *stream) {
+    PCB_REQUIRE(prj && i0 && i1 && w && wx_vals && wx_first && wy && tmpx && out, "pointers");
+    PCB_REQUIRE(prows > 0 && pcols > 0 && C > 0 && strips > 0 && strips <= 65535 && py >= 4 && py <= HX_MAXPY &&
+                px >= 2 && px % 2 == 0 && nk > 0 && K > 0 && x_len > 0 && crop_lo >= 0 && out_cols > 0 &&
+                crop_lo + out_cols <= x_len && y_len > 0, "sizes (even px, 4 <= py <= 64)");
+    HexArgs a;
+    a.prj = prj; a.prows = prows; a.pcols = pcols; a.C = C; a.strips = strips; a.py = py; a.px = px;
+    a.hex_odd = hex_odd ? 1 : 0; a.nk = nk; a.i0 = i0; a.i1 = i1; a.w = w; a.wx_vals = wx_vals; a.wx_first = wx_first;
+    a.K = K; a.x_len = x_len; a.crop_lo = crop_lo; a.out_cols = out_cols; a.wy = wy; a.y_len = y_len;
+    const size_t smem = (size_t)nk * px * C * sizeof(float);
+    if (smem > 220 * 1024) return fail(PCB_ERR_UNSUPPORTED, "%s: a stretched lens row does not fit shared memory", __func__);
+    cudaStream_t st = as_stream(stream);
+    PCB_CUDA(cudaFuncSetAttribute(hex_strip_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hex_strip_x_kernel<<<dim3(py, strips), HX_THREADS, smem, st>>>(a, tmpx);
+    PCB_LAUNCH_OK();
+    hex_strip_y_kernel<<<dim3((out_cols * C + 255) / 256, strips), 256, 0, st>>>(a, tmpx, out);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
 }
 
 int pcb_unpack_bayer(const uint8_t *buf, int64_t nbytes, int bits, uint16_t *out, void *stream) {

@@ -3,9 +3,10 @@ cfg side effects and `lfp_img_align.pkl` checkpoint as the reference
 (lfp_aligner/lfp_resampler.py:11-78, lfp_aligner/lfp_local_resampler.py:11-148), with the per-lenslet
 interp2d / np.interp loops replaced by two launches of the sm_100a resampling kernel.
 
-Only the centroid-based `smp_meth='local'` resampler with `method='linear'` is offered (the only method
-reachable from LfpAligner, lfp_aligner/top_level.py:74); 'global' is a later row of SURVEY §8(f) and is
-rejected loudly rather than silently substituted.
+`smp_meth='local'` is the centroid-based resampler of the hot path (`method='linear'`, the only method reachable
+from LfpAligner, lfp_aligner/top_level.py:74); `smp_meth='global'` (the reference's default,
+lfp_aligner/lfp_global_resampler.py) is the projective rectification + hexagonal row merge, planned on the host in
+float64 (lfp_global_resampler.py here) and evaluated on the device.
 """
 import os
 import pickle
@@ -41,9 +42,8 @@ class LfpResampler(LfpMicroLenses):
 
         meth = self.cfg.params[self.cfg.smp_meth]
         if meth == 'global' or not meth:
-            raise NotImplementedError("smp_meth='global' (lfp_aligner/lfp_global_resampler.py) is not part of the "
-                                      "B200 hot path; set cfg.params['smp_meth'] = 'local'")
-        if meth == 'local':
+            self.global_resampling()
+        elif meth == 'local':
             self.local_resampling()
         if meth not in SMPL_METH and meth:
             self.sta.status_msg('Resampling method %s unrecognized.' % meth, prnt)
@@ -70,6 +70,34 @@ class LfpResampler(LfpMicroLenses):
         tabs = ops.LensTables(tables)
         raw = img if hasattr(img, 'is_cuda') else ops.to_device(img, exact_u16=True)
         self._dev_align, mm = ops.resample_u16(raw, tabs, flip=self._flip)
+        self._mm_dev = mm
+        self.sta.progress(100, prnt)
+        return True
+
+    def global_resampling(self):
+        """LfpGlobalResampler.global_resampling (lfp_global_resampler.py:20-30): projective rectification of the
+        whole exposure, then (hex) row merge / stretch / odd-pitch resize; quantised to uint16 on the device."""
+        from . import lfp_global_resampler as glob
+        if self.sta.interrupt:
+            return False
+        prnt = self.cfg.params[self.cfg.opt_prnt]
+        pat = self.cfg.calibs[self.cfg.pat_type]
+        img = self._lfp_img
+        if getattr(img, 'ndim', 0) != 3 and not (hasattr(img, 'dim') and img.dim() == 3):
+            raise IndexError('LfpResampler needs a (H, W, C) image')
+        tra, oshape, pitch = glob.projective_plan(self._CENTROIDS, tuple(img.shape), pat, self._hex_odd)
+        self._limg_pitch = np.asarray(pitch).astype('int')
+        raw = img if hasattr(img, 'is_cuda') else ops.to_device(img, exact_u16=True)
+        prj = ops.warp_projective(raw, tra, oshape)
+        if pat == 'hex':
+            if 0 in self._limg_pitch:
+                raise Exception('Micro image size cannot be zero.')
+            plan = glob.hex_plan(pitch, self._LENS_Y_MAX, self._LENS_X_MAX, int(prj.shape[1]), self._hex_odd)
+            prj = ops.hex_align(prj, plan, self._LENS_Y_MAX)
+            self._limg_pitch = np.asarray(plan["lnew"]).astype('int')
+        self._dev_align_f32 = prj
+        mm = ops.minmax_f32(prj)
+        self._dev_align = ops.quantize_u16(prj, mm)
         self._mm_dev = mm
         self.sta.progress(100, prnt)
         return True

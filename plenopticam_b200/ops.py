@@ -433,3 +433,40 @@ def scheimpflug(stack, direction):
                                         _ptr(out), _stream()))
     mm = minmax_f32(out)
     return out, quantize_u16(out, mm)
+
+
+# ------------------------------------------------------------------------------------------------------
+# global rectification (lfp_aligner/lfp_global_resampler.py)
+# ------------------------------------------------------------------------------------------------------
+def warp_projective(img, tra_mat, oshape):
+    """skimage.transform.warp(img, ProjectiveTransform(tra_mat).inverse, output_shape=oshape) -> float32 (rows, cols, C)."""
+    _chk_dev(img)
+    H, W, Cn = (int(v) for v in img.shape)
+    rows, cols = int(oshape[0]), int(oshape[1])
+    L, st = nat.lib(), _stream()
+    mm = new_minmax()
+    nat.check(L.pcb_image_minmax(_ptr(img), _pcb_dtype(img), img.numel(), _ptr(mm), st))
+    inv = np.ascontiguousarray(np.linalg.inv(np.asarray(tra_mat, dtype=np.float64)))
+    out = torch.empty((rows, cols, Cn), dtype=torch.float32, device=img.device)
+    nat.check(L.pcb_warp_projective(_ptr(img), _pcb_dtype(img), H, W, Cn, inv.ctypes.data_as(C.POINTER(C.c_double)),
+                                    rows, cols, _ptr(mm), _ptr(out), st))
+    return out
+
+
+def hex_align(prj, plan, LY):
+    """hexagonal_alignment of the rectified image with the host plan of lfp_global_resampler.hex_plan."""
+    _chk_dev(prj)
+    dev = prj.device
+    prows, pcols, Cn = (int(v) for v in prj.shape)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    i0, i1, w = t(plan["i0"]), t(plan["i1"]), t(plan["w"])
+    wxv, wxf, wy = t(plan["wx_vals"]), t(plan["wx_first"]), t(plan["wy"])
+    strips = int(LY) - 1
+    out_cols = plan["x_len"] + plan["crop_hi"] - plan["crop_lo"]
+    tmpx = torch.empty((strips * plan["py"], out_cols, Cn), dtype=torch.float32, device=dev)
+    out = torch.empty((strips * plan["y_len"], out_cols, Cn), dtype=torch.float32, device=dev)
+    nat.check(nat.lib().pcb_hex_align(_ptr(prj), prows, pcols, Cn, strips, plan["py"], plan["px"], plan["hex_odd"],
+                                      plan["lens_new_x"], _ptr(i0), _ptr(i1), _ptr(w), _ptr(wxv), _ptr(wxf),
+                                      int(plan["wx_vals"].shape[0]), plan["x_len"], plan["crop_lo"], out_cols, _ptr(wy),
+                                      plan["y_len"], _ptr(tmpx), _ptr(out), _stream()))
+    return out
