@@ -113,6 +113,9 @@ int pcb_viewpoints(const void *aligned, int dtype, int rows, int cols, int C, in
 int pcb_viewpoints_inverse(const void *vp, int dtype, int M, int S, int T, int C, void *aligned, void *stream);
 int pcb_crop_micro_images(const void *aligned, int dtype, int rows, int cols, int C, int M_in, int M_out,
                           void *cropped, void *stream);
+/* non-square micro images (My_in x Mx_in), e.g. the 13 x 15 pitch of a globally rectified hexagonal light field */
+int pcb_crop_micro_images_yx(const void *aligned, int dtype, int rows, int cols, int C, int My_in, int Mx_in,
+                             int M_out, void *cropped, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (c) Shift-and-sum refocus — replaces LfpShiftAndSum.refo_from_vp without refinement

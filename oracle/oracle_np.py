@@ -269,16 +269,18 @@ def rotate_centroids(centroids, rad, shape):
 # lfp_extractor — K4, K5, K6
 # ----------------------------------------------------------------------------------------------------
 def crop_micro_images(aligned, M_in, M_out):
-    """lfp_cropper.py:34,46-62 — central crop of every micro image, margin k = (M_in - M_out)//2."""
+    """lfp_cropper.py:34,46-62 — central crop of every micro image, margins k = (pitch - M_out)//2 per axis;
+    `M_in` is the aligned pitch, a scalar or (My, Mx) (globally rectified hex light fields are not square)."""
     aligned = np.asarray(aligned)
-    if M_out == M_in:
+    My, Mx = (int(M_in), int(M_in)) if np.ndim(M_in) == 0 else (int(M_in[0]), int(M_in[1]))
+    if M_out == My and M_out == Mx:
         return aligned
-    k = (M_in - M_out) // 2
-    LY, LX = aligned.shape[0] // M_in, aligned.shape[1] // M_in
-    a = aligned[:LY * M_in, :LX * M_in].reshape(LY, M_in, LX, M_in, -1)
+    ky, kx = (My - M_out) // 2, (Mx - M_out) // 2
+    LY, LX = aligned.shape[0] // My, aligned.shape[1] // Mx
+    a = aligned[:LY * My, :LX * Mx].reshape(LY, My, LX, Mx, -1)
     # reference slice: [k + l*M_in : (l+1)*M_in - k] assigned into an M_out-long slot (:60-62);
     # shapes only agree when M_in - 2k == M_out, i.e. equal parity.
-    a = a[:, k:M_in - k, :, k:M_in - k]
+    a = a[:, ky:My - ky, :, kx:Mx - kx]
     return a.reshape(LY * M_out, LX * M_out, aligned.shape[2] if aligned.ndim == 3 else 1)
 
 

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "pcb_viewpoints": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pcb_viewpoints_inverse": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pcb_crop_micro_images": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pcb_crop_micro_images_yx": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pcb_refocus_int_scratch_bytes": (_i64, [_i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pcb_refocus_int": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "pcb_refocus_int_direct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),

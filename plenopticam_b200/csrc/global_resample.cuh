@@ -3,7 +3,7 @@
 //
 //   warp_projective_kernel   skimage.transform.warp(img, ProjectiveTransform(tra_mat).inverse, output_shape)   (:81-82)
 //                            order 1, mode 'constant', cval 0, clip to the input range (published algorithm,
-//                            skimage is not installed here: PARITY UNPINNED, see oracle_np.py::warp_projective)
+//                            skimage is not installed here: PARITY UNPINNED)
 //   hex_strip_x_kernel       per lens-row strip: mean of the three half-pitch-shifted rows (:108-128), the
 //                            2/sqrt(3) stretch along the lens axis (np.interp, :151-167) and the x half of the bicubic
 //                            strip resize (misc.img_resize, :134-137) as a banded operator, cropped (:146)

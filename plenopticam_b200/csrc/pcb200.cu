@@ -175,7 +175,17 @@ int pcb_crop_micro_images(const void *aligned, int dtype, int rows, int cols, in
     PCB_REQUIRE(aligned != nullptr && cropped != nullptr, "aligned, cropped");
     PCB_REQUIRE(rows > 0 && cols > 0 && C > 0 && M_in > 0 && M_out > 0 && M_out <= M_in, "sizes, M_out <= M_in");
     PCB_REQUIRE((M_in - M_out) % 2 == 0, "M_in - M_out even (lfp_cropper.py:34,60-62)");
-    PCB_DISPATCH_COPY_DTYPE(dtype, launch_crop, aligned, cropped, rows, cols, C, M_in, M_out, as_stream(stream));
+    PCB_DISPATCH_COPY_DTYPE(dtype, launch_crop, aligned, cropped, rows, cols, C, M_in, M_in, M_out, as_stream(stream));
+}
+
+int pcb_crop_micro_images_yx(const void *aligned, int dtype, int rows, int cols, int C, int My_in, int Mx_in, int M_out,
+                             void *cropped, void *stream) {
+    PCB_REQUIRE(aligned != nullptr && cropped != nullptr, "aligned, cropped");
+    PCB_REQUIRE(rows > 0 && cols > 0 && C > 0 && My_in > 0 && Mx_in > 0 && M_out > 0 && M_out <= My_in && M_out <= Mx_in,
+                "sizes, M_out <= My_in, Mx_in");
+    PCB_REQUIRE((My_in - M_out) % 2 == 0 && (Mx_in - M_out) % 2 == 0, "even margins (lfp_cropper.py:34,60-62)");
+    PCB_REQUIRE(rows / My_in > 0 && cols / Mx_in > 0, "at least one micro image");
+    PCB_DISPATCH_COPY_DTYPE(dtype, launch_crop, aligned, cropped, rows, cols, C, My_in, Mx_in, M_out, as_stream(stream));
 }
 
 // Planning shared by pcb_refocus_int_scratch_bytes and pcb_refocus_int (host-only, deterministic).

@@ -82,21 +82,23 @@ viewpoints_inverse_kernel(const T *__restrict__ vp, T *__restrict__ aligned, int
     for (int idx = threadIdx.x; idx < n_out; idx += blockDim.x) dst[idx] = row[idx];
 }
 
+// micro images of (My_in x Mx_in) pixels -> central (M_out x M_out), margins ky / kx (lfp_cropper.py:34,58-62; the
+// globally rectified hexagonal light field has a non-square pitch, e.g. 13 x 15)
 template <typename T>
 __global__ void __launch_bounds__(256)
-crop_kernel(const T *__restrict__ aligned, T *__restrict__ cropped, int cols_elems_in, int M_in, int M_out, int kc,
-            int LX, int C) {
+crop_kernel(const T *__restrict__ aligned, T *__restrict__ cropped, int cols_elems_in, int My_in, int Mx_in, int M_out,
+            int ky, int kx, int LX, int C) {
     // one CTA per output row
     const int orow = blockIdx.x;
     const int ly = orow / M_out, v = orow - ly * M_out;
-    const T *src = aligned + (size_t)(ly * M_in + kc + v) * cols_elems_in;
+    const T *src = aligned + (size_t)(ly * My_in + ky + v) * cols_elems_in;
     T *dst = cropped + (size_t)orow * ((size_t)LX * M_out * C);
     const int n = LX * M_out * C;
     const int mc = M_out * C;
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         const int lx = idx / mc;
         const int rem = idx - lx * mc;   // u*C + c
-        dst[idx] = __ldg(src + (lx * M_in + kc) * C + rem);
+        dst[idx] = __ldg(src + (lx * Mx_in + kx) * C + rem);
     }
 }
 
@@ -150,10 +152,11 @@ static int launch_viewpoints_inverse(const void *vp, void *aligned, int M, int S
 }
 
 template <typename T>
-static int launch_crop(const void *aligned, void *cropped, int rows, int cols, int C, int M_in, int M_out,
+static int launch_crop(const void *aligned, void *cropped, int rows, int cols, int C, int My_in, int Mx_in, int M_out,
                        cudaStream_t st) {
-    const int LY = rows / M_in, LX = cols / M_in, kc = (M_in - M_out) / 2;
-    crop_kernel<T><<<LY * M_out, 256, 0, st>>>((const T *)aligned, (T *)cropped, cols * C, M_in, M_out, kc, LX, C);
+    const int LY = rows / My_in, LX = cols / Mx_in;
+    crop_kernel<T><<<LY * M_out, 256, 0, st>>>((const T *)aligned, (T *)cropped, cols * C, My_in, Mx_in, M_out,
+                                              (My_in - M_out) / 2, (Mx_in - M_out) / 2, LX, C);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }

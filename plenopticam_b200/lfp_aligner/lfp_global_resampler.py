@@ -7,9 +7,10 @@ transfer matrix onto an ideal grid with an integer micro-image pitch, warps the 
 resizes every row strip to an odd pitch with a bicubic spline.  Everything per-camera (grid fit, matrices, spline
 operators) is prepared here in float64; the per-pixel work runs on the device (csrc/global_resample.cuh).
 
-scikit-image is not installed in the build container, so `transform.warp` could not be run as an oracle: the warp
-follows its published algorithm (see oracle/oracle_np.py::warp_projective) and its parity is UNPINNED; everything
-else on this path is pinned against the unmodified reference (tests/test_global_resampler.py).
+scikit-image is not installed in the build container, so `transform.warp` itself could not be run for comparison:
+the warp follows its published algorithm (order 1, mode 'constant', cval 0, clip to the input range) and its
+parity is UNPINNED; everything else on this path is pinned against the unmodified reference
+(tests/test_global_resampler.py).
 """
 import numpy as np
 import scipy.sparse.linalg as spla
@@ -145,9 +146,9 @@ def spline_resize_dense(n_in, n_out):
     """Same operator as a dense (n_out, n_in) float64 matrix (small axes only)."""
     x = np.arange(n_in, dtype=np.float64)
     t = np.concatenate([[x[0]] * 4, x[2:-2], [x[-1]] * 4])
-    colloc = BSpline.design_matrix(x, t, 3).toarray()
+    colloc = BSpline.design_matrix(x, t, 3).tocsc()
     ev = BSpline.design_matrix(np.linspace(0, n_in - 1, n_out), t, 3).toarray()
-    return np.linalg.solve(colloc.T, ev.T).T
+    return spla.splu(colloc.T.tocsc()).solve(ev.T).T
 
 
 def hex_plan(pitch, LY, LX, prj_cols, hex_odd):

@@ -21,13 +21,14 @@ class LfpCropper(LfpMicroLenses):
             return False
         M_out = self._size_pitch
         if M_out < self._limg_pitch[0] or M_out < self._limg_pitch[1]:
-            if self._limg_pitch[0] != self._limg_pitch[1] or (self._limg_pitch[0] - M_out) % 2:
-                # the reference's slice assignment (:60-62) raises a broadcast ValueError in these cases
-                raise ValueError('could not crop micro images of size %s to %d' % (tuple(self._limg_pitch), M_out))
+            if (self._limg_pitch[0] - M_out) % 2 or (self._limg_pitch[1] - M_out) % 2 or M_out > min(self._limg_pitch):
+                # an odd margin makes the reference's slice assignment (:60-62) raise a broadcast ValueError
+                raise ValueError('could not broadcast input array: micro images of size %s cannot be cropped to %d'
+                                 % (tuple(int(v) for v in self._limg_pitch), M_out))
             self.sta.status_msg('Render angular domain', self.cfg.params[self.cfg.opt_prnt])
             src = self._lfp_img_align
             dev = src if hasattr(src, 'is_cuda') else ops.to_device(src if src.ndim == 3 else src[..., None])
-            self._dev_out = ops.crop_micro_images(dev, int(self._limg_pitch[0]), int(M_out))
+            self._dev_out = ops.crop_micro_images(dev, (int(self._limg_pitch[0]), int(self._limg_pitch[1])), int(M_out))
             self.new_lfp_img = self._dev_out if hasattr(src, 'is_cuda') else ops.to_host(self._dev_out)
             self.sta.progress(100, self.cfg.params[self.cfg.opt_prnt])
         elif M_out == min(self._limg_pitch):

@@ -209,12 +209,14 @@ def viewpoints_inverse(vp):
 
 
 def crop_micro_images(aligned, M_in, M_out):
+    """Central M_out x M_out crop of every micro image; M_in is the aligned pitch, a scalar or (My, Mx)."""
     _chk_dev(aligned)
     rows, cols, Cn = aligned.shape
-    LY, LX = rows // M_in, cols // M_in
+    My, Mx = (int(M_in), int(M_in)) if np.ndim(M_in) == 0 else (int(M_in[0]), int(M_in[1]))
+    LY, LX = rows // My, cols // Mx
     out = torch.empty((LY * M_out, LX * M_out, Cn), dtype=aligned.dtype, device=aligned.device)
-    nat.check(nat.lib().pcb_crop_micro_images(_ptr(aligned), _pcb_dtype(aligned), rows, cols, Cn, M_in, M_out,
-                                              _ptr(out), _stream()))
+    nat.check(nat.lib().pcb_crop_micro_images_yx(_ptr(aligned), _pcb_dtype(aligned), rows, cols, Cn, My, Mx, M_out,
+                                                 _ptr(out), _stream()))
     return out
 
 

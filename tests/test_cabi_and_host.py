@@ -212,6 +212,9 @@ def test_unsupported_paths_fail_loudly():
     cfg, sta = make_cfg(cent, 'rec', 7)
     with pytest.raises(NotImplementedError):
         LfpResampler(lfp_img=np.zeros((50, 50, 3)), cfg=cfg, sta=sta, method='cubic')
-    cfg.params[cfg.smp_meth] = 'global'
-    with pytest.raises(NotImplementedError):
-        LfpResampler(lfp_img=np.zeros((50, 50, 3)), cfg=cfg, sta=sta).main()
+    # smp_meth='global' is implemented (tests/test_global_resampler.py); without a CUDA device every path raises
+    import torch
+    if not torch.cuda.is_available():
+        cfg.params[cfg.smp_meth] = 'global'
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            LfpResampler(lfp_img=np.zeros((50, 50, 3)), cfg=cfg, sta=sta).main()

@@ -67,3 +67,28 @@ def test_resampler_global_vs_reference_golden(cuda, name, tmp_path):
     assert np.abs(f32 - g["aligned_f64"]).max() <= 2e-5 * scale              # bar: 1e-4 of the range
     d = np.abs(got.astype(np.int64) - g["aligned_u16"].astype(np.int64))
     assert d.max() <= 2 and (d > 0).mean() < 0.05                             # <= 3e-5 of the range
+
+
+def test_oracle_cropper_non_square_pitch_equals_reference_golden():
+    g = golden("cropper_hex_13x15_u16")
+    assert np.array_equal(onp.crop_micro_images(g["aligned"], g["pitch"], int(g["M"])), g["cropped"])
+
+
+@pytest.mark.gpu
+def test_cropper_non_square_pitch_vs_reference_golden(cuda):
+    """The 13 x 15 pitch of a globally rectified hexagonal light field cropped to 9 x 9 (margins 2 and 3)."""
+    from plenopticam_b200.lfp_extractor import LfpCropper, LfpRearranger
+    g = golden("cropper_hex_13x15_u16")
+    cfg, sta = make_cfg(g["centroids"], 'hex', int(g["M"]))
+    obj = LfpCropper(lfp_img_align=g["aligned"], cfg=cfg, sta=sta)
+    obj.main()
+    assert np.array_equal(np.asarray(obj._limg_pitch), g["pitch"])
+    got = obj.lfp_img_align
+    assert got.dtype == np.uint16 and np.array_equal(got, g["cropped"])
+    re = LfpRearranger(got, cfg=cfg, sta=sta)
+    re.main()
+    assert np.array_equal(np.asarray(re.vp_img_arr), onp.compose_viewpoints(g["cropped"], int(g["M"])))
+    # odd margin -> the reference's slice assignment raises
+    cfg2, sta2 = make_cfg(g["centroids"], 'hex', 10)
+    with pytest.raises(ValueError):
+        LfpCropper(lfp_img_align=g["aligned"], cfg=cfg2, sta=sta2).main()
