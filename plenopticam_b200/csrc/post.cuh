@@ -95,7 +95,7 @@ struct SelectState {
     unsigned long long prefix[PS_MAXR];   // key bits resolved so far (high bits)
     unsigned long long rank[PS_MAXR];     // remaining rank inside the current prefix bucket
     int nr;
-    int pad;
+    unsigned int done;                    // histogram CTAs finished in the current pass (last one runs the scan)
     double q[PS_MAXQ];
 };
 
@@ -133,6 +133,7 @@ __global__ void select_init_kernel(SelectState *st, int64_t n, int nq, double q0
     const double q[PS_MAXQ] = {q0, q1, q2, q3};
     if (threadIdx.x == 0) {
         st->nr = 2 * nq;
+        st->done = 0u;
         for (int k = 0; k < nq; ++k) {
             st->q[k] = q[k];
             const double vidx = q[k] / 100.0 * (double)(n - 1);
@@ -145,6 +146,48 @@ __global__ void select_init_kernel(SelectState *st, int64_t n, int nq, double q0
         }
     }
     for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+}
+
+// One warp per rank: lane l owns bins 8l..8l+7; exclusive warp scan of the lane sums, then each lane looks for the
+// bucket holding the rank among its own eight bins.  Runs in the LAST histogram CTA of a pass (PS_MAXR warps).
+__device__ __forceinline__ void select_scan(SelectState *st, int pass) {
+    const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nr = st->nr;
+    if (r < nr) {
+        const volatile uint32_t *h = pass == 0 ? st->hist[0] : st->hist[r];
+        uint32_t c[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) c[b] = h[8 * lane + b];
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) sum += c[b];
+        unsigned long long incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        unsigned long long cum = incl - sum;                    // counts below this lane's bins
+        const unsigned long long k = st->rank[r];
+        const bool mine = k >= cum && k < incl;
+        const unsigned found = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            int b = 0;
+#pragma unroll
+            for (; b < 7; ++b) {
+                if (k < cum + c[b]) break;
+                cum += c[b];
+            }
+            st->rank[r] = k - cum;
+            st->prefix[r] = (st->prefix[r] << 8) | (unsigned long long)(8 * lane + b);
+        } else if (found == 0u && lane == 31) {                  // rank beyond the histogram (cannot happen): last bin
+            st->rank[r] = 0;
+            st->prefix[r] = (st->prefix[r] << 8) | 255ull;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+    if (threadIdx.x == 0) st->done = 0u;
 }
 
 // pass 0 looks at the most significant byte; all ranks share the first-level histogram
@@ -176,48 +219,16 @@ select_hist_kernel(const T *__restrict__ data, int64_t n, int luma, int pass, Se
         const uint32_t v = (&sh[0][0])[i];
         if (v) atomicAdd(&(&st->hist[0][0])[i], v);
     }
-}
-
-// One warp per rank: lane l owns bins 8l..8l+7; exclusive warp scan of the lane sums, then each lane looks for the
-// bucket holding the rank among its own eight bins.  (launched with PS_MAXR warps)
-__global__ void __launch_bounds__(PS_MAXR * 32)
-select_scan_kernel(SelectState *st, int pass) {
-    const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nr = st->nr;
-    if (r < nr) {
-        const uint32_t *h = pass == 0 ? st->hist[0] : st->hist[r];
-        const uint4 lo4 = *reinterpret_cast<const uint4 *>(h + 8 * lane);
-        const uint4 hi4 = *reinterpret_cast<const uint4 *>(h + 8 * lane + 4);
-        const uint32_t c[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-        unsigned long long sum = 0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) sum += c[b];
-        unsigned long long incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        unsigned long long cum = incl - sum;                    // counts below this lane's bins
-        const unsigned long long k = st->rank[r];
-        const bool mine = k >= cum && k < incl;
-        const unsigned found = __ballot_sync(0xffffffffu, mine);
-        if (mine) {
-            int b = 0;
-#pragma unroll
-            for (; b < 7; ++b) {
-                if (k < cum + c[b]) break;
-                cum += c[b];
-            }
-            st->rank[r] = k - cum;
-            st->prefix[r] = (st->prefix[r] << 8) | (unsigned long long)(8 * lane + b);
-        } else if (found == 0u && lane == 31) {                  // rank beyond the histogram (cannot happen): last bin
-            st->rank[r] = 0;
-            st->prefix[r] = (st->prefix[r] << 8) | 255ull;
-        }
-    }
+    // the last CTA to get here resolves one more key byte of every rank (no separate scan launch)
+    __shared__ bool s_last;
+    __threadfence();
     __syncthreads();
-    for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        select_scan(st, pass);
+    }
 }
 
 template <typename T>
@@ -247,10 +258,8 @@ static int run_percentile(const T *data, int64_t n, int luma, const double *q_ho
     PCB_LAUNCH_OK();
     int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
     blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
-    for (int pass = 0; pass < SelKey<T>::PASSES; ++pass) {
+    for (int pass = 0; pass < SelKey<T>::PASSES; ++pass)
         select_hist_kernel<T><<<blocks, 256, 0, st>>>(data, n, luma, pass, ss);
-        select_scan_kernel<<<1, PS_MAXR * 32, 0, st>>>(ss, pass);
-    }
     select_finish_kernel<T><<<1, 32, 0, st>>>(ss, n, result);
     PCB_LAUNCH_OK();
     return PCB_OK;
