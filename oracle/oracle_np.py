@@ -8,8 +8,10 @@ Parity pinning: the reference's own test-suite holds NO golden vectors / known-a
 path (its integration tests only assert `main()` is True).  The oracle is therefore
 pinned against OUTPUTS OF THE REFERENCE ITSELF, produced in the build container by importing the
 unmodified reference through `oracle/ref_shim.py` (see `oracle/gen_golden.py`; vectors are committed
-under `tests/golden/`).  One third-party function stays "parity unpinned": `color_space_converter.rgb2gry`
-(source absent; assumed BT.709 luma) which only feeds the lower contrast percentile.
+under `tests/golden/`).  Two third-party functions stay "parity unpinned": `color_space_converter.rgb2gry`
+(source absent; assumed BT.709 luma) which only feeds the lower contrast percentile and the white-image
+conversion of the devignetter, and `skimage.transform.warp` (scikit-image not installed; restated from its
+published algorithm in `warp_projective`), the one call of the global resampler.
 
 All file:line citations are relative to /root/reference/plenopticam/.
 All arithmetic is float64 unless the reference itself uses float32 (Normalizer).
