@@ -90,6 +90,9 @@ int pcb_resample_u16(const void *raw, int raw_dtype, int H, int W, int C,
                      const pcb_minmax_t *mm, uint16_t *aligned, void *stream);
 /* Normalizer.uint16_norm on an existing float32 buffer (misc/normalizer.py:43-46). */
 int pcb_quantize_u16(const float *in, int64_t n, const pcb_minmax_t *mm, uint16_t *out, void *stream);
+/* Normalizer.uint8_norm (misc/normalizer.py:48-51): what LfpExporter / save_img_file write to 8-bit files
+ * (lfp_extractor/lfp_exporter.py:195, misc/file_rw.py:86). */
+int pcb_quantize_u8(const float *in, int64_t n, const pcb_minmax_t *mm, uint8_t *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (a') Rotation — replaces LfpRotator._rotate_img (lfp_aligner/lfp_rotator.py:129-145):

@@ -80,6 +80,7 @@ _SIGNATURES = {
     "pcb_resample_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pcb_resample_u16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pcb_quantize_u16": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "pcb_quantize_u8": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "pcb_spline_prefilter": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pcb_rotate_sample": (_i, [_vp, _i, _i, _i, C.c_double, _vp, _vp]),
     "pcb_viewpoints": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -122,7 +122,8 @@ struct QuantU16 {
         d = __fsub_rn(mx_, mn_);
         inv = scale ? __frcp_rn(d) : 1.f;
     }
-    __device__ __forceinline__ uint16_t operator()(float x) const {
+    // clip((x - min) / (max - min), 0, 1), the division correctly rounded
+    __device__ __forceinline__ float unit(float x) const {
         float n = x;
         if (scale) {
             const float num = __fsub_rn(x, mn);
@@ -130,8 +131,10 @@ struct QuantU16 {
             const float r = __fmaf_rn(-d, q, num);
             n = __fmaf_rn(r, inv, q);
         }
-        n = fminf(fmaxf(n, 0.f), 1.f);
-        return (uint16_t)__float2uint_rn(__fmul_rn(n, 65535.0f));   // round-half-even like np.round
+        return fminf(fmaxf(n, 0.f), 1.f);
+    }
+    __device__ __forceinline__ uint16_t operator()(float x) const {
+        return (uint16_t)__float2uint_rn(__fmul_rn(unit(x), 65535.0f));   // round-half-even like np.round
     }
 };
 

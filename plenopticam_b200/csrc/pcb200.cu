@@ -127,6 +127,13 @@ int pcb_quantize_u16(const float *in, int64_t n, const pcb_minmax_t *mm, uint16_
     return PCB_OK;
 }
 
+int pcb_quantize_u8(const float *in, int64_t n, const pcb_minmax_t *mm, uint8_t *out, void *stream) {
+    PCB_REQUIRE(in != nullptr && out != nullptr && mm != nullptr && n > 0, "in, out, mm, n > 0");
+    quantize_u8_kernel<<<grid_for(n, 256 * 8), 256, 0, as_stream(stream)>>>(in, n, mm, out);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
 int pcb_spline_prefilter(const void *img, int dtype, int H, int W, int C, float *tmp, float *coef, void *stream) {
     PCB_REQUIRE(img != nullptr && tmp != nullptr && coef != nullptr, "img, tmp, coef");
     PCB_REQUIRE(H > 0 && W > 0 && C > 0 && H <= 65535 * PF_ROWS, "sizes");

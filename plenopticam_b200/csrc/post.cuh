@@ -34,6 +34,16 @@ quantize_u16_kernel(const float *__restrict__ in, int64_t n, const pcb_minmax_t 
         out[i] = qz(__ldg(in + i));
 }
 
+// Normalizer.uint8_norm (misc/normalizer.py:48-51): same normalisation, 255 levels
+__global__ void __launch_bounds__(256)
+quantize_u8_kernel(const float *__restrict__ in, int64_t n, const pcb_minmax_t *mm, uint8_t *__restrict__ out) {
+    QuantU16 qz;
+    qz.init(key_to_float(mm->kmin), key_to_float(mm->kmax));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (uint8_t)__float2uint_rn(__fmul_rn(qz.unit(__ldg(in + i)), 255.0f));
+}
+
 // ---- contrast + sRGB ------------------------------------------------------------------------------
 // Normalizer(img, min=lo, max=hi).type_norm(): with NumPy >= 2 the float32 data meets float64 percentile
 // scalars, so (x-lo)/(hi-lo) is evaluated in float64, clipped, then cast to float32 (SURVEY §8c iv).

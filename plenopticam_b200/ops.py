@@ -161,11 +161,31 @@ def resample_u16(raw, tabs, flip=False, out=None, mm=None):
     return out, mm
 
 
-def quantize_u16(data, mm):
+def quantize_u16(data, mm, out=None):
     _chk_dev(data)
-    out = torch.empty(data.shape, dtype=torch.uint16, device=data.device)
+    if out is None:
+        out = torch.empty(data.shape, dtype=torch.uint16, device=data.device)
     nat.check(nat.lib().pcb_quantize_u16(_ptr(data), data.numel(), _ptr(mm), _ptr(out), _stream()))
     return out
+
+
+def quantize_u8(data, mm, out=None):
+    _chk_dev(data)
+    if out is None:
+        out = torch.empty(data.shape, dtype=torch.uint8, device=data.device)
+    nat.check(nat.lib().pcb_quantize_u8(_ptr(data), data.numel(), _ptr(mm), _ptr(out), _stream()))
+    return out
+
+
+def uint16_norm(data, out=None):
+    """misc.Normalizer(data).uint16_norm() of a float32 CUDA tensor (global min / max; misc/normalizer.py:43-46):
+    what LfpExporter writes for viewpoints and refocus slices (lfp_extractor/lfp_exporter.py:84,134)."""
+    return quantize_u16(data, minmax_f32(data), out=out)
+
+
+def uint8_norm(data, out=None):
+    """misc.Normalizer(data).uint8_norm() (misc/normalizer.py:48-51; lfp_exporter.py:195)."""
+    return quantize_u8(data, minmax_f32(data), out=out)
 
 
 # ------------------------------------------------------------------------------------------------------

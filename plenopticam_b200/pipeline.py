@@ -128,9 +128,9 @@ class LightFieldPipeline(object):
         torch.cuda.current_stream().synchronize()
         return pin_out.numpy()
 
-    def exposure_stream(self, depth=2):
+    def exposure_stream(self, depth=2, out_dtype=np.float32):
         """Pipelined host-buffer entry point for a sequence of exposures (see ExposureStream)."""
-        return ExposureStream(self, depth)
+        return ExposureStream(self, depth, out_dtype)
 
     # -- byte accounting used by bench.py / DESIGN.md --------------------------------------------------------
     def algorithmic_bytes(self):
@@ -163,9 +163,15 @@ class ExposureStream(object):
         stack = es.result(k)
     """
 
-    def __init__(self, pipe, depth=2):
+    def __init__(self, pipe, depth=2, out_dtype=np.float32):
+        """out_dtype: float32 (the reference's `refo_stack`), or uint16 / uint8 = what LfpExporter would write for it
+        (`Normalizer(stack).uint16_norm()` / `.uint8_norm()`, lfp_extractor/lfp_exporter.py:134,195), quantised on the
+        device so that a half / a quarter of the bytes cross PCIe."""
         self.pipe = pipe
         self.depth = int(depth)
+        self.out_dtype = np.dtype(out_dtype)
+        if self.out_dtype not in (np.dtype(np.float32), np.dtype(np.uint16), np.dtype(np.uint8)):
+            raise TypeError("out_dtype must be float32, uint16 or uint8")
         dev = pipe.device
         tdt = ops._NP2TORCH[pipe.raw_dtype]
         with torch.cuda.device(dev):
@@ -173,7 +179,10 @@ class ExposureStream(object):
             self.out_dev = [torch.empty(tuple(pipe.stack.shape), dtype=torch.float32, device=dev)
                             for _ in range(self.depth)]
             self.pin_in = [None] * self.depth
-            self.pin_out = [torch.empty(tuple(pipe.stack.shape), dtype=torch.float32, pin_memory=True)
+            tout = {2: torch.uint16, 1: torch.uint8, 4: torch.float32}[self.out_dtype.itemsize]
+            self.q_dev = [torch.empty(tuple(pipe.stack.shape), dtype=tout, device=dev) for _ in range(self.depth)] \
+                if tout != torch.float32 else None
+            self.pin_out = [torch.empty(tuple(pipe.stack.shape), dtype=tout, pin_memory=True)
                             for _ in range(self.depth)]
             self.s_in = torch.cuda.Stream(device=dev)
             self.s_out = torch.cuda.Stream(device=dev)
@@ -204,10 +213,13 @@ class ExposureStream(object):
         if k >= self.depth:
             cur.wait_event(self.ev_out[s])                    # result slot has left for the host
         self.pipe.run_device(self.raw_dev[s], out=self.out_dev[s])
+        res = self.out_dev[s]
+        if self.q_dev is not None:
+            res = (ops.uint16_norm if self.out_dtype.itemsize == 2 else ops.uint8_norm)(res, out=self.q_dev[s])
         self.ev_run[s].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_run[s])
-            self.pin_out[s].copy_(self.out_dev[s], non_blocking=True)
+            self.pin_out[s].copy_(res, non_blocking=True)
             self.ev_out[s].record(self.s_out)
         self.k += 1
         return k
@@ -218,4 +230,5 @@ class ExposureStream(object):
             raise IndexError("result %d is not in flight" % k)
         s = k % self.depth
         self.ev_out[s].synchronize()
-        return self.pin_out[s].numpy()
+        t = self.pin_out[s]
+        return t.view(torch.int16).numpy().view(np.uint16) if t.dtype == torch.uint16 else t.numpy()

@@ -374,3 +374,31 @@ def test_exposure_stream_matches_single_runs(cuda):
     for k in range(len(raws)):
         assert np.array_equal(outs[k], singles[k]), k
     assert torch.cuda.is_available()
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+@pytest.mark.gpu
+def test_exporter_quantisation_and_quantised_exposure_stream(cuda, bits):
+    """Normalizer(stack).uint16_norm() / .uint8_norm() on the device (lfp_extractor/lfp_exporter.py:134,195;
+    misc/normalizer.py:43-51) and the exposure stream handing out the quantised stack."""
+    from plenopticam_b200 import ops
+    from plenopticam_b200.pipeline import LightFieldPipeline
+    rng = np.random.default_rng(31)
+    x = (rng.random((5, 17, 23, 3)) ** 2 * 3.0 - 0.4).astype(np.float32)
+    mn, mx = x.min(), x.max()
+    n = np.clip((x - mn) / (mx - mn), 0, 1)
+    fn, dt, lv = (ops.uint16_norm, np.uint16, 65535) if bits == 16 else (ops.uint8_norm, np.uint8, 255)
+    assert np.array_equal(ops.to_host(fn(ops.to_device(x))), np.asarray(np.round(n * lv), dtype=dt))
+    LY, LX, M = 12, 16, 7
+    cent = onp.synth_centroids(LY, LX, 9.0, 'rec', jitter=0.1, origin=(6.5, 6.5), seed=3)
+    H, W = int(cent[:, 0].max() + 8), int(cent[:, 1].max() + 8)
+    pipe = LightFieldPipeline(cent, (H, W, 3), np.uint16, M, 'rec', ran_refo=(-2, 2))
+    raws = [onp.synth_raw(H, W, 3, seed=s) for s in range(3)]
+    es = pipe.exposure_stream(depth=2, out_dtype=dt)
+    for k, r in enumerate(raws):
+        es.pinned_input(k)[...] = r
+        es.submit()
+        got = es.result(k).copy()
+        f = pipe.run(r)
+        ref = np.asarray(np.round(np.clip((f - f.min()) / (f.max() - f.min()), 0, 1) * lv), dtype=dt)
+        assert got.dtype == dt and np.array_equal(got, ref), k
