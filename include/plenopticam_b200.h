@@ -207,7 +207,8 @@ int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi,
  *   pcb_hex_align       : hexagonal_alignment + hex_stretch + per-strip misc.img_resize (:84-167) for even (py, px):
  *                         i0/i1/w[nk]: stretch lerp; wx_vals[K][x_len] / wx_first[x_len]: banded x resize of a strip of
  *                         nk*px samples; wy[y_len][py]: dense y resize; kept columns [crop_lo, crop_lo + out_cols).
- *                         tmpx: float32 (strips*py, out_cols, C) scratch; out: float32 (strips*y_len, out_cols, C).
+ *                         stretched: float32 (strips*py, nk*px, C) scratch; tmpx: float32 (strips*py, out_cols, C)
+ *                         scratch; out: float32 (strips*y_len, out_cols, C).
  * ------------------------------------------------------------------------------------------------ */
 int pcb_image_minmax(const void *img, int dtype, int64_t n, pcb_minmax_t *mm, void *stream);
 int pcb_warp_projective(const void *img, int dtype, int H, int W, int C, const double *inv_matrix_host,
@@ -215,7 +216,7 @@ int pcb_warp_projective(const void *img, int dtype, int H, int W, int C, const d
 int pcb_hex_align(const float *prj, int prows, int pcols, int C, int strips, int py, int px, int hex_odd, int nk,
                   const int32_t *i0, const int32_t *i1, const float *w,
                   const float *wx_vals, const int32_t *wx_first, int K, int x_len, int crop_lo, int out_cols,
-                  const float *wy, int y_len, float *tmpx, float *out, void *stream);
+                  const float *wy, int y_len, float *stretched, float *tmpx, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Lytro raw bit-unpacking ("next" row) — replaces LfpDecoder.comp_bayer

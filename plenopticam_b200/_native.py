@@ -100,7 +100,7 @@ _SIGNATURES = {
     "pcb_image_minmax": (_i, [_vp, _i, _i64, _vp, _vp]),
     "pcb_warp_projective": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_double), _i, _i, _vp, _vp, _vp]),
     "pcb_hex_align": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp,
-                           _vp, _vp]),
+                           _vp, _vp, _vp]),
     "pcb_unpack_bayer": (_i, [_vp, _i64, _i, _vp, _vp]),
     "pcb_scheimpflug": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pcb_devig_white": (_i, [_vp, _i, _i64, _i, _vp, _vp]),

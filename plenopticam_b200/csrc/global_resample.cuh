@@ -4,9 +4,10 @@
 //   warp_projective_kernel   skimage.transform.warp(img, ProjectiveTransform(tra_mat).inverse, output_shape)   (:81-82)
 //                            order 1, mode 'constant', cval 0, clip to the input range (published algorithm,
 //                            skimage is not installed here: PARITY UNPINNED)
-//   hex_strip_x_kernel       per lens-row strip: mean of the three half-pitch-shifted rows (:108-128), the
-//                            2/sqrt(3) stretch along the lens axis (np.interp, :151-167) and the x half of the bicubic
-//                            strip resize (misc.img_resize, :134-137) as a banded operator, cropped (:146)
+//   hex_merge_stretch_kernel per lens-row strip: mean of the three half-pitch-shifted rows (:108-128) and the
+//                            2/sqrt(3) stretch along the lens axis (np.interp, :151-167)
+//   hex_resize_x_kernel      the x half of the bicubic strip resize (misc.img_resize, :134-137) as a banded
+//                            operator, cropped (:146)
 //   hex_strip_y_kernel       the y half of the strip resize (py -> py+1 rows)
 // The matrices and spline operators are prepared on the host in float64 (lfp_aligner/lfp_global_resampler.py).
 #pragma once
@@ -92,40 +93,62 @@ __device__ __forceinline__ float hex_merged(const float *A, const float *B, bool
 
 constexpr int HX_THREADS = 512;
 
-// grid (py, strips): one CTA per image row of a strip
-__global__ void __launch_bounds__(HX_THREADS)
-hex_strip_x_kernel(HexArgs p, float *__restrict__ tmpx /* (strips*py, out_cols, C) */) {
-    extern __shared__ __align__(16) float s_row[];            // [nk*px*C] merged + stretched row
-    const int y = blockIdx.x, ly = blockIdx.y;
+// grid (ceil(nk*px*C / 256), py, strips): merged + stretched strip rows, one element per thread
+__global__ void __launch_bounds__(256)
+hex_merge_stretch_kernel(HexArgs p, float *__restrict__ stretched /* (strips*py, nk*px, C) */) {
+    const int y = blockIdx.y, ly = blockIdx.z;
     const int C = p.C;
+    const int mE = p.nk * p.px * C;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= mE) return;
     const bool sw = ((p.hex_odd + ly) & 1) != 0;
     const int ra = ly * p.py + y, rb = (ly + 1) * p.py + y;
-    const float *A = p.prj + (size_t)min(ra, p.prows - 1) * p.pcols * C;
-    const float *B = p.prj + (size_t)min(rb, p.prows - 1) * p.pcols * C;
-    const bool rows_ok = rb < p.prows;
-    const int h = p.px / 2;
-    const int mE = p.nk * p.px * C;
-    for (int e = threadIdx.x; e < mE; e += HX_THREADS) {
+    float v = 0.f;
+    if (rb < p.prows) {
+        const float *A = p.prj + (size_t)ra * p.pcols * C;
+        const float *B = p.prj + (size_t)rb * p.pcols * C;
         const int X = e / C, ch = e - X * C;
         const int k = X / p.px, x = X - k * p.px;
-        const int xa = x + __ldg(p.i0 + k) * p.px, xb = x + __ldg(p.i1 + k) * p.px;
-        const float wk = __ldg(p.w + k);
-        float va = 0.f, vb = 0.f;
-        if (rows_ok) {
-            va = hex_merged(A, B, sw, xa, h, p.px, p.pcols, C, ch);
-            vb = hex_merged(A, B, sw, xb, h, p.px, p.pcols, C, ch);
-        }
-        s_row[e] = va + (vb - va) * wk;                        // np.interp
+        const int h = p.px / 2;
+        const float va = hex_merged(A, B, sw, x + __ldg(p.i0 + k) * p.px, h, p.px, p.pcols, C, ch);
+        const float vb = hex_merged(A, B, sw, x + __ldg(p.i1 + k) * p.px, h, p.px, p.pcols, C, ch);
+        v = va + (vb - va) * __ldg(p.w + k);                    // np.interp
     }
+    stretched[(size_t)(ly * p.py + y) * mE + e] = v;
+}
+
+// grid (py, strips): one CTA per stretched row: the row goes through shared memory once, every thread evaluates the
+// banded spline operator for its output columns (weights tap-major: coalesced)
+__global__ void __launch_bounds__(HX_THREADS)
+hex_resize_x_kernel(HexArgs p, const float *__restrict__ stretched, float *__restrict__ tmpx /* (strips*py, out_cols, C) */) {
+    extern __shared__ __align__(16) float s_row[];            // [nk*px*C]
+    const int row = blockIdx.y * p.py + blockIdx.x;
+    const int C = p.C;
+    const int mE = p.nk * p.px * C;
+    const float *src = stretched + (size_t)row * mE;
+    for (int e = threadIdx.x; e < mE; e += HX_THREADS) s_row[e] = __ldg(src + e);
     __syncthreads();
-    float *dst = tmpx + (size_t)(ly * p.py + y) * p.out_cols * C;
+    float *dst = tmpx + (size_t)row * p.out_cols * C;
     for (int xo = threadIdx.x; xo < p.out_cols; xo += HX_THREADS) {
         const int X = xo + p.crop_lo;
-        const float *px_ = s_row + (size_t)__ldg(p.wx_first + X) * C;
-        for (int ch = 0; ch < C; ++ch) {
-            float acc = 0.f;
-            for (int k = 0; k < p.K; ++k) acc = fmaf(__ldg(p.wx_vals + (size_t)k * p.x_len + X), px_[k * C + ch], acc);
-            dst[(size_t)xo * C + ch] = acc;
+        const float *win = s_row + (size_t)__ldg(p.wx_first + X) * C;
+        if (C == 3) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < p.K; ++k) {
+                const float wk = __ldg(p.wx_vals + (size_t)k * p.x_len + X);
+                a0 = fmaf(wk, win[k * 3 + 0], a0);
+                a1 = fmaf(wk, win[k * 3 + 1], a1);
+                a2 = fmaf(wk, win[k * 3 + 2], a2);
+            }
+            dst[(size_t)xo * 3 + 0] = a0; dst[(size_t)xo * 3 + 1] = a1; dst[(size_t)xo * 3 + 2] = a2;
+        } else {
+            for (int ch = 0; ch < C; ++ch) {
+                float acc = 0.f;
+                for (int k = 0; k < p.K; ++k)
+                    acc = fmaf(__ldg(p.wx_vals + (size_t)k * p.x_len + X), win[k * C + ch], acc);
+                dst[(size_t)xo * C + ch] = acc;
+            }
         }
     }
 }

@@ -426,9 +426,9 @@ int pcb_warp_projective(const void *img, int dtype, int H, int W, int C, const d
 
 int pcb_hex_align(const float *prj, int prows, int pcols, int C, int strips, int py, int px, int hex_odd, int nk,
                   const int32_t *i0, const int32_t *i1, const float *w, const float *wx_vals, const int32_t *wx_first,
-                  int K, int x_len, int crop_lo, int out_cols, const float *wy, int y_len, float *tmpx, float *out,
-                  void *stream) {
-    PCB_REQUIRE(prj && i0 && i1 && w && wx_vals && wx_first && wy && tmpx && out, "pointers");
+                  int K, int x_len, int crop_lo, int out_cols, const float *wy, int y_len, float *stretched, float *tmpx,
+                  float *out, void *stream) {
+    PCB_REQUIRE(prj && i0 && i1 && w && wx_vals && wx_first && wy && stretched && tmpx && out, "pointers");
     PCB_REQUIRE(prows > 0 && pcols > 0 && C > 0 && strips > 0 && strips <= 65535 && py >= 4 && py <= HX_MAXPY &&
                 px >= 2 && px % 2 == 0 && nk > 0 && K > 0 && x_len > 0 && crop_lo >= 0 && out_cols > 0 &&
                 crop_lo + out_cols <= x_len && y_len > 0, "sizes (even px, 4 <= py <= 64)");
@@ -439,8 +439,11 @@ int pcb_hex_align(const float *prj, int prows, int pcols, int C, int strips, int
     const size_t smem = (size_t)nk * px * C * sizeof(float);
     if (smem > 220 * 1024) return fail(PCB_ERR_UNSUPPORTED, "%s: a stretched lens row does not fit shared memory", __func__);
     cudaStream_t st = as_stream(stream);
-    PCB_CUDA(cudaFuncSetAttribute(hex_strip_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hex_strip_x_kernel<<<dim3(py, strips), HX_THREADS, smem, st>>>(a, tmpx);
+    PCB_REQUIRE(py <= 65535, "py");
+    hex_merge_stretch_kernel<<<dim3((nk * px * C + 255) / 256, py, strips), 256, 0, st>>>(a, stretched);
+    PCB_LAUNCH_OK();
+    PCB_CUDA(cudaFuncSetAttribute(hex_resize_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hex_resize_x_kernel<<<dim3(py, strips), HX_THREADS, smem, st>>>(a, stretched, tmpx);
     PCB_LAUNCH_OK();
     hex_strip_y_kernel<<<dim3((out_cols * C + 255) / 256, strips), 256, 0, st>>>(a, tmpx, out);
     PCB_LAUNCH_OK();

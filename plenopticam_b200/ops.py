@@ -485,10 +485,11 @@ def hex_align(prj, plan, LY):
     wxv, wxf, wy = t(plan["wx_vals"]), t(plan["wx_first"]), t(plan["wy"])
     strips = int(LY) - 1
     out_cols = plan["x_len"] + plan["crop_hi"] - plan["crop_lo"]
+    stretched = torch.empty((strips * plan["py"], plan["m"], Cn), dtype=torch.float32, device=dev)
     tmpx = torch.empty((strips * plan["py"], out_cols, Cn), dtype=torch.float32, device=dev)
     out = torch.empty((strips * plan["y_len"], out_cols, Cn), dtype=torch.float32, device=dev)
     nat.check(nat.lib().pcb_hex_align(_ptr(prj), prows, pcols, Cn, strips, plan["py"], plan["px"], plan["hex_odd"],
                                       plan["lens_new_x"], _ptr(i0), _ptr(i1), _ptr(w), _ptr(wxv), _ptr(wxf),
                                       int(plan["wx_vals"].shape[0]), plan["x_len"], plan["crop_lo"], out_cols, _ptr(wy),
-                                      plan["y_len"], _ptr(tmpx), _ptr(out), _stream()))
+                                      plan["y_len"], _ptr(stretched), _ptr(tmpx), _ptr(out), _stream()))
     return out
