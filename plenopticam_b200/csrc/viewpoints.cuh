@@ -14,7 +14,7 @@ namespace pcb {
 template <typename T, int CT>   // CT = compile-time channel count (0 = runtime)
 __global__ void __launch_bounds__(256)
 viewpoints_kernel(const T *__restrict__ aligned, T *__restrict__ vp, int cols_elems, int M_in, int M_out, int kc,
-                  int S, int Tn, int Crt, int tile_t) {
+                  int S, int Tn, int Crt, int tile_t, size_t total_elems) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *row = reinterpret_cast<T *>(smem_raw);
     const int C = CT ? CT : Crt;
@@ -25,19 +25,48 @@ viewpoints_kernel(const T *__restrict__ aligned, T *__restrict__ vp, int cols_el
 
     const T *src = aligned + (size_t)(s * M_in + kc + j) * cols_elems + (size_t)t0 * M_in * C;
     const int n_in = nt * M_in * C;
-    // read the row with VP_UNROLL independent loads in flight per thread (the copy is latency-bound otherwise)
+    // read the row with VP_UNROLL independent loads in flight per thread (the copy is latency-bound otherwise).
+    // 2-byte elements travel as aligned 32-bit words (the row may start on either half of a word: the shared-memory
+    // copy keeps that parity), which halves the load and shared-store instructions.
     constexpr int VP_UNROLL = 8;
-    for (int base = threadIdx.x; base < n_in; base += 256 * VP_UNROLL) {
-        T v[VP_UNROLL];
+    bool by_words = false;
+    if constexpr (sizeof(T) == 2) {
+        const int par = (int)((reinterpret_cast<uintptr_t>(src) >> 1) & 1);
+        const size_t off = (size_t)(src - aligned);
+        by_words = (reinterpret_cast<uintptr_t>(aligned) & 3) == 0 && off + n_in + 1 <= total_elems;
+        if (by_words) {
+            const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(src - par);
+            uint32_t *wrow = reinterpret_cast<uint32_t *>(smem_raw);
+            const int nw = (n_in + par + 1) >> 1;
+            for (int base = threadIdx.x; base < nw; base += 256 * VP_UNROLL) {
+                uint32_t v[VP_UNROLL];
 #pragma unroll
-        for (int u = 0; u < VP_UNROLL; ++u) {
-            const int idx = base + u * 256;
-            if (idx < n_in) v[u] = __ldg(src + idx);
+                for (int u = 0; u < VP_UNROLL; ++u) {
+                    const int idx = base + u * 256;
+                    if (idx < nw) v[u] = __ldg(wsrc + idx);
+                }
+#pragma unroll
+                for (int u = 0; u < VP_UNROLL; ++u) {
+                    const int idx = base + u * 256;
+                    if (idx < nw) wrow[idx] = v[u];
+                }
+            }
+            row += par;
         }
+    }
+    if (!by_words) {
+        for (int base = threadIdx.x; base < n_in; base += 256 * VP_UNROLL) {
+            T v[VP_UNROLL];
 #pragma unroll
-        for (int u = 0; u < VP_UNROLL; ++u) {
-            const int idx = base + u * 256;
-            if (idx < n_in) row[idx] = v[u];
+            for (int u = 0; u < VP_UNROLL; ++u) {
+                const int idx = base + u * 256;
+                if (idx < n_in) v[u] = __ldg(src + idx);
+            }
+#pragma unroll
+            for (int u = 0; u < VP_UNROLL; ++u) {
+                const int idx = base + u * 256;
+                if (idx < n_in) row[idx] = v[u];
+            }
         }
     }
     __syncthreads();
@@ -103,7 +132,7 @@ crop_kernel(const T *__restrict__ aligned, T *__restrict__ cropped, int cols_ele
 }
 
 static inline int vp_tile(int Tn, int M, int C, int esz, int *tile_t, int *ntile, size_t *smem) {
-    const size_t budget = 48 * 1024;
+    const size_t budget = 48 * 1024 - 8;          // default dynamic shared-memory limit minus the parity word
     const size_t row_bytes = (size_t)Tn * M * C * esz;
     int nt = (int)((row_bytes + budget - 1) / budget);
     if (nt < 1) nt = 1;
@@ -111,7 +140,7 @@ static inline int vp_tile(int Tn, int M, int C, int esz, int *tile_t, int *ntile
     if ((size_t)tt * M * C * esz > budget) return 1;   // a single micro-image row exceeds the budget
     *tile_t = tt;
     *ntile = (Tn + tt - 1) / tt;
-    *smem = (size_t)tt * M * C * esz;
+    *smem = (size_t)tt * M * C * esz + 8;      // + one word: rows staged as 32-bit words keep their parity
     return 0;
 }
 
@@ -125,11 +154,14 @@ static int launch_viewpoints(const void *aligned, void *vp, int rows, int cols, 
         return fail(PCB_ERR_UNSUPPORTED, "%s: micro image row too large for shared memory", "pcb_viewpoints");
     dim3 grid(S, M_out, ntile), block(256);
     if (C == 3)
-        viewpoints_kernel<T, 3><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t);
+        viewpoints_kernel<T, 3><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t,
+                                                           (size_t)rows * cols * C);
     else if (C == 1)
-        viewpoints_kernel<T, 1><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t);
+        viewpoints_kernel<T, 1><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t,
+                                                           (size_t)rows * cols * C);
     else
-        viewpoints_kernel<T, 0><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t);
+        viewpoints_kernel<T, 0><<<grid, block, smem, st>>>((const T *)aligned, (T *)vp, cols * C, M_in, M_out, kc, S, Tn, C, tile_t,
+                                                           (size_t)rows * cols * C);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }
