@@ -191,6 +191,11 @@ int pcb_percentile_f32(const float *data, int64_t n, int luma, const double *q_h
                        double *result, void *scratch, void *stream);
 int pcb_percentile_f64(const double *data, int64_t n, int luma, const double *q_host, int nq,
                        double *result, void *scratch, void *stream);   /* 8 x 8-bit passes over 64-bit keys */
+/* Both bounds of LfpContrast.auto_hist_align (lfp_extractor/lfp_contrast.py:252-255) for a 3-channel reference image
+ * in ONE cooperative launch: lohi[0] = percentile(rgb2gry(ref), q_lo), lohi[1] = percentile(ref, q_hi); same exact
+ * order statistics as two pcb_percentile_f32 calls (13 launches).  scratch >= pcb_percentile_scratch_bytes(). */
+int pcb_contrast_bounds(const float *ref, int64_t npx, double q_lo, double q_hi, double *lohi,
+                        void *scratch, void *stream);
 int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi,
                       const pcb_minmax_t *mm /* nullable: fallback for a bound that is exactly 0 */,
                       float *out, void *stream);

@@ -95,6 +95,7 @@ _SIGNATURES = {
                               _vp, _vp, _vp]),
     "pcb_percentile_scratch_bytes": (_i64, []),
     "pcb_percentile_f32": (_i, [_vp, _i64, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
+    "pcb_contrast_bounds": (_i, [_vp, _i64, C.c_double, C.c_double, _vp, _vp, _vp]),
     "pcb_percentile_f64": (_i, [_vp, _i64, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
     "pcb_contrast_srgb": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "pcb_image_minmax": (_i, [_vp, _i, _i64, _vp, _vp]),

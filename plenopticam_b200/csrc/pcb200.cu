@@ -331,6 +331,13 @@ int pcb_percentile_f32(const float *data, int64_t n, int luma, const double *q_h
     return run_percentile<float>(data, n, luma, q_host, nq, result, scratch, as_stream(stream));
 }
 
+int pcb_contrast_bounds(const float *ref, int64_t npx, double q_lo, double q_hi, double *lohi, void *scratch,
+                        void *stream) {
+    PCB_REQUIRE(ref != nullptr && lohi != nullptr && scratch != nullptr && npx > 0, "ref, lohi, scratch, npx > 0");
+    PCB_REQUIRE(q_lo >= 0.0 && q_lo <= 100.0 && q_hi >= 0.0 && q_hi <= 100.0, "0 <= q <= 100");
+    return run_contrast_bounds(ref, npx, q_lo, q_hi, lohi, scratch, as_stream(stream));
+}
+
 int pcb_percentile_f64(const double *data, int64_t n, int luma, const double *q_host, int nq, double *result,
                        void *scratch, void *stream) {
     PCB_REQUIRE(data != nullptr && q_host != nullptr && result != nullptr && scratch != nullptr, "pointers");

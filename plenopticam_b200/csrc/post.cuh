@@ -5,6 +5,7 @@
 //   auto_hist_align + sRGB             (lfp_contrast.py:261, normalizer.py:53-78, gamma_converter.py:41-42)
 #pragma once
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace pcb {
 
@@ -256,6 +257,126 @@ __global__ void select_finish_kernel(const SelectState *st, int64_t n, double *r
         if (t >= 0.5) v = __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t)));
         result[k] = v;
     }
+}
+
+// ---- both contrast bounds of LfpContrast.auto_hist_align in ONE cooperative launch ------------------------
+// lo = percentile(rgb2gry(ref), q_lo), hi = percentile(ref, q_hi) (lfp_extractor/lfp_contrast.py:252-255) on the
+// same reference image: ranks 0,1 select over the luma of the npx pixels, ranks 2,3 over the 3*npx channel values;
+// the four 8-bit passes, their scans and the final interpolation are separated by grid-wide barriers instead of
+// kernel boundaries (13 launches -> 1).
+__global__ void __launch_bounds__(256)
+contrast_bounds_kernel(const float *__restrict__ ref, int64_t npx, double q_lo, double q_hi, SelectState *st,
+                       double *__restrict__ lohi) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t sh[4][256];
+    __shared__ unsigned long long s_prefix[4];
+    const int64_t nval[2] = {npx, 3 * npx};
+    const double q[2] = {q_lo, q_hi};
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 2) {
+            const int f = threadIdx.x;
+            const double vidx = q[f] / 100.0 * (double)(nval[f] - 1);
+            long long lo = (long long)floor(vidx);
+            lo = lo < 0 ? 0 : (lo > nval[f] - 1 ? nval[f] - 1 : lo);
+            const long long hi = lo + 1 > nval[f] - 1 ? nval[f] - 1 : lo + 1;
+            st->rank[2 * f] = (unsigned long long)lo;
+            st->rank[2 * f + 1] = (unsigned long long)hi;
+            st->prefix[2 * f] = st->prefix[2 * f + 1] = 0;
+        }
+        for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+    }
+    __threadfence();
+    grid.sync();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int pass = 0; pass < 4; ++pass) {
+        for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+        if (threadIdx.x < 4) s_prefix[threadIdx.x] = st->prefix[threadIdx.x];
+        __syncthreads();
+        const int shift = (3 - pass) * 8;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) {
+            const float r = __ldg(ref + 3 * i), g = __ldg(ref + 3 * i + 1), b = __ldg(ref + 3 * i + 2);
+            const float y = (float)(0.2126 * (double)r + 0.7152 * (double)g + 0.0722 * (double)b);
+            const uint32_t keys[4] = {float_to_key(y), float_to_key(r), float_to_key(g), float_to_key(b)};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int f = v == 0 ? 0 : 1;                           // value function: luma | channel values
+                const uint32_t bin = (keys[v] >> shift) & 0xffu;
+                if (pass == 0) {
+                    atomicAdd(&sh[2 * f][bin], 1u);                     // both ranks of a function share pass 0
+                } else {
+                    const unsigned long long hi = (unsigned long long)keys[v] >> (shift + 8);
+                    if (hi == s_prefix[2 * f]) atomicAdd(&sh[2 * f][bin], 1u);
+                    if (hi == s_prefix[2 * f + 1]) atomicAdd(&sh[2 * f + 1][bin], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
+            const uint32_t v = (&sh[0][0])[i];
+            if (v) atomicAdd(&(&st->hist[0][0])[i], v);
+        }
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) {
+            const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (r < 4) {
+                const volatile uint32_t *h = pass == 0 ? st->hist[r & ~1] : st->hist[r];
+                uint32_t c[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) c[b] = h[8 * lane + b];
+                unsigned long long sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) sum += c[b];
+                unsigned long long incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                unsigned long long cum = incl - sum;
+                const unsigned long long k = st->rank[r];
+                if (k >= cum && k < incl) {
+                    int b = 0;
+#pragma unroll
+                    for (; b < 7; ++b) {
+                        if (k < cum + c[b]) break;
+                        cum += c[b];
+                    }
+                    st->rank[r] = k - cum;
+                    st->prefix[r] = (st->prefix[r] << 8) | (unsigned long long)(8 * lane + b);
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < PS_MAXR * 256; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+            __threadfence();
+        }
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 2) {
+        const int f = threadIdx.x;
+        const double a = (double)key_to_float((uint32_t)st->prefix[2 * f]);
+        const double b = (double)key_to_float((uint32_t)st->prefix[2 * f + 1]);
+        const double vidx = q[f] / 100.0 * (double)(nval[f] - 1);
+        const double t = vidx - floor(vidx);
+        const double d = __dsub_rn(b, a);
+        double v = __dadd_rn(a, __dmul_rn(d, t));
+        if (t >= 0.5) v = __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t)));
+        lohi[f] = v;
+    }
+}
+
+static int run_contrast_bounds(const float *ref, int64_t npx, double q_lo, double q_hi, double *lohi, void *scratch,
+                               cudaStream_t st) {
+    SelectState *ss = reinterpret_cast<SelectState *>(scratch);
+    int per_sm = 0;
+    PCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contrast_bounds_kernel, 256, 0));
+    int blocks = (int)((npx + 256 * 2 - 1) / (256 * 2));
+    const int cap = sm_count() * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+    blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+    void *args[] = {(void *)&ref, (void *)&npx, (void *)&q_lo, (void *)&q_hi, (void *)&ss, (void *)&lohi};
+    PCB_CUDA(cudaLaunchCooperativeKernel((const void *)contrast_bounds_kernel, dim3(blocks), dim3(256), args, 0, st));
+    return PCB_OK;
 }
 
 template <typename T>

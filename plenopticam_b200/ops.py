@@ -331,6 +331,22 @@ def percentile(data, q, luma=False):
     return res
 
 
+def contrast_bounds(ref, q_lo=0.005, q_hi=99.9, lohi=None, scratch=None):
+    """[percentile(rgb2gry(ref), q_lo), percentile(ref, q_hi)] of a (..., 3) float32 reference image as a float64 CUDA
+    tensor of 2 (lfp_extractor/lfp_contrast.py:252-255), one cooperative launch."""
+    _chk_dev(ref)
+    if ref.dtype != torch.float32 or ref.shape[-1] != 3:
+        raise TypeError("float32 (..., 3) reference image expected")
+    L = nat.lib()
+    if lohi is None:
+        lohi = torch.empty(2, dtype=torch.float64, device=ref.device)
+    if scratch is None:
+        scratch = torch.empty(int(L.pcb_percentile_scratch_bytes()), dtype=torch.uint8, device=ref.device)
+    nat.check(L.pcb_contrast_bounds(_ptr(ref), ref.numel() // 3, float(q_lo), float(q_hi), _ptr(lohi), _ptr(scratch),
+                                    _stream()))
+    return lohi
+
+
 def contrast_srgb(stack, lohi, mm=None, out=None):
     """clip((x-lo)/(hi-lo)) then sRGB; `lohi` is a float64 CUDA tensor [lo, hi]; a bound that is exactly 0
     is replaced on the device by the data min/max in `mm` (misc/normalizer.py:40-41)."""
@@ -346,10 +362,7 @@ def refocuser_postprocess(stack, mm=None, out=None):
     """LfpRefocuser.shift_and_sum's colour management (lfp_refocuser/top_level.py:68-70), on the device and
     without a host round trip: lo = P0.005(luma(stack[0])), hi = P99.9(stack[0]), normalise, sRGB.
     `mm`: min/max keys of the stack (computed here if not supplied by the refocus launch)."""
-    ref = stack[0]
-    lohi = torch.empty(2, dtype=torch.float64, device=stack.device)
-    lohi[0:1] = percentile(ref, [0.005], luma=True)
-    lohi[1:2] = percentile(ref, [99.9], luma=False)
+    lohi = contrast_bounds(stack[0])
     if mm is None:
         mm = minmax_f32(stack)
     return contrast_srgb(stack, lohi, mm=mm, out=out)

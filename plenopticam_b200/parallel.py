@@ -99,8 +99,7 @@ def sharded_refocus_stack(vp, a_list, group=None, postprocess=True, refi=False, 
         src = owner_of(0, len(a_list), world)
         lohi = torch.empty(2, dtype=torch.float64, device=vp.device)
         if rank == src:
-            lohi[0:1] = ops.percentile(local[0], [0.005], luma=True)
-            lohi[1:2] = ops.percentile(local[0], [99.9], luma=False)
+            ops.contrast_bounds(local[0], 0.005, 99.9, lohi=lohi)
         broadcast_bounds(lohi, src, group)
         # Normalizer's falsy-bound fallback needs the min/max of the WHOLE stack (misc/normalizer.py:40-41)
         keys = mm.view(torch.int32).clone()

@@ -82,11 +82,7 @@ class LightFieldPipeline(object):
     def post_process(self, out=None):
         out = self.post if out is None else out
         L, p, st = nat.lib(), ops._ptr, ops._stream()
-        n0 = self.S * self.T * 3
-        nat.check(L.pcb_percentile_f32(p(self.stack), n0 // 3, 1, self._q_lo, 1, C.c_void_p(self.lohi.data_ptr()),
-                                       p(self.scratch), st))
-        nat.check(L.pcb_percentile_f32(p(self.stack), n0, 0, self._q_hi, 1, C.c_void_p(self.lohi.data_ptr() + 8),
-                                       p(self.scratch), st))
+        ops.contrast_bounds(self.stack[0], 0.005, 99.9, lohi=self.lohi, scratch=self.scratch)
         nat.check(L.pcb_contrast_srgb(p(self.stack), self.stack.numel(), p(self.lohi), p(self.mm_stack),
                                       p(out), st))
         return out

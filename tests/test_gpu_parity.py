@@ -402,3 +402,20 @@ def test_exporter_quantisation_and_quantised_exposure_stream(cuda, bits):
         f = pipe.run(r)
         ref = np.asarray(np.round(np.clip((f - f.min()) / (f.max() - f.min()), 0, 1) * lv), dtype=dt)
         assert got.dtype == dt and np.array_equal(got, ref), k
+
+
+@pytest.mark.gpu
+def test_contrast_bounds_single_launch_equals_numpy_percentiles(cuda):
+    from plenopticam_b200 import ops
+    rng = np.random.default_rng(41)
+    for shape, scale in (((97, 113, 3), 1000.0), ((434, 625, 3), 70000.0), ((5, 4, 3), 1.0)):
+        x = (rng.random(shape) ** 2 * scale).astype(np.float32)
+        x[0, 0] = 0.0
+        got = ops.contrast_bounds(ops.to_device(x)).cpu().numpy()
+        lum = (0.2126 * x[..., 0].astype(np.float64) + 0.7152 * x[..., 1].astype(np.float64)
+               + 0.0722 * x[..., 2].astype(np.float64)).astype(np.float32)
+        assert got[0] == np.percentile(lum.astype(np.float64), 0.005)
+        assert got[1] == np.percentile(x.astype(np.float64), 99.9)
+        two = np.array([ops.percentile(ops.to_device(x), [0.005], luma=True).cpu().numpy()[0],
+                        ops.percentile(ops.to_device(x), [99.9]).cpu().numpy()[0]])
+        assert np.array_equal(got, two)
