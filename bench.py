@@ -393,7 +393,7 @@ def main():
     if dom == "refocus_int":
         # the stage is not HBM-limited: one shared-memory read per (pixel, view, slice) is what bounds it
         roofline["on_chip_limiter"] = ("shared-memory wavefronts: LSU data pipe 80-84 % busy in refocus_pxp_kernel "
-                                       "(ncu, profiles/r01b_prof_step.txt; DESIGN.md 4.3)")
+                                       "(ncu, profiles/r01c_prof_step.txt; DESIGN.md 4.3)")
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
         with open(tr_path) as f:
