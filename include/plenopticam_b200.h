@@ -231,6 +231,20 @@ int pcb_hex_align(const float *prj, int prows, int pcols, int C, int strips, int
 int pcb_unpack_bayer(const uint8_t *buf, int64_t nbytes, int bits, uint16_t *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Bayer white balance with highlight protection and soft clipping ("next" row f1) — replaces
+ * CfaProcessor.safe_bayer_awb (lfp_aligner/cfa_processor.py:233-250) = _reshape_bayer (:96-114) +
+ * _correct_bayer_highlights (:171-203) + apply_awb (:142-169) + clamp + soft_clipping (:252-255) on a 2-D mosaic.
+ *   bay, wht : (H, W) float32 on the device (wht may be NULL: a white image of ones), H and W even
+ *   gains_host[4] : HOST pointer, gains of the quad positions (0,0) (0,1) (1,0) (1,1) as CfaProcessor.set_gains
+ *                   (:257-279) orders them for the Bayer pattern
+ *   soft_clip : 1 when cfg.lfpimg has 'exp'; max_lum = 2^-exp; b = exp(7), log1pb = log(1 + exp(7)) as the caller's
+ *               libm rounds them (so the constants equal numpy's)
+ *   out : (H, W) float64.  Bit-identical to the reference up to the soft clipping (exp/log: <= 1 ulp apart).
+ * ------------------------------------------------------------------------------------------------ */
+int pcb_cfa_safe_awb(const float *bay, const float *wht, int H, int W, const double *gains_host, int soft_clip,
+                     double max_lum, double b, double log1pb, double *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Scheimpflug composite ("next" row) — replaces LfpScheimpflug.scheimpflug_from_stack
  * (lfp_refocuser/lfp_scheimpflug.py:68-114): out[y,x,:] = stack[a_map[y,x]][y,x,:] with
  *   mode 0: a_map = a_y[y]   mode 1: a_map = a_x[x]   mode 2: a_map = (a_x[x] + a_y[y]) / 2  (integer mean, :94)

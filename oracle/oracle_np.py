@@ -778,3 +778,53 @@ def resample_global(raw, centroids, pat_type, hex_odd=None):
     if pat_type == 'rec':
         return prj, pitch
     return global_hex_alignment(prj, pitch, LY, LX, hex_odd)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Bayer white balance with highlight protection (lfp_aligner/cfa_processor.py:142-169,171-203,233-255,257-279)
+# ------------------------------------------------------------------------------------------------------
+def cfa_gains(awb, bay_pat):
+    """CfaProcessor.set_gains for a 2-D Bayer image (cfa_processor.py:257-279): per Bayer-quad position gains."""
+    if bay_pat == "GRBG":
+        return np.array([awb[2], awb[1], awb[0], awb[3]], dtype=np.float64)
+    if bay_pat == "BGGR":
+        return np.array([awb[0], awb[2], awb[3], awb[1]], dtype=np.float64)
+    raise ValueError("CfaProcessor.set_gains: Bayer pattern %r is not handled by the reference" % (bay_pat,))
+
+
+def cfa_safe_bayer_awb(bay_img, wht_img, awb, bay_pat, exp_bias=None):
+    """CfaProcessor.safe_bayer_awb (cfa_processor.py:233-250) on a 2-D Bayer image: float64 (H, W).
+    The dtype flow of the reference is kept (float32 inputs, float64 gains and results)."""
+    bay = np.asarray(bay_img).astype('float32')
+    q = np.dstack((bay[0::2, 0::2], bay[0::2, 1::2], bay[1::2, 0::2], bay[1::2, 1::2]))
+    gains = cfa_gains(awb, bay_pat)
+    if wht_img is None:
+        wq = np.ones(q.shape)
+    else:
+        w = np.asarray(wht_img).astype('float32')
+        wq = np.dstack((w[0::2, 0::2], w[0::2, 1::2], w[1::2, 0::2], w[1::2, 1::2]))
+    fact = gains.max()
+    out = q.copy()
+    min_sat, min_idx = q.min(2), q.argmin(2)
+    min_sat_bal = min_sat * gains[min_idx]
+    min_sat = min_sat * wq.mean(2)
+    min_sat[min_sat > 1] = 1
+    min_sat **= 2
+    for i in range(4):
+        ref = np.divide(.99, wq[..., i], out=np.ones_like(wq[..., i]) * float('Inf'), where=wq[..., i] != 0)
+        ref[~np.isfinite(ref)] = 0
+        sel = q[..., i] > ref
+        inm = (min_sat_bal * (1 - min_sat) + q[..., i] * fact * min_sat) / gains[i]
+        out[..., i][sel] = np.maximum(q[..., i][sel].astype('float64'), inm[sel])
+    res = np.zeros(np.array(q.shape[:2]) * 2)
+    res[0::2, 0::2], res[0::2, 1::2], res[1::2, 0::2], res[1::2, 1::2] = (out[..., k] for k in range(4))
+    res[0::2, 0::2] *= gains[0]
+    res[0::2, 1::2] *= gains[1]
+    res[1::2, 0::2] *= gains[2]
+    res[1::2, 1::2] *= gains[3]
+    res[res < 0] = 0
+    if exp_bias is not None:
+        max_lum = 2 ** (-exp_bias)
+        b = np.exp(7)
+        res = np.log((1 + b) / (1 + b * np.exp(-7 * (res / max_lum)))) / np.log(1 + b) * max_lum
+    return res

@@ -103,6 +103,7 @@ _SIGNATURES = {
     "pcb_hex_align": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp,
                            _vp, _vp, _vp]),
     "pcb_unpack_bayer": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "pcb_cfa_safe_awb": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_double), _i, C.c_double, C.c_double, C.c_double, _vp, _vp]),
     "pcb_scheimpflug": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pcb_devig_white": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "pcb_devig_normalize": (_i, [_vp, _i64, _vp, _vp]),

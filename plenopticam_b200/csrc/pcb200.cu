@@ -4,6 +4,7 @@
 #include "post.cuh"
 #include "devignette.cuh"
 #include "scheimpflug.cuh"
+#include "cfa.cuh"
 #include "unpack.cuh"
 #include "refocus.cuh"
 #include "refocus_rows.cuh"
@@ -471,6 +472,25 @@ int pcb_unpack_bayer(const uint8_t *buf, int64_t nbytes, int bits, uint16_t *out
         PCB_REQUIRE(ng > 0, "at least one 3-byte group");
         unpack12_kernel<<<grid_for(ng, 256 * 4), 256, 0, st>>>(buf, ng, out);
     }
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+int pcb_cfa_safe_awb(const float *bay, const float *wht, int H, int W, const double *gains_host, int soft_clip,
+                     double max_lum, double b, double log1pb, double *out, void *stream) {
+    PCB_REQUIRE(bay && out && gains_host, "null pointer");
+    PCB_REQUIRE(H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0, "mosaic needs even, positive dimensions");
+    PCB_REQUIRE((reinterpret_cast<uintptr_t>(bay) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                (wht == nullptr || (reinterpret_cast<uintptr_t>(wht) & 7) == 0), "buffers must be 8 / 16 byte aligned");
+    PCB_REQUIRE(!soft_clip || max_lum > 0.0, "max_lum must be positive");
+    CfaArgs a;
+    a.bay = bay; a.wht = wht; a.H = H; a.W = W; a.out = out;
+    a.fact = gains_host[0];
+    for (int i = 0; i < 4; ++i) { a.g[i] = gains_host[i]; if (gains_host[i] > a.fact) a.fact = gains_host[i]; }
+    a.soft_clip = soft_clip; a.max_lum = max_lum; a.b = b; a.log1pb = log1pb;
+    dim3 grid((W / 2 + 255) / 256, H / 2);
+    if (wht) cfa_safe_awb_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(a);
+    else cfa_safe_awb_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(a);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }

@@ -506,3 +506,28 @@ def hex_align(prj, plan, LY):
                                       int(plan["wx_vals"].shape[0]), plan["x_len"], plan["crop_lo"], out_cols, _ptr(wy),
                                       plan["y_len"], _ptr(stretched), _ptr(tmpx), _ptr(out), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# Bayer white balance (lfp_aligner/cfa_processor.py:233-255)
+# ------------------------------------------------------------------------------------------------------
+def cfa_safe_awb(bay, wht, gains, exp_bias=None, out=None):
+    """CfaProcessor.safe_bayer_awb on a 2-D float32 mosaic (CUDA): float64 (H, W).  `gains`: the four quad-position
+    gains as CfaProcessor.set_gains orders them; `wht` float32 (H, W) or None."""
+    _chk_dev(bay) if wht is None else _chk_dev(bay, wht)
+    if bay.dtype != torch.float32 or bay.dim() != 2 or (wht is not None and (wht.dtype != torch.float32 or
+                                                                          tuple(wht.shape) != tuple(bay.shape))):
+        raise TypeError("float32 (H, W) mosaic (and white image of the same shape) expected")
+    H, W = (int(v) for v in bay.shape)
+    g = np.ascontiguousarray(np.asarray(gains, dtype=np.float64).ravel())
+    if g.size != 4:
+        raise ValueError("four Bayer gains expected")
+    if out is None:
+        out = torch.empty((H, W), dtype=torch.float64, device=bay.device)
+    soft = exp_bias is not None
+    max_lum = float(2 ** (-exp_bias)) if soft else 1.0
+    b = float(np.exp(7))
+    nat.check(nat.lib().pcb_cfa_safe_awb(_ptr(bay), None if wht is None else _ptr(wht), H, W,
+                                         g.ctypes.data_as(C.POINTER(C.c_double)), int(soft), max_lum, b,
+                                         float(np.log(1 + b)), _ptr(out), _stream()))
+    return out
