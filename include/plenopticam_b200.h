@@ -199,6 +199,11 @@ int pcb_contrast_bounds(const float *ref, int64_t npx, double q_lo, double q_hi,
 int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi,
                       const pcb_minmax_t *mm /* nullable: fallback for a bound that is exactly 0 */,
                       float *out, void *stream);
+/* Same with a uint16 / uint8 / float32 input (dtype PCB_U16 / PCB_U8 / PCB_F32): LfpContrast.main of the extractor
+ * (lfp_extractor/lfp_contrast.py:43-67) runs auto_hist_align + srgb_conv over the integer-typed 4-D light field;
+ * Normalizer reads it as float32 (misc/normalizer.py:36), which is exact for these types. */
+int pcb_contrast_srgb_typed(const void *in, int dtype, int64_t n, const double *lohi, const pcb_minmax_t *mm,
+                            float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Global rectification ("next" row; the reference's default smp_meth) — device side of

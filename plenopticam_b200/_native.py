@@ -98,6 +98,7 @@ _SIGNATURES = {
     "pcb_contrast_bounds": (_i, [_vp, _i64, C.c_double, C.c_double, _vp, _vp, _vp]),
     "pcb_percentile_f64": (_i, [_vp, _i64, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
     "pcb_contrast_srgb": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "pcb_contrast_srgb_typed": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "pcb_image_minmax": (_i, [_vp, _i, _i64, _vp, _vp]),
     "pcb_warp_projective": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_double), _i, _i, _vp, _vp, _vp]),
     "pcb_hex_align": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp,

@@ -505,12 +505,24 @@ int pcb_scheimpflug(const float *stack, int N, int S, int T, int C, const int32_
     return PCB_OK;
 }
 
-int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, const pcb_minmax_t *mm, float *out,
-                      void *stream) {
+int pcb_contrast_srgb_typed(const void *in, int dtype, int64_t n, const double *lohi, const pcb_minmax_t *mm, float *out,
+                            void *stream) {
     PCB_REQUIRE(in != nullptr && out != nullptr && lohi != nullptr && n > 0, "in, out, lohi, n > 0");
-    contrast_srgb_kernel<<<grid_for(n, 256 * 8), 256, 0, as_stream(stream)>>>(in, n, lohi, mm, out);
+    const int g = grid_for(n, 256 * 8);
+    cudaStream_t st = as_stream(stream);
+    switch (dtype) {
+    case PCB_F32: contrast_srgb_kernel<float><<<g, 256, 0, st>>>((const float *)in, n, lohi, mm, out); break;
+    case PCB_U16: contrast_srgb_kernel<uint16_t><<<g, 256, 0, st>>>((const uint16_t *)in, n, lohi, mm, out); break;
+    case PCB_U8:  contrast_srgb_kernel<uint8_t><<<g, 256, 0, st>>>((const uint8_t *)in, n, lohi, mm, out); break;
+    default: return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", "pcb_contrast_srgb_typed", dtype);
+    }
     PCB_LAUNCH_OK();
     return PCB_OK;
+}
+
+int pcb_contrast_srgb(const float *in, int64_t n, const double *lohi, const pcb_minmax_t *mm, float *out,
+                      void *stream) {
+    return pcb_contrast_srgb_typed(in, PCB_F32, n, lohi, mm, out, stream);
 }
 
 }  // extern "C"

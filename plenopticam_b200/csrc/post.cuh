@@ -61,8 +61,31 @@ __device__ __forceinline__ float contrast_srgb_one(float x, double lo, double in
                            : __fmul_rn(y, 12.92f);
 }
 
+// four consecutive samples as float4 (uint16 / uint8 inputs are integer-valued, exact in float32 like the
+// reference's np.asarray(data, dtype='float32'), misc/normalizer.py:36)
+template <typename T> struct Vec4In;
+template <> struct Vec4In<float> {
+    static constexpr int ALIGN = 16;
+    __device__ static __forceinline__ float4 ld(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+};
+template <> struct Vec4In<uint16_t> {
+    static constexpr int ALIGN = 8;
+    __device__ static __forceinline__ float4 ld(const uint16_t *p) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(p));
+        return make_float4((float)(w.x & 0xffffu), (float)(w.x >> 16), (float)(w.y & 0xffffu), (float)(w.y >> 16));
+    }
+};
+template <> struct Vec4In<uint8_t> {
+    static constexpr int ALIGN = 4;
+    __device__ static __forceinline__ float4 ld(const uint8_t *p) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p));
+        return make_float4((float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu), (float)(w >> 24));
+    }
+};
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-contrast_srgb_kernel(const float *__restrict__ in, int64_t n, const double *__restrict__ lohi,
+contrast_srgb_kernel(const T *__restrict__ in, int64_t n, const double *__restrict__ lohi,
                      const pcb_minmax_t *__restrict__ mm, float *__restrict__ out) {
     double lo = lohi[0], hi = lohi[1];
     if (mm != nullptr) {   // misc/normalizer.py:40-41: a falsy bound falls back to the data's own min / max
@@ -73,12 +96,12 @@ contrast_srgb_kernel(const float *__restrict__ in, int64_t n, const double *__re
     const double inv = scale ? 1.0 / (hi - lo) : 1.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = n >> 2;
-    const float4 *in4 = reinterpret_cast<const float4 *>(in);
     float4 *out4 = reinterpret_cast<float4 *>(out);
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & (Vec4In<T>::ALIGN - 1)) == 0 &&
+                        (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     if (vec_ok) {
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-            float4 v = __ldg(in4 + i);
+            float4 v = Vec4In<T>::ld(in + 4 * i);
             v.x = contrast_srgb_one(v.x, lo, inv, scale);
             v.y = contrast_srgb_one(v.y, lo, inv, scale);
             v.z = contrast_srgb_one(v.z, lo, inv, scale);
@@ -86,10 +109,10 @@ contrast_srgb_kernel(const float *__restrict__ in, int64_t n, const double *__re
             out4[i] = v;
         }
         for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-            out[i] = contrast_srgb_one(__ldg(in + i), lo, inv, scale);
+            out[i] = contrast_srgb_one(ld_as_float(in + i), lo, inv, scale);
     } else {
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-            out[i] = contrast_srgb_one(__ldg(in + i), lo, inv, scale);
+            out[i] = contrast_srgb_one(ld_as_float(in + i), lo, inv, scale);
     }
 }
 

@@ -352,10 +352,30 @@ def contrast_srgb(stack, lohi, mm=None, out=None):
     is replaced on the device by the data min/max in `mm` (misc/normalizer.py:40-41)."""
     _chk_dev(stack, lohi)
     if out is None:
-        out = torch.empty_like(stack)
-    nat.check(nat.lib().pcb_contrast_srgb(_ptr(stack), stack.numel(), _ptr(lohi),
-                                          _ptr(mm) if mm is not None else C.c_void_p(0), _ptr(out), _stream()))
+        out = torch.empty(tuple(stack.shape), dtype=torch.float32, device=stack.device)
+    nat.check(nat.lib().pcb_contrast_srgb_typed(_ptr(stack), _pcb_dtype(stack), stack.numel(), _ptr(lohi),
+                                                _ptr(mm) if mm is not None else C.c_void_p(0), _ptr(out), _stream()))
     return out
+
+
+def image_minmax(data, mm=None):
+    """Running min / max keys of a uint8 / uint16 / float32 CUDA tensor."""
+    _chk_dev(data)
+    mm = new_minmax() if mm is None else mm
+    nat.check(nat.lib().pcb_image_minmax(_ptr(data), _pcb_dtype(data), data.numel(), _ptr(mm), _stream()))
+    return mm
+
+
+def viewpoints_contrast(vp, ref_view=None, out=None):
+    """LfpContrast.main with its options off (lfp_extractor/lfp_contrast.py:62-65): histogram alignment of the whole
+    light field against the central view (lo = P0.005 of its luma, hi = P99.9) and sRGB; float32 like the reference."""
+    _chk_dev(vp)
+    if ref_view is None:
+        c = int(vp.shape[0]) // 2
+        ref_view = vp[c, c]
+    ref32 = ref_view.to(torch.float32).contiguous()
+    lohi = contrast_bounds(ref32)
+    return contrast_srgb(vp, lohi, mm=image_minmax(vp), out=out)
 
 
 def refocuser_postprocess(stack, mm=None, out=None):
