@@ -113,6 +113,17 @@ __device__ __forceinline__ void block_minmax_commit(float mn, float mx, pcb_minm
 // reciprocal-multiply with one FMA correction: with inv = RN(1/d),  q = RN(num*inv),  r = num - d*q (exact in an
 // FMA),  q' = RN(q + r*inv)  is the correctly rounded num/d (4 instructions instead of the ~12 of a generic
 // __fdiv_rn with its slow-path check).
+// Correctly rounded a / d for a divisor that is the same for every sample (Markstein, see above); checked exhaustively
+// against __fdiv_rn for a < 2^24, d = 1..16 (tools/checks/div_by_const.cu).
+struct DivByConst {
+    float d, inv;
+    __device__ __forceinline__ void init(float d_) { d = d_; inv = __frcp_rn(d_); }
+    __device__ __forceinline__ float operator()(float a) const {
+        const float q = __fmul_rn(a, inv);
+        return __fmaf_rn(__fmaf_rn(-d, q, a), inv, q);
+    }
+};
+
 struct QuantU16 {
     float mn, d, inv;
     bool scale;

@@ -201,8 +201,10 @@ refocus_px_kernel(PxArgs p, PxCtl ctl) {
 }
 
 // out[n,y,x,:] = (acc[n,y,x] + sum_{j: source row clamped} edge[n,j,side,x]) / M ;  fused min/max.
-// The three floats of a pixel are transposed through shared memory so that the row leaves in 128-byte runs.
+// The three floats of a pixel are transposed through shared memory (warp-locally) so that the row leaves in
+// 128-byte runs.
 constexpr int PXF_THREADS = 256;
+constexpr int PXF_IT = 3;          // row segments whose accumulator loads are in flight together
 
 template <bool EXACT24>
 __global__ void __launch_bounds__(PXF_THREADS)
@@ -226,34 +228,50 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
     const int cnt = s_cnt;
     const size_t arow = ((size_t)n * S + y) * Tp;
     float *orow = out + ((size_t)n * S + y) * (size_t)T * 3;
-    const float fM = (float)M;
+    DivByConst divM;
+    divM.init((float)M);
     float mn = INFINITY, mx = -INFINITY;
-    for (int xb = 0; xb < T; xb += PXF_THREADS) {
-        const int x = xb + threadIdx.x;
-        if (x < T) {
-            unsigned long long rg = accRG[arow + x];
-            uint32_t b = accB[arow + x];
-            for (int c = 0; c < cnt; ++c) {
-                rg += __ldg(edgeRG + (size_t)s_rows[c] * Tp + x);
-                b += __ldg(edgeB + (size_t)s_rows[c] * Tp + x);
-            }
-            const uint32_t v[3] = {(uint32_t)rg, (uint32_t)(rg >> 32), b};
+    // the accumulator words of PXF_IT row segments are requested up front (the kernel is bound by the latency of
+    // these loads, not by their bandwidth); each segment then goes through the shared-memory transposition
+    for (int xb0 = 0; xb0 < T; xb0 += PXF_THREADS * PXF_IT) {
+        unsigned long long rg[PXF_IT];
+        uint32_t b[PXF_IT];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const float f = EXACT24 ? __fdiv_rn((float)v[ch], fM) : (float)((double)v[ch] / (double)M);
-                s_tile[threadIdx.x * 3 + ch] = f;
-                mn = fminf(mn, f);
-                mx = fmaxf(mx, f);
-            }
+        for (int k = 0; k < PXF_IT; ++k) {
+            const int x = xb0 + k * PXF_THREADS + threadIdx.x;
+            rg[k] = 0ull; b[k] = 0u;
+            if (x < T) { rg[k] = accRG[arow + x]; b[k] = accB[arow + x]; }
         }
-        __syncthreads();
-        const int ne = min(PXF_THREADS, T - xb) * 3;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int e = threadIdx.x + k * PXF_THREADS;
-            if (e < ne) orow[(size_t)xb * 3 + e] = s_tile[e];
+        for (int k = 0; k < PXF_IT; ++k) {
+            const int xb = xb0 + k * PXF_THREADS;
+            if (xb >= T) break;
+            const int x = xb + threadIdx.x;
+            if (x < T) {
+                for (int c = 0; c < cnt; ++c) {
+                    rg[k] += __ldg(edgeRG + (size_t)s_rows[c] * Tp + x);
+                    b[k] += __ldg(edgeB + (size_t)s_rows[c] * Tp + x);
+                }
+                const uint32_t v[3] = {(uint32_t)rg[k], (uint32_t)(rg[k] >> 32), b[k]};
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float f = EXACT24 ? divM((float)v[ch]) : (float)((double)v[ch] / (double)M);
+                    s_tile[threadIdx.x * 3 + ch] = f;
+                    mn = fminf(mn, f);
+                    mx = fmaxf(mx, f);
+                }
+            }
+            // a warp's 32 pixels are 96 consecutive floats of the output row: the transposition stays inside the warp
+            __syncwarp();
+            const int wb = (threadIdx.x & ~31) * 3, lane = threadIdx.x & 31;
+            const int ne = (min(PXF_THREADS, T - xb) - (int)(threadIdx.x & ~31)) * 3;     // elements this warp owns
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int e = lane + q * 32;
+                if (e < ne) orow[(size_t)xb * 3 + wb + e] = s_tile[wb + e];
+            }
+            __syncwarp();
         }
-        __syncthreads();
     }
     if (mm != nullptr) block_minmax_commit(mn, mx, mm);
 }

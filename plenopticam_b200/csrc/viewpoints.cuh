@@ -25,49 +25,26 @@ viewpoints_kernel(const T *__restrict__ aligned, T *__restrict__ vp, int cols_el
 
     const T *src = aligned + (size_t)(s * M_in + kc + j) * cols_elems + (size_t)t0 * M_in * C;
     const int n_in = nt * M_in * C;
-    // read the row with VP_UNROLL independent loads in flight per thread (the copy is latency-bound otherwise).
-    // 2-byte elements travel as aligned 32-bit words (the row may start on either half of a word: the shared-memory
-    // copy keeps that parity), which halves the load and shared-store instructions.
-    constexpr int VP_UNROLL = 8;
-    bool by_words = false;
-    if constexpr (sizeof(T) == 2) {
-        const int par = (int)((reinterpret_cast<uintptr_t>(src) >> 1) & 1);
-        const size_t off = (size_t)(src - aligned);
-        by_words = (reinterpret_cast<uintptr_t>(aligned) & 3) == 0 && off + n_in + 1 <= total_elems;
-        if (by_words) {
-            const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(src - par);
-            uint32_t *wrow = reinterpret_cast<uint32_t *>(smem_raw);
-            const int nw = (n_in + par + 1) >> 1;
-            for (int base = threadIdx.x; base < nw; base += 256 * VP_UNROLL) {
-                uint32_t v[VP_UNROLL];
-#pragma unroll
-                for (int u = 0; u < VP_UNROLL; ++u) {
-                    const int idx = base + u * 256;
-                    if (idx < nw) v[u] = __ldg(wsrc + idx);
-                }
-#pragma unroll
-                for (int u = 0; u < VP_UNROLL; ++u) {
-                    const int idx = base + u * 256;
-                    if (idx < nw) wrow[idx] = v[u];
-                }
-            }
-            row += par;
-        }
-    }
-    if (!by_words) {
-        for (int base = threadIdx.x; base < n_in; base += 256 * VP_UNROLL) {
-            T v[VP_UNROLL];
-#pragma unroll
-            for (int u = 0; u < VP_UNROLL; ++u) {
-                const int idx = base + u * 256;
-                if (idx < n_in) v[u] = __ldg(src + idx);
-            }
-#pragma unroll
-            for (int u = 0; u < VP_UNROLL; ++u) {
-                const int idx = base + u * 256;
-                if (idx < n_in) row[idx] = v[u];
-            }
-        }
+    // The row is copied with 16-byte asynchronous global -> shared copies (no register staging, the whole tile in
+    // flight at once).  Rows start at arbitrary element alignment (row pitch 56 250 B at Illum size): the shared-memory
+    // copy starts at the same offset inside a 16-byte line as the source, so the 16-byte interior lines up on both
+    // sides; the few head / tail elements are copied by plain loads.
+    {
+        const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+        row = reinterpret_cast<T *>(smem_raw + mis);
+        constexpr int EPL = 16 / (int)sizeof(T);                           // elements per 16-byte line
+        const int head = min(n_in, mis ? (16 - mis) / (int)sizeof(T) : 0);
+        const int nlines = (n_in - head) / EPL;
+        const int tail0 = head + nlines * EPL;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(row + head);
+        const T *gbase = src + head;
+        for (int k = threadIdx.x; k < nlines; k += 256)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * k), "l"(gbase + (size_t)k * EPL)
+                         : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (threadIdx.x < head) row[threadIdx.x] = __ldg(src + threadIdx.x);
+        if (threadIdx.x < n_in - tail0) row[tail0 + threadIdx.x] = __ldg(src + tail0 + threadIdx.x);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 
@@ -132,7 +109,7 @@ crop_kernel(const T *__restrict__ aligned, T *__restrict__ cropped, int cols_ele
 }
 
 static inline int vp_tile(int Tn, int M, int C, int esz, int *tile_t, int *ntile, size_t *smem) {
-    const size_t budget = 48 * 1024 - 8;          // default dynamic shared-memory limit minus the parity word
+    const size_t budget = 48 * 1024 - 16;         // default dynamic shared-memory limit minus the alignment slack
     const size_t row_bytes = (size_t)Tn * M * C * esz;
     int nt = (int)((row_bytes + budget - 1) / budget);
     if (nt < 1) nt = 1;
@@ -140,7 +117,7 @@ static inline int vp_tile(int Tn, int M, int C, int esz, int *tile_t, int *ntile
     if ((size_t)tt * M * C * esz > budget) return 1;   // a single micro-image row exceeds the budget
     *tile_t = tt;
     *ntile = (Tn + tt - 1) / tt;
-    *smem = (size_t)tt * M * C * esz + 8;      // + one word: rows staged as 32-bit words keep their parity
+    *smem = (size_t)tt * M * C * esz + 16;     // + one line: the staged row keeps the source's offset inside a 16-byte line
     return 0;
 }
 
