@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--small", action="store_true", help="reduced shape (smoke-testing the harness only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fuse-post", action="store_true",
+                    help="linear stack + separate contrast kernels instead of the fused refocus epilogue")
     return ap.parse_args()
 
 
@@ -240,7 +242,9 @@ def workload_config(w, args):
     return {"workload": "illum_align+viewpoints+refocus%d (raw %dx%dx%d u16, %dx%d hex lenslets, M=%d, a in [%d,%d))"
                         % (args.slices, w["W"], w["H"], w["C"], w["LY"], w["LX"], w["M"], w["ran_refo"][0], w["ran_refo"][1]),
             "exposures_per_gpu_per_step": 1, "l2_policy": "inputs larger than L2 (249 MB raw per exposure, ring of 3)",
-            "parallelism": "exposures sharded over GPUs, no data-path collective"}
+            "parallelism": "exposures sharded over GPUs, no data-path collective",
+            "post": "separate contrast kernels" if getattr(args, "no_fuse_post", False)
+                    else "contrast + sRGB fused into the refocus epilogue"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -280,7 +284,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    stage_names = ["resample_minmax", "resample_u16", "viewpoints", "refocus_int", "post"]
+    # default: colour management fused into the refocus epilogue (pcb_refocus_int_srgb): four stages; --no-fuse-post
+    # runs the linear stack + contrast kernels separately (five stages, one more pass over the stack)
+    fused = not args.no_fuse_post
+    stage_names = ["resample_minmax", "resample_u16", "viewpoints", "refocus_int"] + ([] if fused else ["post"])
     from plenopticam_b200 import ops
     L, p = _native.lib(), ops._ptr
 
@@ -294,6 +301,11 @@ def main():
         if ev: ev[2].record(stream)
         pipe.viewpoints()
         if ev: ev[3].record(stream)
+        if fused:
+            if pipe.refocus_post() is False:
+                raise SystemExit("bench.py: the fused refocus epilogue does not apply to this workload")
+            if ev: ev[4].record(stream)
+            return
         pipe.refocus()
         if ev: ev[4].record(stream)
         pipe.post_process()
@@ -416,7 +428,7 @@ def main():
         "aligned_lfs_per_s": world * K / (elapsed_ms * 1e-3),
         "stage_ms": stage_ms, "stage_gbs": stage_gbs,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-        "gpu_launches": 9 * K, "clocks": clocks,
+        "gpu_launches": (10 if fused else 9) * K, "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:

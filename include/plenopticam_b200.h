@@ -142,6 +142,19 @@ int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C
                            const int32_t *a_list_dev, int N, const uint8_t *view_zeroed_dev,
                            float *out, pcb_minmax_t *mm, void *stream);
 
+/* pcb_refocus_int with LfpRefocuser.shift_and_sum's colour management (lfp_refocuser/top_level.py:68-70) fused into the
+ * epilogue — the "fused normalisation and contrast clipping" form of the stack: out receives
+ * srgb(clip((x - lo) / (hi - lo))) with lo = percentile(rgb2gry(slice 0), q_lo), hi = percentile(slice 0, q_hi), the
+ * linear stack is never written (one pass over N slices less).  Same values as pcb_refocus_int + pcb_contrast_bounds +
+ * pcb_contrast_srgb, bit for bit.  ref_slice: (S,T,C) float32 scratch (linear slice 0), lohi: double[2] (device, out),
+ * pscratch: pcb_percentile_scratch_bytes(), mm: reset by the caller, receives min / max of the LINEAR stack (a bound
+ * that is exactly 0 falls back to them, misc/normalizer.py:40-41, through a fix-up launch that otherwise returns at
+ * once).  PCB_ERR_UNSUPPORTED when the packed-pixel kernel does not apply (not uint16 RGB, M > 16, rows > 2048 px). */
+int pcb_refocus_int_srgb(const void *vp, int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
+                         const uint8_t *view_zeroed_host, void *scratch, int64_t scratch_bytes, double q_lo,
+                         double q_hi, float *ref_slice, double *lohi, void *pscratch, float *out, pcb_minmax_t *mm,
+                         void *stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * (c') Sub-pixel "refocus refinement" — replaces refo_from_vp with opt_refi (lfp_refocuser/lfp_shiftandsum.py:93-135)
  *     and the two misc.img_resize calls per view / per slice (misc/data_proc.py:57-92).

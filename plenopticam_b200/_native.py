@@ -89,6 +89,7 @@ _SIGNATURES = {
     "pcb_crop_micro_images_yx": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pcb_refocus_int_scratch_bytes": (_i64, [_i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pcb_refocus_int": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "pcb_refocus_int_srgb": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcb_refocus_int_direct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refi_prefilter": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refocus_refi": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -278,6 +278,27 @@ int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C, const
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
 
+// Shift-and-sum with the refocuser's colour management fused into the epilogue: the linear stack never reaches HBM.
+int pcb_refocus_int_srgb(const void *vp, int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
+                         const uint8_t *view_zeroed_host, void *scratch, int64_t scratch_bytes, double q_lo, double q_hi,
+                         float *ref_slice, double *lohi, void *pscratch, float *out, pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(vp != nullptr && a_list_host != nullptr && view_zeroed_host != nullptr && out != nullptr &&
+                scratch != nullptr && ref_slice != nullptr && lohi != nullptr && pscratch != nullptr && mm != nullptr,
+                "pointers");
+    PCB_REQUIRE(M > 0 && S > 0 && T > 0 && C > 0 && N > 0 && N <= 65535, "sizes");
+    PCB_REQUIRE(M % 2 == 1, "odd M (even M changes the slice shape, lfp_shiftandsum.py:123-124)");
+    PCB_REQUIRE(scratch_bytes >= pcb_refocus_int_scratch_bytes(dtype, M, S, T, C, a_list_host, N, view_zeroed_host),
+                "scratch_bytes >= pcb_refocus_int_scratch_bytes(...)");
+    const RefocusPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host, vp);
+    if (!pl.pxp.ok)
+        return fail(PCB_ERR_UNSUPPORTED, "%s: the fused epilogue exists for the packed-pixel kernel only (uint16 RGB, "
+                    "M <= 16, row <= 2048 px); use pcb_refocus_int + pcb_contrast_bounds + pcb_contrast_srgb", __func__);
+    PxpFusedPost post;
+    post.q_lo = q_lo; post.q_hi = q_hi; post.ref_slice = ref_slice; post.lohi = lohi; post.pscratch = pscratch;
+    return launch_refocus_pxp(pl.px, pl.pxp, (const uint16_t *)vp, a_list_host, view_zeroed_host, scratch, out, mm,
+                              as_stream(stream), &post);
+}
+
 // The direct (slice-stationary) form only; kept addressable for A/B measurements and as the general path.
 int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C, const int32_t *a_list_dev, int N,
                            const uint8_t *view_zeroed_dev, float *out, pcb_minmax_t *mm, void *stream) {

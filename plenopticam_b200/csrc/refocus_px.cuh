@@ -206,12 +206,31 @@ refocus_px_kernel(PxArgs p, PxCtl ctl) {
 constexpr int PXF_THREADS = 256;
 constexpr int PXF_IT = 3;          // row segments whose accumulator loads are in flight together
 
-template <bool EXACT24>
+// POST fuses the refocuser's colour management into this epilogue (LfpRefocuser.shift_and_sum,
+// lfp_refocuser/top_level.py:68-70): 0 = linear stack; 1 = clip((x - lo) / (hi - lo)) + sRGB with the bounds in
+// lohi[2], the min / max of the LINEAR values still go to *mm; 2 = fix-up pass, launched after every POST = 1 launch of
+// the stack has finished: Normalizer replaces a bound that is exactly 0 by the data min / max (misc/normalizer.py:
+// 40-41), known only then — the pass returns at once unless that changes a bound, else it rewrites the stack.
+template <bool EXACT24, int POST = 0>
 __global__ void __launch_bounds__(PXF_THREADS)
 refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const uint32_t *__restrict__ accB,
                            const unsigned long long *__restrict__ edgeRG, const uint32_t *__restrict__ edgeB,
                            PxCtl ctl, float *__restrict__ out, int M, int S, int T, int Tp, int n0,
-                           pcb_minmax_t *mm) {
+                           pcb_minmax_t *mm, const double *__restrict__ lohi = nullptr) {
+    double lo = 0.0, inv = 1.0;
+    bool scale = false;
+    if (POST) {
+        lo = lohi[0];
+        double hi = lohi[1];
+        if (POST == 2) {
+            const double dmin = (double)key_to_float(mm->kmin), dmax = (double)key_to_float(mm->kmax);
+            if (!((lo == 0.0 && dmin != 0.0) || (hi == 0.0 && dmax != 0.0))) return;
+            if (lo == 0.0) lo = dmin;
+            if (hi == 0.0) hi = dmax;
+        }
+        scale = (hi != lo) && (hi != 0.0);
+        inv = scale ? 1.0 / (hi - lo) : 1.0;
+    }
     __shared__ int s_rows[16];     // edge-table row index (n*M + j)*2 + side of every clamped contribution
     __shared__ int s_cnt;
     __shared__ float s_tile[PXF_THREADS * 3];
@@ -256,7 +275,7 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const float f = EXACT24 ? divM((float)v[ch]) : (float)((double)v[ch] / (double)M);
-                    s_tile[threadIdx.x * 3 + ch] = f;
+                    s_tile[threadIdx.x * 3 + ch] = POST ? contrast_srgb_one(f, lo, inv, scale) : f;
                     mn = fminf(mn, f);
                     mx = fmaxf(mx, f);
                 }
@@ -273,7 +292,7 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
             __syncwarp();
         }
     }
-    if (mm != nullptr) block_minmax_commit(mn, mx, mm);
+    if (POST != 2 && mm != nullptr) block_minmax_commit(mn, mx, mm);
 }
 
 struct PxPlan {

@@ -332,9 +332,31 @@ static int launch_pxp_variant(const PxpPlan &pl, const PxpArgs &a, const PxpCtl 
     return PCB_OK;
 }
 
+// Colour management fused into the finalize pass (pcb_refocus_int_srgb).
+struct PxpFusedPost {
+    double q_lo, q_hi;       // percentiles of slice 0: luma / all channels (lfp_contrast.py:252-255)
+    float *ref_slice;        // (S, T, 3) float32 scratch: the linear slice 0
+    double *lohi;            // [2] device
+    void *pscratch;          // pcb_percentile_scratch_bytes()
+};
+
+template <int POST>
+static int launch_pxp_finalize(const PxpPlan &pl, const PxpArgs &a, const PxCtl &fctl, float *out, int n0, int nloc,
+                               pcb_minmax_t *mm, const double *lohi, cudaStream_t st) {
+    dim3 fgrid(a.S, nloc);
+    if (pl.exact24)
+        refocus_px_finalize_kernel<true, POST><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, fctl, out,
+                                                                            a.M, a.S, a.T, a.Tp, n0, mm, lohi);
+    else
+        refocus_px_finalize_kernel<false, POST><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, fctl,
+                                                                             out, a.M, a.S, a.T, a.Tp, n0, mm, lohi);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
 static int launch_refocus_pxp(const PxPlan &px, const PxpPlan &pl, const uint16_t *vp, const int32_t *a_list_host,
                               const uint8_t *view_zeroed_host, void *scratch, float *out, pcb_minmax_t *mm,
-                              cudaStream_t st) {
+                              cudaStream_t st, const PxpFusedPost *post = nullptr) {
     PxpArgs a = pl.a;
     char *sp = reinterpret_cast<char *>(scratch);
     a.vp = vp;
@@ -353,25 +375,35 @@ static int launch_refocus_pxp(const PxPlan &px, const PxpPlan &pl, const uint16_
         if (ctl.nact[j]) fctl.row_active |= 1u << j;
     }
     const int N = a.N;
-    for (int n0 = 0; n0 < N; n0 += RR_MAX_SLICES) {
-        const int nloc = N - n0 < RR_MAX_SLICES ? N - n0 : RR_MAX_SLICES;
-        for (int k = 0; k < RR_MAX_SLICES; ++k) fctl.a[k] = ctl.a[k] = k < nloc ? a_list_host[n0 + k] : 0;
-        a.n0 = n0;
-        a.nsl = nloc;
-        int rc;
-        if (pl.maxt == 640)
-            rc = launch_pxp_variant<640, 1>(pl, a, ctl, st);
-        else
-            rc = pl.ppt == 1 ? launch_pxp_variant<1024, 1>(pl, a, ctl, st) : launch_pxp_variant<1024, 2>(pl, a, ctl, st);
-        if (rc) return rc;
-        dim3 fgrid(a.S, nloc);
-        if (pl.exact24)
-            refocus_px_finalize_kernel<true><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, fctl, out,
-                                                                          a.M, a.S, a.T, a.Tp, n0, mm);
-        else
-            refocus_px_finalize_kernel<false><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, fctl,
-                                                                           out, a.M, a.S, a.T, a.Tp, n0, mm);
-        PCB_LAUNCH_OK();
+    // pass: 0 = accumulate + (linear finalize | nothing), 1 = fused finalize, 2 = its fix-up
+    for (int pass = 0; pass < (post ? 3 : 1); ++pass) {
+        if (pass == 1) {                                   // bounds from the linear slice 0
+            for (int k = 0; k < RR_MAX_SLICES; ++k) fctl.a[k] = k == 0 ? a_list_host[0] : 0;
+            int rc = launch_pxp_finalize<0>(pl, a, fctl, post->ref_slice, 0, 1, nullptr, nullptr, st);
+            if (rc) return rc;
+            rc = run_contrast_bounds(post->ref_slice, (int64_t)a.S * a.T, post->q_lo, post->q_hi, post->lohi,
+                                     post->pscratch, st);
+            if (rc) return rc;
+        }
+        for (int n0 = 0; n0 < N; n0 += RR_MAX_SLICES) {
+            const int nloc = N - n0 < RR_MAX_SLICES ? N - n0 : RR_MAX_SLICES;
+            for (int k = 0; k < RR_MAX_SLICES; ++k) fctl.a[k] = ctl.a[k] = k < nloc ? a_list_host[n0 + k] : 0;
+            a.n0 = n0;
+            a.nsl = nloc;
+            int rc = PCB_OK;
+            if (pass == 0) {
+                if (pl.maxt == 640)
+                    rc = launch_pxp_variant<640, 1>(pl, a, ctl, st);
+                else
+                    rc = pl.ppt == 1 ? launch_pxp_variant<1024, 1>(pl, a, ctl, st) : launch_pxp_variant<1024, 2>(pl, a, ctl, st);
+                if (rc == PCB_OK && !post) rc = launch_pxp_finalize<0>(pl, a, fctl, out, n0, nloc, mm, nullptr, st);
+            } else if (pass == 1) {
+                rc = launch_pxp_finalize<1>(pl, a, fctl, out, n0, nloc, mm, post->lohi, st);
+            } else {
+                rc = launch_pxp_finalize<2>(pl, a, fctl, out, n0, nloc, mm, post->lohi, st);
+            }
+            if (rc) return rc;
+        }
     }
     return PCB_OK;
 }

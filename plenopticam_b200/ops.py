@@ -273,6 +273,8 @@ class RefocusPlan(object):
         if nbytes < 0:
             raise ValueError("invalid refocus configuration")
         self.scratch = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        self.fused = None            # None: not tried yet; True / False: pcb_refocus_int_srgb applies / does not
+        self.ref_slice = None
 
     def launch(self, vp, out, mm=None):
         M, S, T, Cn = self.shape
@@ -280,6 +282,29 @@ class RefocusPlan(object):
                                             _ptr(self.scratch), self.scratch.numel(), _ptr(out),
                                             _ptr(mm) if mm is not None else C.c_void_p(0), _stream()))
         return out
+
+
+def _refocus_plan_launch_srgb(self, vp, out, mm, lohi, pscratch, q_lo=0.005, q_hi=99.9):
+    """Stack with LfpRefocuser's colour management fused into the epilogue (pcb_refocus_int_srgb).  Returns False when
+    the library has no fused form for this configuration (the caller then runs the separate kernels)."""
+    if self.fused is False:
+        return False
+    M, S, T, Cn = self.shape
+    if self.ref_slice is None:
+        self.ref_slice = torch.empty((S, T, Cn), dtype=torch.float32, device=self.scratch.device)
+    try:
+        nat.check(nat.lib().pcb_refocus_int_srgb(_ptr(vp), self.dtype, M, S, T, Cn, self.a_ptr, self.N, self.z_ptr,
+                                                 _ptr(self.scratch), self.scratch.numel(), q_lo, q_hi,
+                                                 _ptr(self.ref_slice), _ptr(lohi), _ptr(pscratch), _ptr(out), _ptr(mm),
+                                                 _stream()))
+    except NotImplementedError:
+        self.fused = False
+        return False
+    self.fused = True
+    return True
+
+
+RefocusPlan.launch_srgb = _refocus_plan_launch_srgb
 
 
 def refocus_int(vp, a_list, view_zeroed=None, out=None, mm=None, plan=None):
@@ -376,6 +401,24 @@ def viewpoints_contrast(vp, ref_view=None, out=None):
     ref32 = ref_view.to(torch.float32).contiguous()
     lohi = contrast_bounds(ref32)
     return contrast_srgb(vp, lohi, mm=image_minmax(vp), out=out)
+
+
+def refocus_int_srgb(vp, a_list, view_zeroed=None, out=None, plan=None):
+    """LfpShiftAndSum + the colour management of LfpRefocuser.shift_and_sum in one go: float32 sRGB stack.  Uses the
+    fused epilogue when the library offers it for this light field, else the separate kernels (same values)."""
+    _chk_dev(vp)
+    if plan is None:
+        plan = RefocusPlan(tuple(vp.shape), vp.dtype, a_list, view_zeroed, vp.device)
+    M, S, T, Cn = plan.shape
+    if out is None:
+        out = torch.empty((plan.N, S, T, Cn), dtype=torch.float32, device=vp.device)
+    mm = new_minmax()
+    lohi = torch.empty(2, dtype=torch.float64, device=vp.device)
+    pscratch = torch.empty(int(nat.lib().pcb_percentile_scratch_bytes()), dtype=torch.uint8, device=vp.device)
+    if plan.launch_srgb(vp, out, mm, lohi, pscratch):
+        return out
+    stack = plan.launch(vp, torch.empty_like(out), mm)
+    return refocuser_postprocess(stack, mm=mm, out=out)
 
 
 def refocuser_postprocess(stack, mm=None, out=None):

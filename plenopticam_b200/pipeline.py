@@ -25,11 +25,12 @@ class LightFieldPipeline(object):
     """
 
     def __init__(self, centroids, raw_shape, raw_dtype, M, pat_type, ran_refo=(0, 2), flip=False,
-                 postprocess=True, device=None):
+                 postprocess=True, device=None, fuse_post=True):
         self.device = ops.require_cuda() if device is None else torch.device(device)
         self.M = int(M)
         self.flip = bool(flip)
         self.postprocess = bool(postprocess)
+        self.fuse_post = bool(fuse_post)     # colour management in the refocus epilogue (pcb_refocus_int_srgb)
         self.raw_shape = tuple(int(v) for v in raw_shape)
         self.raw_dtype = np.dtype(raw_dtype)
         if self.M % 2 == 0:
@@ -87,11 +88,22 @@ class LightFieldPipeline(object):
                                       p(out), st))
         return out
 
+    def refocus_post(self, out=None):
+        """Stack + colour management with the fused epilogue (the linear stack is not materialised); False when the
+        library has no fused form for this light field."""
+        out = self.post if out is None else out
+        nat.check(nat.lib().pcb_minmax_reset(ops._ptr(self.mm_stack), ops._stream()))
+        return out if self.refocus_plan.launch_srgb(self.vp, out, self.mm_stack, self.lohi, self.scratch) else False
+
     def run_device(self, raw=None, out=None):
         """All stages on the current stream; returns the final device tensor (sRGB stack, or the linear
         stack if postprocess=False)."""
         self.align(raw)
         self.viewpoints()
+        if self.postprocess and self.fuse_post:
+            res = self.refocus_post(out)
+            if res is not False:
+                return res
         self.refocus()
         if self.postprocess:
             return self.post_process(out)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--slices", type=int, default=64)
     ap.add_argument("--small", action="store_true")
+    ap.add_argument("--no-fuse-post", action="store_true")
     args = ap.parse_args()
 
     import torch
@@ -42,9 +43,12 @@ def main():
         ev[1].record()
         pipe.viewpoints()
         ev[2].record()
-        pipe.refocus()
-        ev[3].record()
-        pipe.post_process()
+        if args.no_fuse_post or pipe.refocus_post() is False:
+            pipe.refocus()
+            ev[3].record()
+            pipe.post_process()
+        else:
+            ev[3].record()                  # fused epilogue: "refocus" below is 0, "post" carries the whole stage
         ev[4].record()
         torch.cuda.synchronize()
         print("step %d: " % it + ", ".join("%s %.3f ms" % (n, ev[k].elapsed_time(ev[k + 1])) for k, n in enumerate(names)))
