@@ -215,7 +215,7 @@ template <bool EXACT24, int POST = 0>
 __global__ void __launch_bounds__(PXF_THREADS)
 refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const uint32_t *__restrict__ accB,
                            const unsigned long long *__restrict__ edgeRG, const uint32_t *__restrict__ edgeB,
-                           PxCtl ctl, float *__restrict__ out, int M, int S, int T, int Tp, int n0,
+                           PxCtl ctl, float *__restrict__ out, int M, int S, int T, int Tp, int n0, int nsl,
                            pcb_minmax_t *mm, const double *__restrict__ lohi = nullptr) {
     double lo = 0.0, inv = 1.0;
     bool scale = false;
@@ -234,10 +234,18 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
     __shared__ int s_rows[16];     // edge-table row index (n*M + j)*2 + side of every clamped contribution
     __shared__ int s_cnt;
     __shared__ float s_tile[PXF_THREADS * 3];
-    const int y = blockIdx.x, n = n0 + blockIdx.y;
+    DivByConst divM;
+    divM.init((float)M);
+    float mn = INFINITY, mx = -INFINITY;
+    // one CTA per (slice, row) for POST 0 / 1; the fix-up pass runs a small grid that strides over the rows, so that
+    // the launch that usually has nothing to do costs microseconds
+    const int row_step = POST == 2 ? (int)gridDim.x : S * nsl;       // POST 0 / 1: exactly one row per CTA
+    for (int row = blockIdx.x; row < S * nsl; row += row_step) {
+    const int sl = POST == 2 ? row / S : (int)blockIdx.y;
+    const int y = POST == 2 ? row - sl * S : (int)blockIdx.x, n = n0 + sl;
     if (threadIdx.x < 32) {                    // M <= 16: one lane per view-row, compacted with a ballot
         const int j = threadIdx.x;
-        const int ys = y + ctl.a[blockIdx.y] * (M / 2 - j);
+        const int ys = y + ctl.a[sl] * (M / 2 - j);
         const bool clamped = j < M && ((ctl.row_active >> j) & 1u) && (ys < 0 || ys > S - 1);
         const unsigned m = __ballot_sync(0xffffffffu, clamped);
         if (clamped) s_rows[__popc(m & ((1u << j) - 1u))] = (n * M + j) * 2 + (ys < 0 ? 0 : 1);
@@ -247,9 +255,6 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
     const int cnt = s_cnt;
     const size_t arow = ((size_t)n * S + y) * Tp;
     float *orow = out + ((size_t)n * S + y) * (size_t)T * 3;
-    DivByConst divM;
-    divM.init((float)M);
-    float mn = INFINITY, mx = -INFINITY;
     // the accumulator words of PXF_IT row segments are requested up front (the kernel is bound by the latency of
     // these loads, not by their bandwidth); each segment then goes through the shared-memory transposition
     for (int xb0 = 0; xb0 < T; xb0 += PXF_THREADS * PXF_IT) {
@@ -291,6 +296,8 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
             }
             __syncwarp();
         }
+    }
+    if (POST == 2) __syncthreads();            // s_rows / s_cnt are rewritten by the next row
     }
     if (POST != 2 && mm != nullptr) block_minmax_commit(mn, mx, mm);
 }
@@ -423,10 +430,10 @@ static int launch_refocus_px(const PxPlan &pl, const uint16_t *vp, const int32_t
         dim3 fgrid(a.S, nloc);
         if (pl.exact24)
             refocus_px_finalize_kernel<true><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, ctl, out,
-                                                                          a.M, a.S, a.T, a.Tp, n0, mm);
+                                                                          a.M, a.S, a.T, a.Tp, n0, nloc, mm);
         else
             refocus_px_finalize_kernel<false><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, ctl,
-                                                                           out, a.M, a.S, a.T, a.Tp, n0, mm);
+                                                                           out, a.M, a.S, a.T, a.Tp, n0, nloc, mm);
         PCB_LAUNCH_OK();
     }
     return PCB_OK;

@@ -344,12 +344,13 @@ template <int POST>
 static int launch_pxp_finalize(const PxpPlan &pl, const PxpArgs &a, const PxCtl &fctl, float *out, int n0, int nloc,
                                pcb_minmax_t *mm, const double *lohi, cudaStream_t st) {
     dim3 fgrid(a.S, nloc);
+    if (POST == 2) fgrid = dim3(min(a.S * nloc, 8 * sm_count()), 1);     // usually returns at once: keep the launch small
     if (pl.exact24)
         refocus_px_finalize_kernel<true, POST><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, fctl, out,
-                                                                            a.M, a.S, a.T, a.Tp, n0, mm, lohi);
+                                                                            a.M, a.S, a.T, a.Tp, n0, nloc, mm, lohi);
     else
         refocus_px_finalize_kernel<false, POST><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, fctl,
-                                                                             out, a.M, a.S, a.T, a.Tp, n0, mm, lohi);
+                                                                             out, a.M, a.S, a.T, a.Tp, n0, nloc, mm, lohi);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }

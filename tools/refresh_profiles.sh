@@ -10,6 +10,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_l_$tag.log 2>&1
 timeout 300 python tools/profile_stage.py --steps 3 > gpurun_out/plain_prof_$tag.log 2>&1 || exit 1
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k 'regex:resample_col|viewpoints_kernel|refocus_pxp|finalize|contrast_' -s 14 -c 7 -f -o gpurun_out/prof_step_$tag \
+    -k 'regex:resample_col|viewpoints_kernel|refocus_pxp|finalize|contrast_' -s 16 -c 8 -f -o gpurun_out/prof_step_$tag \
     python tools/profile_stage.py --steps 3 > gpurun_out/ncu_s_$tag.log 2>&1; tail -2 gpurun_out/ncu_s_$tag.log
 ls -la gpurun_out/prof_step_$tag.ncu-rep
