@@ -116,7 +116,19 @@ def main():
                 print("REFOCUS FAIL", dict(case=case, kern=kern, M=M, S=S, T=T, a=a_list[:6], n=len(a_list), mask=mk,
                                            info=got if isinstance(got, str) else float(np.abs(got - ref).max())))
         os.environ.pop("PCB_REFOCUS_KERNEL", None)
-    print("refocus: %d cases x 4 kernel forms, %d failures" % (args.cases, bad_r))
+        # colour management fused into the epilogue == the separate kernels, bit for bit (whatever form applies)
+        try:
+            mm = ops.new_minmax()
+            sep = ops.refocuser_postprocess(ops.refocus_int(dev, a_list, view_zeroed=mask, mm=mm), mm=mm)
+            fus = ops.refocus_int_srgb(dev, a_list, view_zeroed=mask)
+            ok = bool(torch.equal(sep, fus))
+        except Exception as e:                                   # noqa: BLE001
+            ok = False
+            print(repr(e))
+        if not ok:
+            bad_r += 1
+            print("FUSED POST FAIL", dict(case=case, M=M, S=S, T=T, a=a_list[:6], n=len(a_list), mask=mk))
+    print("refocus: %d cases x 4 kernel forms + fused epilogue, %d failures" % (args.cases, bad_r))
     # ---------------------------------------------------------------- refinement, viewpoints, post-processing
     from plenopticam_b200.lfp_refocuser.refinement import refocus_refi
     bad_o = 0
