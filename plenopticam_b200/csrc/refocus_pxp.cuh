@@ -29,6 +29,7 @@ struct PxpCtl {                      // per-launch control block, passed by valu
     uint8_t rows[16];                // the view-rows with at least one unmasked view
     int32_t nrows;
     int32_t maxa;                    // max |a| of this launch (per-view margins)
+    int32_t gsz;                     // view rows per sweep (see pxp_tile)
 };
 
 struct PxpArgs {
@@ -77,6 +78,19 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long
 }
 __device__ __forceinline__ void red_add_u32(uint32_t *p, uint32_t v) {
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Tile order.  The view rows are walked in sweeps of `gsz` consecutive rows, each sweep r-major over the whole image:
+// accumulator row y of slice a receives the tiles r = y + a (c0 - j), so it stays live while r crosses
+// |a| * (span of c0 - j inside the sweep) image rows.  With all M view rows in one sweep the live accumulator rows of a
+// 64-slice stack (109 MB) overflow L2 and cycle through DRAM; sweeps of 5 view rows keep them at about 31 MB.
+__device__ __forceinline__ void pxp_tile(const PxpArgs &p, const PxpCtl &ctl, int t, int &j, int &r) {
+    const int per_sweep = ctl.gsz * p.S;
+    const int g = t / per_sweep;
+    const int rem = t - g * per_sweep;
+    const int gn = min(ctl.gsz, ctl.nrows - g * ctl.gsz);          // rows of this sweep (the last one may be short)
+    r = rem / gn;
+    j = ctl.rows[g * ctl.gsz + (rem - r * gn)];
 }
 
 // Elected thread: one bulk copy per active view row of tile (j, r): the 16-byte aligned superset of the row
@@ -223,10 +237,12 @@ refocus_pxp_kernel(PxpArgs p, PxpCtl ctl) {
     uint32_t *b_t = p.accB + tid;                  // bank inside the slice loop costs uniform-register spills
     asm volatile("" : "+l"(rg_t), "+l"(b_t));
     uint32_t parity = 0;
-    if (tid == 0) pxp_issue_tile(p, ctl, raw, &s_bar, ctl.rows[t % ctl.nrows], t / ctl.nrows);
+    int j, r;
+    pxp_tile(p, ctl, t, j, r);
+    if (tid == 0) pxp_issue_tile(p, ctl, raw, &s_bar, j, r);
 
     for (;;) {
-        const int j = ctl.rows[t % ctl.nrows], r = t / ctl.nrows;
+        pxp_tile(p, ctl, t, j, r);
         // raw rows of tile t have landed -> packed buffer
         mbar_wait(&s_bar, parity);
         parity ^= 1u;
@@ -235,7 +251,9 @@ refocus_pxp_kernel(PxpArgs p, PxpCtl ctl) {
         const int tn = t + gridDim.x;
         if (tid == 0 && tn < p.ntiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads of `raw` before async writes
-            pxp_issue_tile(p, ctl, raw, &s_bar, ctl.rows[tn % ctl.nrows], tn / ctl.nrows);
+            int jn, rn;
+            pxp_tile(p, ctl, tn, jn, rn);
+            pxp_issue_tile(p, ctl, raw, &s_bar, jn, rn);
         }
         constexpr int BATCH = MAXT <= 640 ? 16 : 8 / PPT;
         const bool symc = 2 * (p.M / 2 - (int)ctl.first[j]) == (int)ctl.nact[j] - 1;
@@ -300,6 +318,17 @@ static PxpPlan plan_refocus_pxp(const PxPlan &px, int M, int S, int T, int N, in
     }
     if (c.nrows == 0) return pl;
     c.maxa = max_abs_a;
+    {   // sweeps of view rows: only worth it when the live accumulator rows would not fit L2 in one sweep
+        const char *e = getenv("PCB_PXP_SWEEP_ROWS");
+        int gsz = e ? atoi(e) : 0;
+        if (gsz <= 0) {
+            // live rows ~ sum over slices of (M - 1) |a|; the plan sees max |a| only: assume a symmetric range
+            const double live_mb = (double)(M - 1) * max_abs_a * 0.5 * (N < RR_MAX_SLICES ? N : RR_MAX_SLICES) * px.a.Tp * 12.0 / 1e6;
+            gsz = live_mb > 48.0 ? 5 : c.nrows;
+        }
+        if (gsz > c.nrows) gsz = c.nrows;
+        c.gsz = gsz;
+    }
     const int rawStride = (T * 6 + 30 + 15) & ~15;
     const size_t rawOffset = (max_packed + 127) & ~(size_t)127;
     pl.smem = rawOffset + (size_t)max_nact * rawStride;
