@@ -58,14 +58,44 @@ def fit_projective(coords):
     if not (dims[0] > 3 and dims[1] > 3):
         return np.identity(3)                            # grid_fitter.py:62-66: too few points, no fit
     grid = grid_points(dims)
+    # `project(p, grid, flip_xy=True)` with everything that does not depend on p hoisted out of the ~500 residual
+    # evaluations of a fit (234 794 points at Illum size); the floating-point operations and their order are the same,
+    # so the iteration — and the matrix — stay bit-identical to the straightforward form (fit_projective_plain)
+    pts = np.concatenate((grid[:, :2].T, np.ones(len(grid))[np.newaxis, :]), axis=0)
+    pts[:2, :] = pts[:2, :][::-1]
+    ty, tx = np.ascontiguousarray(coords[:, 0]), np.ascontiguousarray(coords[:, 1])
+    m = np.empty((3, 3))
+    quo = np.empty((2, pts.shape[1]))
+
+    def residual(p):
+        m.ravel()[:8] = p
+        m[2, 2] = 1.0
+        prj = np.dot(m, pts)
+        quo[...] = 0.0
+        np.divide(prj[:2, :], prj[2, :], out=quo, where=prj[2, :] != 0)
+        dy = ty - quo[1]                                # rows come back flipped: quo[1] is y, quo[0] is x
+        dx = tx - quo[0]
+        return np.sqrt(dy * dy + dx * dx)
+
+    p0 = np.array([1., 0., 0., 0., 1., 0., 0., 0.])
+    p = leastsq(residual, p0)[0]
+    return np.append(p, 1.0).reshape(3, 3)
+
+
+def fit_projective_plain(coords):
+    """fit_projective written like the reference's residual (grid_fitter.py:139-164); kept to pin the fast form."""
+    coords = np.asarray(coords, dtype=np.float64)
+    dims = (int(coords[:, 2].max() + 1), int(coords[:, 3].max() + 1))
+    if not (dims[0] > 3 and dims[1] > 3):
+        return np.identity(3)
+    grid = grid_points(dims)
     target = coords[:, :2]
 
     def residual(p):
         y, x = project(p, grid, flip_xy=True)
         return np.sqrt(np.sum((target - np.stack([y, x], axis=1)) ** 2, axis=1))
 
-    p0 = np.array([1., 0., 0., 0., 1., 0., 0., 0.])
-    p = leastsq(residual, p0)[0]
+    p = leastsq(residual, np.array([1., 0., 0., 0., 1., 0., 0., 0.]))[0]
     return np.append(p, 1.0).reshape(3, 3)
 
 
@@ -78,8 +108,28 @@ def upper_factor(pmat):
     return k
 
 
+_PLAN_CACHE = {}          # per-camera plans: the fits and spline operators depend on the calibration, not on the exposure
+_PLAN_CACHE_MAX = 4
+
+
+def _cached(key, build):
+    if key not in _PLAN_CACHE:
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        _PLAN_CACHE[key] = build()
+    return _PLAN_CACHE[key]
+
+
 def projective_plan(centroids, img_shape, pat_type, hex_odd):
-    """(tra_mat, oshape (rows, cols), pitch (py, px)) of LfpGlobalResampler.projective_alignment (:32-79)."""
+    """(tra_mat, oshape (rows, cols), pitch (py, px)) of LfpGlobalResampler.projective_alignment (:32-79); computed
+    once per calibration (two Levenberg-Marquardt fits over all centroids) and reused for later exposures."""
+    cent = np.ascontiguousarray(np.asarray(centroids, dtype=np.float64))
+    key = ('prj', hash(cent.tobytes()), cent.shape, tuple(int(v) for v in img_shape[:2]), str(pat_type), int(bool(hex_odd)))
+    tra, oshape, pitch = _cached(key, lambda: _projective_plan(cent, img_shape, pat_type, hex_odd))
+    return tra.copy(), oshape.copy(), pitch.copy()
+
+
+def _projective_plan(centroids, img_shape, pat_type, hex_odd):
     cent = np.asarray(centroids, dtype=np.float64)
     pmat_cent = fit_projective(cent)
     K = upper_factor(pmat_cent)
@@ -152,7 +202,13 @@ def spline_resize_dense(n_in, n_out):
 
 
 def hex_plan(pitch, LY, LX, prj_cols, hex_odd):
-    """Geometry and operators of LfpGlobalResampler.hexagonal_alignment / hex_stretch (:84-167)."""
+    """Geometry and operators of LfpGlobalResampler.hexagonal_alignment / hex_stretch (:84-167); cached per geometry
+    (the banded spline operator of a 8750 -> 9375 resize takes seconds to build)."""
+    key = ('hex', int(pitch[0]), int(pitch[1]), int(LY), int(LX), int(prj_cols), int(bool(hex_odd)))
+    return _cached(key, lambda: _hex_plan(pitch, LY, LX, prj_cols, hex_odd))
+
+
+def _hex_plan(pitch, LY, LX, prj_cols, hex_odd):
     py, px = int(pitch[0]), int(pitch[1])
     if py < 4:
         raise NotImplementedError("micro-image pitch below 4 pixels (cubic spline resize of a lens row)")

@@ -556,9 +556,11 @@ def hex_align(prj, plan, LY):
     _chk_dev(prj)
     dev = prj.device
     prows, pcols, Cn = (int(v) for v in prj.shape)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    i0, i1, w = t(plan["i0"]), t(plan["i1"]), t(plan["w"])
-    wxv, wxf, wy = t(plan["wx_vals"]), t(plan["wx_first"]), t(plan["wy"])
+    cache = plan.setdefault("_device", {})               # operator tables stay on the device with the (cached) plan
+    if str(dev) not in cache:
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        cache[str(dev)] = tuple(t(plan[k]) for k in ("i0", "i1", "w", "wx_vals", "wx_first", "wy"))
+    i0, i1, w, wxv, wxf, wy = cache[str(dev)]
     strips = int(LY) - 1
     out_cols = plan["x_len"] + plan["crop_hi"] - plan["crop_lo"]
     stretched = torch.empty((strips * plan["py"], plan["m"], Cn), dtype=torch.float32, device=dev)

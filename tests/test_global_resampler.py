@@ -92,3 +92,17 @@ def test_cropper_non_square_pitch_vs_reference_golden(cuda):
     cfg2, sta2 = make_cfg(g["centroids"], 'hex', 10)
     with pytest.raises(ValueError):
         LfpCropper(lfp_img_align=g["aligned"], cfg=cfg2, sta=sta2).main()
+
+
+def test_fast_grid_fit_is_bit_identical_to_the_plain_form_and_plans_are_cached():
+    from plenopticam_b200.lfp_aligner import lfp_global_resampler as glob
+    cent = onp.synth_centroids(28, 35, 14.285, 'hex', hex_odd=True, jitter=0.15, rot_deg=0.05, origin=(9.5, 9.5), seed=5)
+    assert np.array_equal(glob.fit_projective(cent), glob.fit_projective_plain(cent))
+    glob._PLAN_CACHE.clear()
+    a = glob.projective_plan(cent, (420, 520, 3), 'hex', 1)
+    n = len(glob._PLAN_CACHE)
+    b = glob.projective_plan(cent.tolist(), (420, 520, 3), 'hex', 1)          # same calibration: no second fit
+    assert len(glob._PLAN_CACHE) == n == 1
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    a[0][0, 0] += 1.0                                                          # callers get copies
+    assert not np.array_equal(a[0], glob.projective_plan(cent, (420, 520, 3), 'hex', 1)[0])
