@@ -24,7 +24,7 @@ __device__ __forceinline__ int mirror_idx(int i, int n) {
     return i < n ? i : period - i;
 }
 
-// horizontal pass: out[y, x, c] = sum_k h[|k|] in[y, mirror(x+k), c]
+// horizontal pass: out[y, x, c] = sum_k h[|k|] in[y, mirror(x+k), c]   (any channel count; one output per thread)
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 prefilter_rows_kernel(const TIn *__restrict__ in, float *__restrict__ out, int H, int W, int C, PfTaps taps) {
@@ -52,27 +52,77 @@ prefilter_rows_kernel(const TIn *__restrict__ in, float *__restrict__ out, int H
     }
 }
 
-// vertical pass on the row-filtered image; threads run along the contiguous (x, c) axis, each CTA walks a
-// strip of rows keeping a sliding register window of 2K+1 samples.
-constexpr int PF_ROWS = 32;   // output rows per CTA
+// The same for C == 3 with a register window: a thread owns PR_P adjacent pixels of one channel and reads their
+// PR_P + 2K samples once (4 shared-memory reads per output instead of 29).  PR_P * 3 = 27 is odd, so the lane
+// stride is conflict free; results go back through shared memory so that the row leaves in contiguous runs.
+constexpr int PR_P = 9;
+constexpr int PR_G = 85;                       // pixel groups per CTA: 3 channels x 85 groups = 255 threads
+constexpr int PR_TW = PR_P * PR_G;             // 765 pixels per CTA
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+prefilter_rows3_kernel(const TIn *__restrict__ in, float *__restrict__ out, int H, int W, PfTaps taps) {
+    __shared__ float s_in[(PR_TW + 2 * PF_K) * 3];
+    __shared__ float s_out[PR_TW * 3];
+    const int y = blockIdx.y;
+    const int x0 = blockIdx.x * PR_TW;
+    const int npx = min(PR_TW, W - x0);
+    const TIn *src = in + (size_t)y * W * 3;
+    const bool interior = x0 >= PF_K && x0 + PR_TW + PF_K <= W;
+    if (interior) {
+        const TIn *p = src + (size_t)(x0 - PF_K) * 3;
+        for (int idx = threadIdx.x; idx < (PR_TW + 2 * PF_K) * 3; idx += 256) s_in[idx] = ld_as_float(p + idx);
+    } else {
+        for (int idx = threadIdx.x; idx < (PR_TW + 2 * PF_K) * 3; idx += 256) {
+            const int px = idx / 3, c = idx - px * 3;
+            s_in[idx] = ld_as_float(src + (size_t)mirror_idx(x0 - PF_K + px, W) * 3 + c);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * PR_G) {
+        const int c = threadIdx.x / PR_G, g = threadIdx.x - c * PR_G;
+        const float *p = s_in + g * (PR_P * 3) + c;
+        float w[PR_P + 2 * PF_K];
+#pragma unroll
+        for (int m = 0; m < PR_P + 2 * PF_K; ++m) w[m] = p[m * 3];
+        float *o = s_out + g * (PR_P * 3) + c;
+#pragma unroll
+        for (int j = 0; j < PR_P; ++j) {
+            float acc = taps.h[0] * w[j + PF_K];
+#pragma unroll
+            for (int k = 1; k <= PF_K; ++k) acc = fmaf(taps.h[k], w[j + PF_K + k] + w[j + PF_K - k], acc);
+            o[j * 3] = acc;
+        }
+    }
+    __syncthreads();
+    float *dst = out + ((size_t)y * W + x0) * 3;
+    for (int idx = threadIdx.x; idx < npx * 3; idx += 256) dst[idx] = s_out[idx];
+}
+
+// vertical pass on the row-filtered image; threads run along the contiguous (x, c) axis.  A CTA owns a strip of PF_ROWS
+// rows: every thread requests the PF_ROWS + 2K samples of its column up front (all loads in flight, static register
+// indices: no sliding-window moves) and then evaluates the PF_ROWS outputs from registers.
+constexpr int PF_ROWS = 16;   // output rows per CTA
 __global__ void __launch_bounds__(256)
 prefilter_cols_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C, PfTaps taps) {
     const size_t rowlen = (size_t)W * C;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= rowlen) return;
     const int y0 = blockIdx.y * PF_ROWS;
-    float win[2 * PF_K + 1];
+    float win[PF_ROWS + 2 * PF_K];
+    if (y0 >= PF_K && y0 + PF_ROWS + PF_K <= H) {             // interior strip: no mirroring
+        const float *p = in + (size_t)(y0 - PF_K) * rowlen + e;
 #pragma unroll
-    for (int k = 0; k < 2 * PF_K; ++k) win[k + 1] = __ldg(in + (size_t)mirror_idx(y0 - PF_K + k, H) * rowlen + e);
-    const int y1 = min(y0 + PF_ROWS, H);
-    for (int y = y0; y < y1; ++y) {
+        for (int k = 0; k < PF_ROWS + 2 * PF_K; ++k) win[k] = __ldg(p + (size_t)k * rowlen);
+    } else {
 #pragma unroll
-        for (int k = 0; k < 2 * PF_K; ++k) win[k] = win[k + 1];
-        win[2 * PF_K] = __ldg(in + (size_t)mirror_idx(y + PF_K, H) * rowlen + e);
-        float acc = taps.h[0] * win[PF_K];
+        for (int k = 0; k < PF_ROWS + 2 * PF_K; ++k) win[k] = __ldg(in + (size_t)mirror_idx(y0 - PF_K + k, H) * rowlen + e);
+    }
 #pragma unroll
-        for (int k = 1; k <= PF_K; ++k) acc = fmaf(taps.h[k], win[PF_K + k] + win[PF_K - k], acc);
-        out[(size_t)y * rowlen + e] = acc;
+    for (int r = 0; r < PF_ROWS; ++r) {
+        float acc = taps.h[0] * win[r + PF_K];
+#pragma unroll
+        for (int k = 1; k <= PF_K; ++k) acc = fmaf(taps.h[k], win[r + PF_K + k] + win[r + PF_K - k], acc);
+        if (y0 + r < H) out[(size_t)(y0 + r) * rowlen + e] = acc;
     }
 }
 
@@ -140,7 +190,11 @@ static PfTaps prefilter_taps() {
 template <typename TIn>
 static int launch_prefilter(const void *img, int H, int W, int C, float *tmp, float *coef, cudaStream_t st) {
     const PfTaps taps = prefilter_taps();
-    {
+    if (C == 3) {
+        dim3 grid((W + PR_TW - 1) / PR_TW, H), block(256);
+        prefilter_rows3_kernel<TIn><<<grid, block, 0, st>>>((const TIn *)img, tmp, H, W, taps);
+        PCB_LAUNCH_OK();
+    } else {
         const int tile_w = 256;
         dim3 grid((W + tile_w - 1) / tile_w, H), block(tile_w);
         const size_t smem = (size_t)(tile_w + 2 * PF_K) * C * sizeof(float);
