@@ -160,10 +160,15 @@ rotate_sample_kernel(const float *__restrict__ coef, float *__restrict__ out, in
         wx[3] = t3 * (1.f / 6.f);
     }
     int ry[4], rx[4];
+    if (iy >= 1 && iy + 2 < H && ix >= 1 && ix + 2 < W) {      // interior: no mirroring (almost every pixel)
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        ry[p] = mirror_idx(iy - 1 + p, H);
-        rx[p] = mirror_idx(ix - 1 + p, W);
+        for (int p = 0; p < 4; ++p) { ry[p] = iy - 1 + p; rx[p] = ix - 1 + p; }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            ry[p] = mirror_idx(iy - 1 + p, H);
+            rx[p] = mirror_idx(ix - 1 + p, W);
+        }
     }
     for (int c = 0; c < C; ++c) {
         float acc = 0.f;
