@@ -179,6 +179,17 @@ int pcb_refi_prefilter(const void *vp, int dtype, int M, int S, int T, int C,
                        const float *py_vals, const int32_t *py_first, int Kpy,
                        const float *px_vals, const int32_t *px_first, int Kpx,
                        const uint8_t *view_zeroed, float *tmp, float *coef, void *stream);
+/* pcb_refi_prefilter with the interior of both operators given as ONE symmetric filter: away from the border the rows of
+ * P are the cubic B-spline prefilter sqrt(3) (sqrt(3) - 2)^|k| (29 taps at 1e-8).  hx_host / hy_host: HOST arrays of
+ * ntx = nty = 29 taps; rows x_lo..x_hi (y_lo..y_hi) of the tables equal them exactly with first = row - cx (cyy).  Those
+ * rows run from the kernel-parameter bank with a register window (same summation order: bit-identical to the table
+ * kernels), the border rows keep the tables.  A NULL / mismatching description falls back to the tables. */
+int pcb_refi_prefilter_toeplitz(const void *vp, int dtype, int M, int S, int T, int C,
+                                const float *py_vals, const int32_t *py_first, int Kpy,
+                                const float *px_vals, const int32_t *px_first, int Kpx,
+                                const uint8_t *view_zeroed, float *tmp, float *coef,
+                                const float *hx_host, int ntx, int cx, int x_lo, int x_hi,
+                                const float *hy_host, int nty, int cyy, int y_lo, int y_hi, void *stream);
 int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N,
                      const float *dy_vals, const int32_t *dy_first, int Kgy,
                      const float *dx_vals, const int32_t *dx_first, int Kx,

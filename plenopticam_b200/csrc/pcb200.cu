@@ -328,6 +328,34 @@ int pcb_refi_prefilter(const void *vp, int dtype, int M, int S, int T, int C, co
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
 
+// Same with the interior of both prefilter operators described as one symmetric filter (host arrays of 29 taps; rows /
+// columns lo..hi equal it exactly, sample offset c): those rows run from the kernel-parameter bank with a register window.
+int pcb_refi_prefilter_toeplitz(const void *vp, int dtype, int M, int S, int T, int C, const float *py_vals,
+                                const int32_t *py_first, int Kpy, const float *px_vals, const int32_t *px_first, int Kpx,
+                                const uint8_t *view_zeroed, float *tmp, float *coef, const float *hx_host, int ntx, int cx,
+                                int x_lo, int x_hi, const float *hy_host, int nty, int cyy, int y_lo, int y_hi,
+                                void *stream) {
+    PCB_REQUIRE(vp && py_vals && py_first && px_vals && px_first && view_zeroed && tmp && coef, "pointers");
+    PCB_REQUIRE(M > 0 && M * M <= 65535 && S >= 4 && T >= 4 && S <= 65535 && Kpy > 0 && Kpx > 0, "sizes");
+    PCB_REQUIRE(C == 3, "3 colour channels (lfp_shiftandsum.py:97)");
+    RpTaps tx, ty;
+    memset(&tx, 0, sizeof(tx)); memset(&ty, 0, sizeof(ty));
+    tx.lo = 1; tx.hi = 0; ty.lo = 1; ty.hi = 0;
+    if (hx_host && ntx == RPT_K && cx >= 0 && x_lo - cx >= 0 && x_hi - cx + RPT_K - 1 < T && x_hi >= x_lo) {
+        memcpy(tx.h, hx_host, sizeof(tx.h)); tx.c = cx; tx.lo = x_lo; tx.hi = x_hi;
+    }
+    if (hy_host && nty == RPT_K && cyy >= 0 && y_lo - cyy >= 0 && y_hi - cyy + RPT_K - 1 < S && y_hi >= y_lo) {
+        memcpy(ty.h, hy_host, sizeof(ty.h)); ty.c = cyy; ty.lo = y_lo; ty.hi = y_hi;
+    }
+    cudaStream_t st = as_stream(stream);
+    switch (dtype) {
+    case PCB_U16: return launch_refi_prefilter<uint16_t>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty);
+    case PCB_F32: return launch_refi_prefilter<float>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty);
+    case PCB_U8:  return launch_refi_prefilter<uint8_t>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty);
+    }
+    return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
 int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N, const float *dy_vals,
                      const int32_t *dy_first, int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx,
                      const int32_t *iy, const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,

@@ -59,8 +59,8 @@ constexpr int RP_GY = 8;
 __global__ void __launch_bounds__(256)
 refi_prefilter_y_kernel(const float *__restrict__ tmp, int S, int E, const float *__restrict__ py_vals,
                         const int32_t *__restrict__ py_first, int Kg, const uint8_t *__restrict__ view_zeroed,
-                        float *__restrict__ coef) {
-    const int gy = blockIdx.y, view = blockIdx.z;
+                        float *__restrict__ coef, int gy0 = 0) {
+    const int gy = gy0 + blockIdx.y, view = blockIdx.z;
     if (view_zeroed[view]) return;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
@@ -84,6 +84,103 @@ refi_prefilter_y_kernel(const float *__restrict__ tmp, int S, int E, const float
         const int y = gy * RP_GY + q;
         if (y < S) coef[((size_t)view * S + y) * E + e] = acc[q];
     }
+}
+
+// ---- prefilter, Toeplitz interior ---------------------------------------------------------------------------------
+// Away from the image border the rows of P are one and the same symmetric filter (the cubic B-spline prefilter
+// sqrt(3) z1^|k|, 29 taps at 1e-8): the host hands over those taps and the range of rows that equal them EXACTLY (as
+// float32), and the kernels below run that range with the taps in the kernel-parameter bank and a register window,
+// in the same summation order as the table kernels above (bit-identical results); border rows keep the tables.
+constexpr int RPT_K = 29;                      // taps of the interior filter this fast path is built for
+struct RpTaps { float h[RPT_K]; int c, lo, hi; };   // row x in [lo, hi] uses samples x - c ... x - c + RPT_K - 1
+
+constexpr int RPX_P = 9;                       // adjacent pixels of one channel per thread (27-float lane stride)
+template <typename TIn>
+__global__ void __launch_bounds__(RP_THREADS)
+refi_prefilter_x3_kernel(const TIn *__restrict__ vp, int S, int T, const float *__restrict__ px_vals,
+                         const int32_t *__restrict__ px_first, int Kp, RpTaps tp,
+                         const uint8_t *__restrict__ view_zeroed, float *__restrict__ tmp) {
+    extern __shared__ __align__(16) float s_buf[];        // [T*3] samples, [T*3] results
+    const int r = blockIdx.x, view = blockIdx.y;
+    if (view_zeroed[view]) return;
+    const int E = T * 3;
+    float *s_row = s_buf, *s_out = s_buf + E;
+    const TIn *src = vp + ((size_t)view * S + r) * E;
+    for (int e = threadIdx.x; e < E; e += RP_THREADS) s_row[e] = ld_as_float(src + e);
+    __syncthreads();
+    // tasks: (channel, group of RPX_P pixels) for the groups that lie inside [lo, hi], then one task per border
+    // (pixel, channel) — a border pixel costs about as much as half a group, so it gets a thread of its own
+    const int g_lo = (tp.lo + RPX_P - 1) / RPX_P;
+    const int g_hi = tp.hi >= RPX_P - 1 ? (tp.hi - (RPX_P - 1)) / RPX_P + 1 : 0;      // one past the last inner group
+    const int ngi = max(g_hi - g_lo, 0);
+    const int xl = ngi ? g_lo * RPX_P : T;                   // border pixels: [0, xl) and [xr, T)
+    const int xr = ngi ? g_hi * RPX_P : T;
+    const int nbx = xl + (T - xr);
+    for (int task = threadIdx.x; task < 3 * (ngi + nbx); task += RP_THREADS) {
+        if (task < 3 * ngi) {
+            const int c = task / ngi, g = g_lo + (task - c * ngi);
+            const int xa = g * RPX_P;
+            const float *p = s_row + (xa - tp.c) * 3 + c;
+            // every sample is read once and goes to the (up to RPX_P) outputs it contributes to; for a fixed output the
+            // taps still arrive in ascending order
+            float acc[RPX_P];
+#pragma unroll
+            for (int j = 0; j < RPX_P; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int m = 0; m < RPX_P + RPT_K - 1; ++m) {
+                const float v = p[m * 3];
+#pragma unroll
+                for (int j = 0; j < RPX_P; ++j)
+                    if (m - j >= 0 && m - j < RPT_K) acc[j] = fmaf(tp.h[m - j], v, acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < RPX_P; ++j) s_out[(xa + j) * 3 + c] = acc[j];
+        } else {
+            const int bt = task - 3 * ngi;
+            const int c = bt / nbx, bx = bt - c * nbx;
+            const int x = bx < xl ? bx : xr + (bx - xl);
+            const float *px = s_row + px_first[x] * 3 + c;
+            float acc = 0.f;
+            for (int m = 0; m < Kp; ++m) acc = fmaf(__ldg(px_vals + (size_t)m * T + x), px[m * 3], acc);
+            s_out[x * 3 + c] = acc;
+        }
+    }
+    __syncthreads();
+    float *dst = tmp + ((size_t)view * S + r) * E;
+    for (int e = threadIdx.x; e < E; e += RP_THREADS) dst[e] = s_out[e];
+}
+
+// grid (ceil(E/256), strips, M*M): rows y0 + blockIdx.y * RPY_R ... of the interior; thread = one (x, c) element.
+constexpr int RPY_R = 16;
+__global__ void __launch_bounds__(256)
+refi_prefilter_yt_kernel(const float *__restrict__ tmp, int S, int E, RpTaps tp, int y_first,
+                         const uint8_t *__restrict__ view_zeroed, float *__restrict__ coef) {
+    const int view = blockIdx.z;
+    if (view_zeroed[view]) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int y0 = y_first + blockIdx.y * RPY_R;
+    const float *col = tmp + ((size_t)view * S + (y0 - tp.c)) * E + e;
+    float acc[RPY_R];
+#pragma unroll
+    for (int j = 0; j < RPY_R; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int m0 = 0; m0 < RPY_R + RPT_K - 1; m0 += 11) {            // 44 samples in four batches of 11 loads in flight
+        float v[11];
+#pragma unroll
+        for (int u = 0; u < 11; ++u)
+            if (m0 + u < RPY_R + RPT_K - 1) v[u] = __ldg(col + (size_t)(m0 + u) * E);
+#pragma unroll
+        for (int u = 0; u < 11; ++u) {
+            const int m = m0 + u;
+#pragma unroll
+            for (int j = 0; j < RPY_R; ++j)
+                if (m < RPY_R + RPT_K - 1 && m - j >= 0 && m - j < RPT_K) acc[j] = fmaf(tp.h[m - j], v[u], acc[j]);
+        }
+    }
+    float *o = coef + ((size_t)view * S + y0) * E + e;
+#pragma unroll
+    for (int j = 0; j < RPY_R; ++j) o[(size_t)j * E] = acc[j];
 }
 
 // ---- horizontal pass ---------------------------------------------------------------------------------------------
@@ -232,20 +329,52 @@ refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *_
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
+// tx / ty: interior Toeplitz description of the two axes (lo > hi: none)
 template <typename TIn>
 static int launch_refi_prefilter(const void *vp, int M, int S, int T, const float *py_vals, const int32_t *py_first,
                                  int Kpy, const float *px_vals, const int32_t *px_first, int Kpx,
-                                 const uint8_t *view_zeroed, float *tmp, float *coef, cudaStream_t st) {
+                                 const uint8_t *view_zeroed, float *tmp, float *coef, cudaStream_t st,
+                                 const RpTaps *tx = nullptr, const RpTaps *ty = nullptr) {
     const int E = T * 3;
     const size_t smem = (size_t)E * sizeof(float);
-    if (smem > 200 * 1024) return fail(PCB_ERR_UNSUPPORTED, "%s: image row does not fit shared memory", "pcb_refi_prefilter");
-    PCB_CUDA(cudaFuncSetAttribute(refi_prefilter_x_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    refi_prefilter_x_kernel<TIn><<<dim3(S, M * M), RP_THREADS, smem, st>>>((const TIn *)vp, S, T, px_vals, px_first, Kpx,
-                                                                         view_zeroed, tmp);
+    if (2 * smem > 200 * 1024) return fail(PCB_ERR_UNSUPPORTED, "%s: image row does not fit shared memory", "pcb_refi_prefilter");
+    if (tx && tx->hi - tx->lo + 1 >= 2 * RPX_P) {
+        PCB_CUDA(cudaFuncSetAttribute(refi_prefilter_x3_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem)));
+        refi_prefilter_x3_kernel<TIn><<<dim3(S, M * M), RP_THREADS, 2 * smem, st>>>((const TIn *)vp, S, T, px_vals, px_first,
+                                                                                  Kpx, *tx, view_zeroed, tmp);
+    } else {
+        PCB_CUDA(cudaFuncSetAttribute(refi_prefilter_x_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        refi_prefilter_x_kernel<TIn><<<dim3(S, M * M), RP_THREADS, smem, st>>>((const TIn *)vp, S, T, px_vals, px_first, Kpx,
+                                                                             view_zeroed, tmp);
+    }
     PCB_LAUNCH_OK();
-    refi_prefilter_y_kernel<<<dim3((E + 255) / 256, (S + RP_GY - 1) / RP_GY, M * M), 256, 0, st>>>(
-        tmp, S, E, py_vals, py_first, Kpy, view_zeroed, coef);
-    PCB_LAUNCH_OK();
+    const int G = (S + RP_GY - 1) / RP_GY;
+    const dim3 gx((E + 255) / 256);
+    // interior rows in strips of RPY_R, aligned to the row groups of the table kernel; the groups before / after keep it
+    int ya = 0, strips = 0;
+    if (ty && ty->hi >= ty->lo) {
+        ya = ((ty->lo + RP_GY - 1) / RP_GY) * RP_GY;
+        strips = (ty->hi + 1 - ya) / RPY_R;
+        if (strips < 1) strips = 0;
+    }
+    if (strips > 0) {
+        refi_prefilter_yt_kernel<<<dim3(gx.x, strips, M * M), 256, 0, st>>>(tmp, S, E, *ty, ya, view_zeroed, coef);
+        PCB_LAUNCH_OK();
+        const int g_before = ya / RP_GY, g_after0 = (ya + strips * RPY_R) / RP_GY;
+        if (g_before > 0) {
+            refi_prefilter_y_kernel<<<dim3(gx.x, g_before, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
+                                                                                view_zeroed, coef, 0);
+            PCB_LAUNCH_OK();
+        }
+        if (g_after0 < G) {
+            refi_prefilter_y_kernel<<<dim3(gx.x, G - g_after0, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
+                                                                                    view_zeroed, coef, g_after0);
+            PCB_LAUNCH_OK();
+        }
+    } else {
+        refi_prefilter_y_kernel<<<dim3(gx.x, G, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy, view_zeroed, coef, 0);
+        PCB_LAUNCH_OK();
+    }
     return PCB_OK;
 }
 

@@ -143,6 +143,22 @@ class AxisOperators(object):
     def prefilter_tap_major(self):
         return np.ascontiguousarray(self.p_vals.T), self.p_first
 
+    def prefilter_toeplitz(self):
+        """Interior of P as ONE filter: (taps (Kp,) float32, c, lo, hi) such that every row x in [lo, hi] of the band
+        equals `taps` exactly (as float32) with first[x] = x - c; (None, 0, 1, 0) when there is no such run.  Away from
+        the border the inverse collocation matrix is the cubic B-spline prefilter sqrt(3) (sqrt(3) - 2)^|k|."""
+        n, r0 = self.n, self.n // 2
+        c = int(r0 - self.p_first[r0])
+        same = (self.p_first == np.arange(n) - c) & np.all(self.p_vals == self.p_vals[r0], axis=1)
+        if not same[r0]:
+            return None, 0, 1, 0
+        lo = hi = r0
+        while lo > 0 and same[lo - 1]:
+            lo -= 1
+        while hi < n - 1 and same[hi + 1]:
+            hi += 1
+        return np.ascontiguousarray(self.p_vals[r0]), c, int(lo), int(hi)
+
     def prefilter_grouped(self):
         """Vertical prefilter pass: groups of PREFILTER_GROUP output rows share one window:
         vals (G, Kg, PREFILTER_GROUP) float32, first (G,) int32, Kg."""
@@ -224,6 +240,7 @@ class RefinementPlan(object):
         pxv, pxf = Bx.prefilter_tap_major()                 # horizontal: lanes along x -> (Kp, T)
         self.py_v, self.py_f, self.Kpy = t(pyv), t(pyf), int(Kpy)
         self.px_v, self.px_f, self.Kpx = t(pxv), t(pxf), int(Bx.Kp)
+        self.tx, self.ty = Bx.prefilter_toeplitz(), Ay.prefilter_toeplitz()      # interior filters (host)
         # per-slice bands
         dyv, dyf, self.Kgy = Ay.grouped()
         dxv, dxf, xlo, xhi = Bx.tap_major()
@@ -275,8 +292,12 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None):
     L, p, st = nat.lib(), ops._ptr, ops._stream()
     coef = torch.empty((M, M, S, T, Cn), dtype=torch.float32, device=dev)     # B-spline coefficients of every view
     tmp = torch.empty((M, M, S, T, Cn), dtype=torch.float32, device=dev)
-    nat.check(L.pcb_refi_prefilter(p(vp), ops._pcb_dtype(vp), M, S, T, Cn, p(plan.py_v), p(plan.py_f), plan.Kpy,
-                                   p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp), p(coef), st))
+    (hx, cx, xlo, xhi), (hy, cy, ylo, yhi) = plan.tx, plan.ty
+    hptr = lambda h: h.ctypes.data_as(C.c_void_p) if h is not None else C.c_void_p(0)
+    nat.check(L.pcb_refi_prefilter_toeplitz(p(vp), ops._pcb_dtype(vp), M, S, T, Cn, p(plan.py_v), p(plan.py_f), plan.Kpy,
+                                            p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp), p(coef),
+                                            hptr(hx), 0 if hx is None else int(hx.size), cx, xlo, xhi,
+                                            hptr(hy), 0 if hy is None else int(hy.size), cy, ylo, yhi, st))
     del tmp
     out = torch.empty((N, S, T, Cn), dtype=torch.float32, device=dev)
     hbuf = torch.empty((plan.batch, M, S, T, Cn), dtype=torch.float32, device=dev)

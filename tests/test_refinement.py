@@ -103,3 +103,52 @@ def test_refi_medium_vs_oracle(cuda, dtype):
     assert np.abs(got - ref).max() <= 5e-6 * np.abs(ref).max()
     mn, mx = ops.minmax_values(mm)
     assert mn == got.min() and mx == got.max()
+
+
+def test_prefilter_interior_is_one_symmetric_filter():
+    """Away from the border the rows of P are the cubic B-spline prefilter sqrt(3) (sqrt(3) - 2)^|k|, exactly equal as
+    float32: what the register-window kernels rely on."""
+    from plenopticam_b200.lfp_refocuser import refinement as rf
+    ops_ = rf.AxisOperators(96, 5, [0])
+    h, c, lo, hi = ops_.prefilter_toeplitz()
+    assert h is not None and h.size == 29 and c == 14 and np.array_equal(h, h[::-1])
+    assert lo <= 30 and hi >= 96 - 31
+    z1 = np.sqrt(3.0) - 2.0
+    assert np.allclose(h, np.sqrt(3.0) * z1 ** np.abs(np.arange(29) - 14), rtol=0, atol=2e-7)
+    for x in range(lo, hi + 1):
+        assert ops_.p_first[x] == x - c and np.array_equal(ops_.p_vals[x], h)
+    small = rf.AxisOperators(24, 5, [0]).prefilter_toeplitz()           # too short for an interior
+    assert small[2] > small[3] or small[3] - small[2] < 8
+
+
+@pytest.mark.gpu
+def test_prefilter_register_window_kernels_equal_table_kernels(cuda):
+    """pcb_refi_prefilter_toeplitz == pcb_refi_prefilter bit for bit (same summation order)."""
+    import ctypes as C
+    import torch
+    from plenopticam_b200 import _native as nat
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_refocuser import refinement as rf
+    M, S, T = 3, 101, 118
+    rng = np.random.default_rng(8)
+    vp = ops.to_device(rng.integers(0, 65536, size=(M, M, S, T, 3), dtype=np.uint16))
+    plan = rf.device_plan(S, T, M, [-1, 0, 1], np.zeros((M, M), dtype=bool), vp.device)
+    (hx, cx, xlo, xhi), (hy, cy, ylo, yhi) = plan.tx, plan.ty
+    assert hx is not None and hy is not None and xhi - xlo > 40 and yhi - ylo > 40
+    L, p, st = nat.lib(), ops._ptr, ops._stream()
+    outs = []
+    for fast in (False, True):
+        tmp = torch.zeros((M, M, S, T, 3), dtype=torch.float32, device=vp.device)
+        coef = torch.zeros_like(tmp)
+        if fast:
+            nat.check(L.pcb_refi_prefilter_toeplitz(p(vp), ops._pcb_dtype(vp), M, S, T, 3, p(plan.py_v), p(plan.py_f),
+                                                    plan.Kpy, p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp),
+                                                    p(coef), hx.ctypes.data_as(C.c_void_p), int(hx.size), cx, xlo, xhi,
+                                                    hy.ctypes.data_as(C.c_void_p), int(hy.size), cy, ylo, yhi, st))
+        else:
+            nat.check(L.pcb_refi_prefilter(p(vp), ops._pcb_dtype(vp), M, S, T, 3, p(plan.py_v), p(plan.py_f), plan.Kpy,
+                                           p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp), p(coef), st))
+        torch.cuda.synchronize()
+        outs.append((tmp, coef))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
