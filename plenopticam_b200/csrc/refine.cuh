@@ -207,6 +207,7 @@ refine_h_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, con
     __shared__ int s_x0[RF_MAXM];                          // first staged pixel of view i
     __shared__ int s_wE[RF_MAXM];                          // staged floats per row of view i
     __shared__ int s_act[RF_MAXM];                         // the unmasked view columns of this view-row
+    __shared__ int2 s_view[RF_MAXM];                       // per ACTIVE view: {float offset of pixel 0 in s_win, row pitch}
     __shared__ int s_nact;
     __shared__ int s_ix[RH_MAX_IX];                        // ix[n][i] of the batch
     const int j = blockIdx.z;
@@ -226,11 +227,21 @@ refine_h_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, con
             s_x0[i] = a;
             s_off[i] = off;
             s_wE[i] = (b - a + 1) * 3;
-            if ((act >> i) & 1u) { off += (b - a + 1) * 3 * RH_ROWS; s_act[na++] = i; }
+            if ((act >> i) & 1u) {
+                s_view[na] = make_int2(off - a * 3, (b - a + 1) * 3);
+                off += (b - a + 1) * 3 * RH_ROWS;
+                s_act[na++] = i;
+            }
         }
         s_nact = na;
     }
-    for (int e = tid; e < nb * M; e += RH_THREADS) s_ix[e] = __ldg(ix + e);
+    __syncthreads();
+    // operator index of every (slice, ACTIVE view) of the batch, compacted so that the slice loop indexes it by ii
+    const int nact = s_nact;
+    for (int e = tid; e < nb * nact; e += RH_THREADS) {
+        const int n = e / nact, ii = e - n * nact;
+        s_ix[e] = __ldg(ix + n * M + s_act[ii]);
+    }
     __syncthreads();
     // ---- stage the coefficient windows (rows beyond S replicate nothing: they are never read)
     for (int i = 0; i < M; ++i) {
@@ -246,22 +257,21 @@ refine_h_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, con
     __syncthreads();
     if (tx >= xcn) return;
     const int x = xc0 + tx;
-    const int nact = s_nact;
 
     for (int n = sg; n < nb; n += RH_SG) {                 // the RH_SG thread groups of a CTA take slices round-robin
         float acc[RH_ROWS][3];
 #pragma unroll
         for (int rr = 0; rr < RH_ROWS; ++rr) acc[rr][0] = acc[rr][1] = acc[rr][2] = 0.f;
-        const int *ixn = s_ix + n * M;
+        const int *ixn = s_ix + n * nact;
         for (int ii = 0; ii < nact; ++ii) {
-            const int i = s_act[ii];
-            const int sidx = ixn[i];                                       // uniform, from shared memory
+            const int sidx = ixn[ii];                                      // uniform, from shared memory
+            const int2 vw = s_view[ii];
             const int f = __ldg(dx_first + (size_t)sidx * T + x);
             float w[K];
 #pragma unroll
             for (int m = 0; m < K; ++m) w[m] = __ldg(dx_vals + ((size_t)sidx * K + m) * T + x);
-            const int wE = s_wE[i];
-            const float *px = s_win + s_off[i] + (f - s_x0[i]) * 3;
+            const int wE = vw.y;
+            const float *px = s_win + vw.x + f * 3;
 #pragma unroll
             for (int rr = 0; rr < RH_ROWS; ++rr) {
 #pragma unroll
