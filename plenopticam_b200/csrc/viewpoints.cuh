@@ -62,11 +62,15 @@ viewpoints_kernel(const T *__restrict__ aligned, T *__restrict__ vp, int cols_el
     }
 }
 
+// Inverse: the M view runs of one aligned row (s, j) are requested together with 16-byte asynchronous copies (each run
+// keeps its source's offset inside a 16-byte line, see viewpoints_kernel), then interleaved out of shared memory into
+// one contiguous row.  run_pitch: bytes reserved per run (>= run bytes + 32, multiple of 16).
 template <typename T, int CT>
 __global__ void __launch_bounds__(256)
-viewpoints_inverse_kernel(const T *__restrict__ vp, T *__restrict__ aligned, int M, int S, int Tn, int Crt, int tile_t) {
+viewpoints_inverse_kernel(const T *__restrict__ vp, T *__restrict__ aligned, int M, int S, int Tn, int Crt, int tile_t,
+                          int run_pitch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *row = reinterpret_cast<T *>(smem_raw);
+    __shared__ int s_mis[64];                              // per view: byte offset of its run inside its slot
     const int C = CT ? CT : Crt;
     const int s = blockIdx.x, j = blockIdx.y;
     const int t0 = blockIdx.z * tile_t;
@@ -74,18 +78,47 @@ viewpoints_inverse_kernel(const T *__restrict__ vp, T *__restrict__ aligned, int
     if (nt <= 0) return;
 
     const int n_view = nt * C;
+    constexpr int EPL = 16 / (int)sizeof(T);
     for (int i = 0; i < M; ++i) {
         const T *src = vp + (((size_t)(j * M + i) * S + s) * Tn + t0) * C;
-        for (int idx = threadIdx.x; idx < n_view; idx += blockDim.x) {
-            const int t = idx / C;
-            const int c = idx - t * C;
-            row[(t * M + i) * C + c] = __ldg(src + idx);
-        }
+        const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+        T *run = reinterpret_cast<T *>(smem_raw + (size_t)i * run_pitch + mis);
+        const int head = min(n_view, mis ? (16 - mis) / (int)sizeof(T) : 0);
+        const int nlines = (n_view - head) / EPL;
+        const int tail0 = head + nlines * EPL;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(run + head);
+        const T *gbase = src + head;
+        for (int k = threadIdx.x; k < nlines; k += 256)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * k), "l"(gbase + (size_t)k * EPL)
+                         : "memory");
+        if (threadIdx.x < head) run[threadIdx.x] = __ldg(src + threadIdx.x);
+        if (threadIdx.x < n_view - tail0) run[tail0 + threadIdx.x] = __ldg(src + tail0 + threadIdx.x);
+        if (threadIdx.x == 0) s_mis[i] = mis;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     T *dst = aligned + (size_t)(s * M + j) * ((size_t)Tn * M * C) + (size_t)t0 * M * C;
     const int n_out = nt * M * C;
-    for (int idx = threadIdx.x; idx < n_out; idx += blockDim.x) dst[idx] = row[idx];
+    const int mc = M * C;
+    if (mc <= 256) {
+        // a thread keeps its (view, channel) and walks the lens columns: no division in the copy loop; the
+        // (256 / mc) * mc active threads of a pass write one contiguous stretch
+        const int tq_n = 256 / mc;
+        const int tq = threadIdx.x / mc, rem = threadIdx.x - tq * mc;
+        if (tq < tq_n) {
+            const int i = rem / C, c = rem - i * C;
+            const T *run = reinterpret_cast<const T *>(smem_raw + (size_t)i * run_pitch + s_mis[i]) + c;
+            for (int t = tq; t < nt; t += tq_n) dst[t * mc + rem] = run[t * C];
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < n_out; idx += 256) {
+            const int t = idx / mc;
+            const int rem = idx - t * mc;
+            const int i = rem / C, c = rem - i * C;
+            dst[idx] = reinterpret_cast<const T *>(smem_raw + (size_t)i * run_pitch + s_mis[i])[t * C + c];
+        }
+    }
 }
 
 // micro images of (My_in x Mx_in) pixels -> central (M_out x M_out), margins ky / kx (lfp_cropper.py:34,58-62; the
@@ -101,10 +134,29 @@ crop_kernel(const T *__restrict__ aligned, T *__restrict__ cropped, int cols_ele
     T *dst = cropped + (size_t)orow * ((size_t)LX * M_out * C);
     const int n = LX * M_out * C;
     const int mc = M_out * C;
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int lx = idx / mc;
-        const int rem = idx - lx * mc;   // u*C + c
-        dst[idx] = __ldg(src + (lx * Mx_in + kx) * C + rem);
+    if (mc <= (int)blockDim.x) {
+        // a thread keeps its position (u, c) inside the micro image and walks the lens columns: no division per element
+        const int lq_n = blockDim.x / mc;
+        const int lq = threadIdx.x / mc, rem = threadIdx.x - lq * mc;
+        if (lq < lq_n) {
+            const T *sp = src + kx * C + rem;
+            constexpr int U = 4;
+            int lx = lq;
+            for (; lx + (U - 1) * lq_n < LX; lx += U * lq_n) {            // U independent loads in flight
+                T v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = __ldg(sp + (size_t)(lx + u * lq_n) * Mx_in * C);
+#pragma unroll
+                for (int u = 0; u < U; ++u) dst[(size_t)(lx + u * lq_n) * mc + rem] = v[u];
+            }
+            for (; lx < LX; lx += lq_n) dst[(size_t)lx * mc + rem] = __ldg(sp + (size_t)lx * Mx_in * C);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int lx = idx / mc;
+            const int rem = idx - lx * mc;   // u*C + c
+            dst[idx] = __ldg(src + (lx * Mx_in + kx) * C + rem);
+        }
     }
 }
 
@@ -145,17 +197,26 @@ static int launch_viewpoints(const void *aligned, void *vp, int rows, int cols, 
 
 template <typename T>
 static int launch_viewpoints_inverse(const void *vp, void *aligned, int M, int S, int Tn, int C, cudaStream_t st) {
-    int tile_t, ntile;
-    size_t smem;
-    if (vp_tile(Tn, M, C, sizeof(T), &tile_t, &ntile, &smem))
-        return fail(PCB_ERR_UNSUPPORTED, "%s: micro image row too large for shared memory", "pcb_viewpoints_inverse");
+    if (M > 64) return fail(PCB_ERR_UNSUPPORTED, "%s: more than 64 x 64 views", "pcb_viewpoints_inverse");
+    // tiles of tile_t lens columns: M runs of tile_t * C elements, each in a slot with 32 bytes of alignment slack
+    const size_t budget = 48 * 1024;
+    int ntile = 1, tile_t = Tn;
+    size_t run_pitch = 0;
+    for (;; ++ntile) {
+        tile_t = (Tn + ntile - 1) / ntile;
+        run_pitch = (((size_t)tile_t * C * sizeof(T) + 32) + 15) & ~(size_t)15;
+        if ((size_t)M * run_pitch <= budget) break;
+        if (tile_t == 1) return fail(PCB_ERR_UNSUPPORTED, "%s: micro image row too large for shared memory", "pcb_viewpoints_inverse");
+    }
+    ntile = (Tn + tile_t - 1) / tile_t;
+    const size_t smem = (size_t)M * run_pitch;
     dim3 grid(S, M, ntile), block(256);
     if (C == 3)
-        viewpoints_inverse_kernel<T, 3><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t);
+        viewpoints_inverse_kernel<T, 3><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t, (int)run_pitch);
     else if (C == 1)
-        viewpoints_inverse_kernel<T, 1><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t);
+        viewpoints_inverse_kernel<T, 1><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t, (int)run_pitch);
     else
-        viewpoints_inverse_kernel<T, 0><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t);
+        viewpoints_inverse_kernel<T, 0><<<grid, block, smem, st>>>((const T *)vp, (T *)aligned, M, S, Tn, C, tile_t, (int)run_pitch);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }
