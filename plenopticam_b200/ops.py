@@ -464,6 +464,21 @@ def percentile_f64(data, q):
     return res
 
 
+def devignette_divide(lfp, wn, out=None, out_dtype=torch.float32):
+    """lfp / wn where wn != 0, else 0 (lfp_devignetter.py:83-93) with an already normalised gray white image `wn`
+    ((H, W) float64 CUDA tensor, e.g. the second result of `devignette`): the per-exposure part of de-vignetting."""
+    _chk_dev(lfp, wn)
+    H, W = int(lfp.shape[0]), int(lfp.shape[1])
+    Cl = int(lfp.shape[2]) if lfp.dim() == 3 else 1
+    if wn.dtype != torch.float64 or tuple(wn.shape) != (H, W):
+        raise TypeError("normalised white image must be a float64 (H, W) tensor")
+    if out is None:
+        out = torch.empty(tuple(lfp.shape), dtype=out_dtype, device=lfp.device)
+    nat.check(nat.lib().pcb_devig_divide(_ptr(lfp), _TORCH2PCB_F64[lfp.dtype], H * W, Cl, _ptr(wn), _ptr(out),
+                                         _TORCH2PCB_F64[out.dtype], _stream()))
+    return out
+
+
 def devignette(lfp, wht, gauss_1d, out_dtype=torch.float64):
     """White-image division on the device.
 

@@ -25,7 +25,7 @@ class LightFieldPipeline(object):
     """
 
     def __init__(self, centroids, raw_shape, raw_dtype, M, pat_type, ran_refo=(0, 2), flip=False,
-                 postprocess=True, device=None, fuse_post=True):
+                 postprocess=True, device=None, fuse_post=True, wht_img=None):
         self.device = ops.require_cuda() if device is None else torch.device(device)
         self.M = int(M)
         self.flip = bool(flip)
@@ -59,6 +59,18 @@ class LightFieldPipeline(object):
             self.scratch = torch.empty(int(nat.lib().pcb_percentile_scratch_bytes()), dtype=torch.uint8, device=dev)
             self._q_lo = (C.c_double * 1)(0.005)
             self._q_hi = (C.c_double * 1)(99.9)
+            # de-vignetting (LfpAligner with opt_vign, lfp_aligner/top_level.py:51-57): the normalised gray white image
+            # depends on the calibration only and is prepared once; every exposure is divided by it (float64 division,
+            # float32 image) and then takes the float resampler
+            self.wn = None
+            if wht_img is not None:
+                from .lfp_aligner.lfp_devignetter import gauss_kernel_1d
+                wht = wht_img if hasattr(wht_img, 'is_cuda') else ops.to_device_any(np.asarray(wht_img))
+                probe = torch.zeros((self.raw_shape[0], self.raw_shape[1], 1), dtype=torch.float32, device=dev)
+                _, self.wn, stats = ops.devignette(probe, wht, gauss_kernel_1d(int(self.M)), out_dtype=torch.float32)
+                self.noise_lev = float(stats[2].item())
+                self.devig = torch.empty(self.raw_shape, dtype=torch.float32, device=dev)
+                del probe
             # pinned staging for the host-buffer entry point
             self._pin_in = None
             self._pin_out = None
@@ -67,6 +79,8 @@ class LightFieldPipeline(object):
     # -- stage launches (enqueue only) ---------------------------------------------------------------------
     def align(self, raw=None):
         raw = self.raw if raw is None else raw
+        if self.wn is not None:
+            raw = ops.devignette_divide(raw, self.wn, out=self.devig)
         ops.resample_u16(raw, self.tabs, flip=self.flip, out=self.aligned, mm=self.mm_align)
         return self.aligned
 

@@ -51,3 +51,33 @@ def test_stage_classes_chained_vs_reference_golden(cuda, tmp_path):
     rf2 = LfpRefocuser(g["vp"], cfg=cfg, sta=sta)
     assert rf2.main() is True
     assert np.abs(rf2.refo_stack.astype(np.float64) - g["stack"]).max() <= 2e-6
+
+
+@pytest.mark.gpu
+def test_pipeline_with_white_image_equals_the_stage_classes(cuda, tmp_path):
+    """LightFieldPipeline(wht_img=...) = de-vignetting + resampling + gather + stack + colour management in one executor:
+    same aligned image as LfpAligner(opt_vign) and same stack as the chained classes, and the reference within 1e-4."""
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_aligner import LfpAligner
+    from plenopticam_b200.lfp_extractor import LfpExtractor
+    from plenopticam_b200.lfp_refocuser import LfpRefocuser
+    from plenopticam_b200.pipeline import LightFieldPipeline
+    g = golden("config1_chain")
+    M = int(g["M"])
+    ran = [int(v) for v in g["ran_refo"]]
+    cfg, sta = make_cfg(g["centroids"], 'rec', M, ran_refo=ran, tmpdir=tmp_path)
+    for k, v in ((cfg.opt_vign, True), (cfg.opt_rota, False), (cfg.opt_view, True), (cfg.opt_refo, True), (cfg.opt_pflu, False)):
+        cfg.params[k] = v
+    al = LfpAligner(g["lfp"], cfg=cfg, sta=sta, wht_img=g["wht"])
+    assert al.main() is True
+    ex = LfpExtractor(al.lfp_img, cfg=cfg, sta=sta)
+    assert ex.main() is True
+    rf = LfpRefocuser(ex.vp_img_linear, cfg=cfg, sta=sta)
+    assert rf.main() is True
+
+    pipe = LightFieldPipeline(g["centroids"], g["lfp"].shape, np.uint16, M, 'rec', ran_refo=ran, wht_img=g["wht"])
+    out = pipe.run(g["lfp"]).copy()
+    assert np.array_equal(ops.to_host(pipe.aligned), al.lfp_img)
+    assert np.array_equal(out, rf.refo_stack)
+    assert np.abs(out.astype(np.float64) - g["stack"]).max() <= 1e-4
+    assert pipe.noise_lev > 0
