@@ -23,6 +23,10 @@
 extern "C" {
 #endif
 
+/* ABI revision: bumped whenever an entry point is added or its arguments change.  pcb_version() returns the value the
+ * library was built with; a binding refuses a library of another revision (plenopticam_b200/_native.py). */
+#define PCB_ABI_VERSION 200
+
 #define PCB_OK               0
 #define PCB_ERR_INVALID      1   /* bad argument (null pointer, non-positive size, unsupported dtype)  */
 #define PCB_ERR_CUDA         2   /* a CUDA runtime call / launch failed                                  */
@@ -197,6 +201,36 @@ int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N,
                      const int32_t *xlo_host, const int32_t *xhi_host,
                      const uint8_t *view_zeroed_host, const uint8_t *view_zeroed,
                      float *tmp, float *out, pcb_minmax_t *mm, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-GPU, slice-sharded stack (no counterpart in the single-process reference): every GPU
+ * evaluates its own block of refocus parameters and the kernel that finishes a slice stores it, tile by tile, into the
+ * stack buffer of EVERY GPU of the job through peer-mapped pointers (NVLink / NVSwitch stores) - compute and exchange
+ * in one kernel, no separate all-gather.
+ *   pcb_peer_alloc / pcb_peer_free : a buffer other processes can map (plain cudaMalloc on the current device: IPC
+ *                        handles cover whole allocations, so a sub-allocated pointer cannot be exported).  The one
+ *                        place this library allocates.
+ *   pcb_peer_export    : 64-byte handle of such a buffer (cudaIpcGetMemHandle), to be passed to the other processes
+ *   pcb_peer_open / _close : map / unmap a peer's buffer from its handle (enables peer access on first use)
+ *   pcb_fanout_t       : where a finished block goes: n destinations (index 0..n-1; the local buffer is one of them),
+ *                        out[d] = address of the FIRST slice of this call inside destination d, mm[d] = that
+ *                        destination's running min / max (nullable: all or none)
+ *   pcb_refocus_refi_fanout : pcb_refocus_refi with the destinations in *dst_host (HOST struct, copied at the call)
+ * ------------------------------------------------------------------------------------------------ */
+#define PCB_MAX_PEERS 16
+typedef struct { float *out[PCB_MAX_PEERS]; pcb_minmax_t *mm[PCB_MAX_PEERS]; int32_t n; int32_t reserved; } pcb_fanout_t;
+int pcb_peer_alloc(int64_t bytes, void **dptr_host);
+int pcb_peer_free(void *dptr);
+int pcb_peer_export(void *dptr, unsigned char handle_host[64]);
+int pcb_peer_open(const unsigned char handle_host[64], void **dptr_host);
+int pcb_peer_close(void *dptr);
+int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N,
+                            const float *dy_vals, const int32_t *dy_first, int Kgy,
+                            const float *dx_vals, const int32_t *dx_first, int Kx,
+                            const int32_t *iy, const int32_t *ix,
+                            const int32_t *xlo_host, const int32_t *xhi_host,
+                            const uint8_t *view_zeroed_host, const uint8_t *view_zeroed,
+                            float *tmp, const pcb_fanout_t *dst_host, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Post-processing of the stack — replaces LfpContrast.auto_hist_align + GammaConverter.srgb_conv as used

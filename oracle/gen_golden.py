@@ -183,6 +183,24 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "refocuser_post_u16.npz"), vp=vp_u16p, M=5, ran_refo=(-1, 2), stack=st)
     print("refocuser", st.shape, st.dtype, st.min(), st.max())
 
+    # ---- refinement, round 2: M = 7 with a range that starts negative (shifts a in [-7, 7) up-sampled pixels);
+    #      its own generator so that every file above stays byte-identical
+    rng7 = np.random.default_rng(77)
+    vp_u16r = rng7.integers(0, 65536, size=(7, 7, 11, 13, 3), dtype=np.uint16)
+    st = run_shiftandsum(vp_u16r, 7, (-1, 1), refi=True)
+    np.savez_compressed(os.path.join(GOLDEN, "refocus_refi_m7_neg_u16.npz"), vp=vp_u16r, M=7, ran_refo=(-1, 1), stack=st)
+    print("refocus refi M=7 negative range", st.shape)
+
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "refi_m7":          # only the round-2 addition
+        _main = main
+
+        def main():
+            rng7 = np.random.default_rng(77)
+            vp_u16r = rng7.integers(0, 65536, size=(7, 7, 11, 13, 3), dtype=np.uint16)
+            st = run_shiftandsum(vp_u16r, 7, (-1, 1), refi=True)
+            np.savez_compressed(os.path.join(GOLDEN, "refocus_refi_m7_neg_u16.npz"), vp=vp_u16r, M=7, ran_refo=(-1, 1),
+                                stack=st)
+            print("refocus refi M=7 negative range", st.shape)
     main()

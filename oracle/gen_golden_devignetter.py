@@ -19,24 +19,7 @@ from oracle import oracle_np as onp  # noqa: E402
 GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
-def white_image(H, W, cent, pitch, C, seed, dtype):
-    """cos^4-like vignette per lenslet + noise, a few dead (zero) pixels."""
-    rng = np.random.default_rng(seed)
-    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
-    d2 = np.full((H, W), 1e9)
-    for y, x in cent[:, :2]:
-        y0, y1 = int(max(0, y - pitch)), int(min(H, y + pitch + 1))
-        x0, x1 = int(max(0, x - pitch)), int(min(W, x + pitch + 1))
-        sub = (yy[y0:y1, x0:x1] - y) ** 2 + (xx[y0:y1, x0:x1] - x) ** 2
-        d2[y0:y1, x0:x1] = np.minimum(d2[y0:y1, x0:x1], sub)
-    vig = np.cos(np.clip(np.sqrt(d2) / pitch, 0, 1) * 1.2) ** 4
-    img = vig[..., None] * np.array([0.9, 1.0, 0.8])[None, None, :C] if C > 1 else vig
-    img = img * (0.9 + 0.1 * rng.random(img.shape))
-    img = np.round(img * 60000).astype(dtype) if np.issubdtype(dtype, np.integer) else img.astype(dtype)
-    flat = img.reshape(-1, C) if C > 1 else img.reshape(-1, 1)
-    dead = rng.choice(flat.shape[0], size=7, replace=False)
-    flat[dead] = 0
-    return img
+from plenopticam_b200.misc.synth import white_image  # noqa: E402,F401
 
 
 def run(lfp, wht, cent, M):

@@ -408,10 +408,11 @@ def img_resize(img, scale):
     return np.einsum('yn,nmc,xm->yxc', Wy, img, Wx, optimize=True)
 
 
-def refocus_refi(vp, ran_refo, M):
+def refocus_refi(vp, ran_refo, M, a_list=None):
     """lfp_shiftandsum.py:77-139 with opt_refi: every view upsampled xM (:102), shifts in upsampled
     pixels a in range(M*r0, M*r1) (:93-94), summed, cropped (:123-124), downsampled x1/M (:135).
-    Materialises the upsampled views; use only at small sizes."""
+    Materialises the upsampled views; use only at small sizes.  `a_list`: evaluate only these members of the
+    range (the slices are independent; saves time in the large-M parity tests)."""
     vp64 = _apply_aperture(vp, M)
     vp64 /= M
     S, T, C = vp64.shape[2:]
@@ -425,7 +426,10 @@ def refocus_refi(vp, ran_refo, M):
     ys = np.arange(S * M)
     xs = np.arange(T * M)
     stack = []
-    for a in range(M * ran_refo[0], M * ran_refo[1]):
+    full = range(M * ran_refo[0], M * ran_refo[1])
+    if a_list is not None:
+        assert all(a in full for a in a_list)
+    for a in (full if a_list is None else a_list):
         acc = np.zeros((S * M, T * M, C))
         for j in range(M):
             yi = np.clip(ys + a * (c - j), 0, S * M - 1)
@@ -479,40 +483,7 @@ def refocuser_postprocess(stack):
 # ----------------------------------------------------------------------------------------------------
 # synthetic data (BASELINE.json configs)
 # ----------------------------------------------------------------------------------------------------
-def synth_centroids(LY, LX, pitch, pat_type='hex', hex_odd=True, jitter=0.15, rot_deg=0.0, origin=None, seed=0):
-    """Centroid table rows [y, x, ly, lx] for a rec / hex MLA with Gaussian jitter and optional rotation.
-    Same row layout as `GridFitter.grid_gen` (lfp_calibrator/grid_fitter.py:215-256)."""
-    rng = np.random.default_rng(seed)
-    py = pitch * (np.sqrt(3) / 2 if pat_type == 'hex' else 1.0)
-    oy, ox = origin if origin is not None else (pitch / 2 + 2.0, pitch / 2 + 2.0)
-    ly, lx = np.meshgrid(np.arange(LY), np.arange(LX), indexing='ij')
-    y = oy + ly * py
-    x = ox + lx * pitch
-    if pat_type == 'hex':
-        x = x + (pitch / 2) * np.mod(ly + (0 if hex_odd else 1), 2)
-    y = y + rng.normal(0, jitter, y.shape)
-    x = x + rng.normal(0, jitter, x.shape)
-    if rot_deg:
-        t = np.deg2rad(rot_deg)
-        cy, cx = y.mean(), x.mean()
-        y, x = (cy + np.cos(t) * (y - cy) + np.sin(t) * (x - cx),
-                cx - np.sin(t) * (y - cy) + np.cos(t) * (x - cx))
-    return np.stack([y.ravel(), x.ravel(), ly.ravel().astype(float), lx.ravel().astype(float)], axis=1)
-
-
-def synth_raw(H, W, C=3, seed=0, dtype=np.uint16):
-    """Low-frequency sinusoid mix + uniform noise, uint16 range (post-demosaic RGB is uint16,
-    lfp_aligner/cfa_processor.py:73)."""
-    rng = np.random.default_rng(seed)
-    yy = np.arange(H, dtype=np.float32)[:, None, None]
-    xx = np.arange(W, dtype=np.float32)[None, :, None]
-    ph = np.arange(C, dtype=np.float32)[None, None, :]
-    img = 0.5 + 0.2 * np.sin(yy / 37.0 + ph) * np.cos(xx / 53.0 - ph) + 0.15 * np.sin((xx + yy) / 11.0 + 2 * ph)
-    img = img + 0.1 * rng.random((H, W, C), dtype=np.float32)
-    img = np.clip(img, 0, 1)
-    if np.issubdtype(dtype, np.integer):
-        return np.round(img * 65535.0).astype(dtype)
-    return img.astype(dtype)
+from plenopticam_b200.misc.synth import synth_centroids, synth_raw  # noqa: E402,F401  (neutral data generators)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -11,7 +11,8 @@ Why a shim is needed:
     tifffile / docutils / matplotlib are not installed.
 The shim pre-seeds `sys.modules` with inert stubs and replaces `interp2d` with the replacement that
 SciPy's own removal notice prescribes: `RectBivariateSpline(x, y, z.T, kx=k, ky=k, s=0)` (both are
-FITPACK `regrid_smth`).  The reference sources themselves are untouched and never copied.
+FITPACK `regrid_smth`).  The reference sources themselves are untouched; `oracle/make_ref.sh` snapshots them byte for byte into the git-ignored
+`oracle/_ref/` so that the benchmark's reference arm can run them on the GPU box (where /root/reference is absent).
 """
 import importlib
 import os
@@ -20,7 +21,22 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PLENOPTICAM_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    """$PLENOPTICAM_REFERENCE, else the read-only checkout of the build container, else the byte-identical snapshot
+    `sh oracle/make_ref.sh` leaves under oracle/_ref (git-ignored; it is what reaches the GPU box)."""
+    env = os.environ.get("PLENOPTICAM_REFERENCE")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(cand, "plenopticam")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:

@@ -4,6 +4,8 @@ There is no CPU fallback: if the library cannot be loaded, every operator raises
 library in-tree with nvcc for sm_100a (the built .so is git-ignored but travels with the snapshot).
 """
 import ctypes as C
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -24,6 +26,15 @@ PCB_REC, PCB_HEX = 0, 1
 PCB_LENS_INVALID = -2 ** 31
 
 # numpy mirrors of the C structs
+PCB_MAX_PEERS = 16
+
+
+class Fanout(C.Structure):
+    """pcb_fanout_t"""
+    _fields_ = [("out", C.c_void_p * PCB_MAX_PEERS), ("mm", C.c_void_p * PCB_MAX_PEERS), ("n", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 LENS_DTYPE = np.dtype([("oy", "<i4"), ("ox", "<i4"), ("wy", "<f4"), ("wx", "<f4")])
 HEXCOL_DTYPE = np.dtype([("x0", "<i4"), ("x1", "<i4"), ("w", "<f4"), ("reserved", "<i4")])
 
@@ -39,30 +50,60 @@ def _sources():
     return sorted(os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh")))
 
 
+#: ABI the binding below was written against; `pcb_version()` of the loaded library must return it.  Bump together
+#: with PCB_ABI_VERSION in include/plenopticam_b200.h whenever an entry point is added or its arguments change.
+ABI_VERSION = 200
+
+STAMP_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash():
+    """sha256 over the CUDA sources, the header and the compiler flags: what the .so must have been built from.
+    (File times do not survive the snapshot to the GPU box, a content hash does.)"""
+    h = hashlib.sha256()
+    for path in _sources() + [HEADER]:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB_PATH):
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH)):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(s) > t for s in _sources() + [HEADER])
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/pcb200.cu -> libpcb200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/pcb200.cu -> libpcb200.so for sm_100a (nvcc cross-compiles without a GPU).  Serialised over
+    processes with a file lock: of N ranks starting together one compiles, the others wait and find a fresh library."""
     if not force and not _stale():
         return LIB_PATH
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        raise NativeLibraryError("nvcc not found; cannot build %s" % LIB_PATH)
-    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC_DIR, "pcb200.cu")]
-    if verbose:
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0:
-        if os.path.exists(tmp):
-            os.remove(tmp)
-        raise NativeLibraryError("nvcc failed:\n" + res.stdout)
-    os.replace(tmp, LIB_PATH)
+    with open(LIB_PATH + ".lock", "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+            if not os.path.exists(nvcc):
+                raise NativeLibraryError("nvcc not found; cannot build %s" % LIB_PATH)
+            want = source_hash()
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC_DIR, "pcb200.cu")]
+            if verbose:
+                print(" ".join(cmd))
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise NativeLibraryError("nvcc failed:\n" + res.stdout)
+            os.replace(tmp, LIB_PATH)
+            with open(STAMP_PATH, "w") as f:
+                f.write(want + "\n")
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -96,6 +137,13 @@ _SIGNATURES = {
                                          _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "pcb_refocus_refi": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp]),
+    "pcb_refocus_refi_fanout": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _vp]),
+    "pcb_peer_alloc": (_i, [_i64, C.POINTER(C.c_void_p)]),
+    "pcb_peer_free": (_i, [_vp]),
+    "pcb_peer_export": (_i, [_vp, C.c_char_p]),
+    "pcb_peer_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "pcb_peer_close": (_i, [_vp]),
     "pcb_percentile_scratch_bytes": (_i64, []),
     "pcb_percentile_f32": (_i, [_vp, _i64, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
     "pcb_contrast_bounds": (_i, [_vp, _i64, C.c_double, C.c_double, _vp, _vp, _vp]),
@@ -130,16 +178,21 @@ def lib():
         if _lib is not None:
             return _lib
         if _stale():
-            try:
-                build()
-            except NativeLibraryError:
-                if not os.path.exists(LIB_PATH):
-                    raise
+            # never load a library that was not built from the sources in this tree: a failed rebuild raises
+            build()
         try:
             handle = C.CDLL(LIB_PATH)
         except OSError as e:
             raise NativeLibraryError("cannot load %s (%s); run `python -c 'import __graft_entry__ as g; g.build()'`"
                                      % (LIB_PATH, e))
+        try:
+            handle.pcb_version.restype = C.c_int
+            got = int(handle.pcb_version())
+        except AttributeError:
+            raise NativeLibraryError("%s does not export pcb_version" % LIB_PATH)
+        if got != ABI_VERSION:
+            raise NativeLibraryError("%s has ABI version %d, the binding expects %d (header and binding out of step)"
+                                     % (LIB_PATH, got, ABI_VERSION))
         for name, (res, args) in _SIGNATURES.items():
             try:
                 fn = getattr(handle, name)

@@ -42,14 +42,17 @@ inline int fail(int code, const char *fmt, const char *a = "", long long b = 0) 
         }                                                                                         \
     } while (0)
 
-// SM count of the current device (persistent / strip-mined grids)
+// SM count of the CURRENT device (persistent / strip-mined grids); cached per device ordinal, so a process that
+// drives several GPUs sizes every grid for the device it launches on
 static inline int sm_count() {
-    static int n = 0;
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev];
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
     }
     return n;
 }
@@ -104,6 +107,40 @@ __device__ __forceinline__ void block_minmax_commit(float mn, float mx, pcb_minm
         if (lane == 0) {
             atomicMin(&mm->kmin, float_to_key(mn));
             atomicMax(&mm->kmax, float_to_key(mx));
+        }
+    }
+}
+
+// Same, committed to the running min / max of every destination of a fan-out (atomics on peer-mapped memory travel
+// over NVLink like any other access).
+__device__ __forceinline__ void block_minmax_commit_fanout(float mn, float mx, const pcb_fanout_t &dst) {
+    __shared__ float s_mn[32], s_mx[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        mn = lane < nw ? s_mn[lane] : INFINITY;
+        mx = lane < nw ? s_mx[lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane < dst.n && lane < PCB_MAX_PEERS) {          // one lane per destination
+            pcb_minmax_t *mm = nullptr;
+#pragma unroll
+            for (int d = 0; d < PCB_MAX_PEERS; ++d)
+                if (d == lane) mm = dst.mm[d];
+            if (mm != nullptr) {
+                atomicMin(&mm->kmin, float_to_key(mn));
+                atomicMax(&mm->kmax, float_to_key(mx));
+            }
         }
     }
 }

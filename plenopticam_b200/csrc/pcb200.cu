@@ -54,7 +54,7 @@ static int devig_divide_out(const void *lfp, int64_t npx, int C, const double *w
 
 extern "C" {
 
-int pcb_version(void) { return 100; }
+int pcb_version(void) { return PCB_ABI_VERSION; }
 
 const char *pcb_last_error(void) { return g_err; }
 
@@ -356,19 +356,94 @@ int pcb_refi_prefilter_toeplitz(const void *vp, int dtype, int M, int S, int T, 
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
 
+static int check_refocus_refi(const float *coef, int M, int S, int T, int C, int N, const float *dy_vals,
+                              const int32_t *dy_first, int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx,
+                              const int32_t *iy, const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
+                              const uint8_t *view_zeroed_host, const uint8_t *view_zeroed, float *tmp) {
+    PCB_REQUIRE(coef && dy_vals && dy_first && dx_vals && dx_first && iy && ix && xlo_host && xhi_host &&
+                view_zeroed_host && view_zeroed && tmp, "pointers");
+    PCB_REQUIRE(M > 0 && M <= RF_MAXM && M % 2 == 1 && S >= 4 && T >= 4 && N > 0 && N <= 65535 && Kgy > 0 && Kx > 0,
+                "sizes, odd M <= 32");
+    PCB_REQUIRE(C == 3, "3 colour channels (lfp_shiftandsum.py:97)");
+    PCB_REQUIRE((S + RH_ROWS - 1) / RH_ROWS <= 65535, "S");
+    return PCB_OK;
+}
+
 int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N, const float *dy_vals,
                      const int32_t *dy_first, int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx,
                      const int32_t *iy, const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
                      const uint8_t *view_zeroed_host, const uint8_t *view_zeroed, float *tmp, float *out,
                      pcb_minmax_t *mm, void *stream) {
-    PCB_REQUIRE(coef && dy_vals && dy_first && dx_vals && dx_first && iy && ix && xlo_host && xhi_host &&
-                view_zeroed_host && view_zeroed && tmp && out, "pointers");
-    PCB_REQUIRE(M > 0 && M <= RF_MAXM && M % 2 == 1 && S >= 4 && T >= 4 && N > 0 && N <= 65535 && Kgy > 0 && Kx > 0,
-                "sizes, odd M <= 32");
-    PCB_REQUIRE(C == 3, "3 colour channels (lfp_shiftandsum.py:97)");
-    PCB_REQUIRE((S + RH_ROWS - 1) / RH_ROWS <= 65535, "S");
+    int rc = check_refocus_refi(coef, M, S, T, C, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host,
+                                xhi_host, view_zeroed_host, view_zeroed, tmp);
+    if (rc) return rc;
+    PCB_REQUIRE(out != nullptr, "out");
+    pcb_fanout_t dst;
+    memset(&dst, 0, sizeof(dst));
+    dst.out[0] = out;
+    dst.mm[0] = mm;
+    dst.n = 1;
     return launch_refine(coef, M, S, T, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host, xhi_host,
-                         view_zeroed_host, tmp, out, mm, as_stream(stream));
+                         view_zeroed_host, tmp, dst, as_stream(stream));
+}
+
+int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N, const float *dy_vals,
+                            const int32_t *dy_first, int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx,
+                            const int32_t *iy, const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
+                            const uint8_t *view_zeroed_host, const uint8_t *view_zeroed, float *tmp,
+                            const pcb_fanout_t *dst_host, void *stream) {
+    int rc = check_refocus_refi(coef, M, S, T, C, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host,
+                                xhi_host, view_zeroed_host, view_zeroed, tmp);
+    if (rc) return rc;
+    PCB_REQUIRE(dst_host != nullptr && dst_host->n >= 1 && dst_host->n <= PCB_MAX_PEERS, "1 <= destinations <= 16");
+    pcb_fanout_t dst = *dst_host;
+    for (int d = 0; d < PCB_MAX_PEERS; ++d) {
+        if (d < dst.n) {
+            PCB_REQUIRE(dst.out[d] != nullptr, "destination pointer");
+            PCB_REQUIRE((dst.mm[d] != nullptr) == (dst.mm[0] != nullptr), "min/max targets: all or none");
+        } else {
+            dst.out[d] = nullptr;
+            dst.mm[d] = nullptr;
+        }
+    }
+    return launch_refine(coef, M, S, T, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host, xhi_host,
+                         view_zeroed_host, tmp, dst, as_stream(stream));
+}
+
+// ---- peer-mapped buffers (slice-sharded stacks) --------------------------------------------------------------------
+int pcb_peer_alloc(int64_t bytes, void **dptr_host) {
+    PCB_REQUIRE(bytes > 0 && dptr_host != nullptr, "bytes > 0, dptr");
+    PCB_CUDA(cudaMalloc(dptr_host, (size_t)bytes));
+    return PCB_OK;
+}
+
+int pcb_peer_free(void *dptr) {
+    PCB_REQUIRE(dptr != nullptr, "dptr");
+    PCB_CUDA(cudaFree(dptr));
+    return PCB_OK;
+}
+
+int pcb_peer_export(void *dptr, unsigned char handle_host[64]) {
+    PCB_REQUIRE(dptr != nullptr && handle_host != nullptr, "dptr, handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PCB_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle_host, &h, 64);
+    return PCB_OK;
+}
+
+int pcb_peer_open(const unsigned char handle_host[64], void **dptr_host) {
+    PCB_REQUIRE(handle_host != nullptr && dptr_host != nullptr, "handle, dptr");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, 64);
+    PCB_CUDA(cudaIpcOpenMemHandle(dptr_host, h, cudaIpcMemLazyEnablePeerAccess));
+    return PCB_OK;
+}
+
+int pcb_peer_close(void *dptr) {
+    PCB_REQUIRE(dptr != nullptr, "dptr");
+    PCB_CUDA(cudaIpcCloseMemHandle(dptr));
+    return PCB_OK;
 }
 
 int64_t pcb_percentile_scratch_bytes(void) { return (int64_t)sizeof(SelectState); }

@@ -294,10 +294,13 @@ refine_h_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, con
 
 // ---- vertical pass -----------------------------------------------------------------------------------------------
 // grid (Gy, ceil(E/256), nb): thread = one (x, c) element of a group of 4 output rows of slice n.
+// The finished values go to every destination of `dst` (pcb_fanout_t): the local stack and, in a slice-sharded job, the
+// peer-mapped stacks of the other GPUs - the exchange is these stores, issued as soon as a tile is done, so the NVLink
+// traffic overlaps the arithmetic of the CTAs that are still running.
 __global__ void __launch_bounds__(256)
 refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *__restrict__ dy_vals,
                 const int32_t *__restrict__ dy_first, int Kg, const int32_t *__restrict__ iy, RefineHCtl ctl,
-                float *__restrict__ out, pcb_minmax_t *mm) {
+                pcb_fanout_t dst) {
     const int gy = blockIdx.x;
     const int Gy = gridDim.x;
     const int n = blockIdx.z;
@@ -323,19 +326,21 @@ refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *_
             }
         }
         const float invM = 1.0f / (float)M;
-        float *out_n = out + (size_t)n * S * E;
+        const size_t o_n = (size_t)n * S * E + e;
 #pragma unroll
         for (int q = 0; q < RF_GROUP; ++q) {
             const int y = gy * RF_GROUP + q;
             if (y < S) {
                 const float v = acc[q] * invM;
-                out_n[(size_t)y * E + e] = v;
+#pragma unroll
+                for (int d = 0; d < PCB_MAX_PEERS; ++d)
+                    if (d < dst.n) dst.out[d][o_n + (size_t)y * E] = v;
                 mn = fminf(mn, v);
                 mx = fmaxf(mx, v);
             }
         }
     }
-    if (mm != nullptr) block_minmax_commit(mn, mx, mm);
+    if (dst.mm[0] != nullptr) block_minmax_commit_fanout(mn, mx, dst);
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
@@ -401,7 +406,7 @@ static int launch_refine_h(const float *coef, int M, int S, int T, int nb, const
 static int launch_refine(const float *coef, int M, int S, int T, int nb, const float *dy_vals, const int32_t *dy_first,
                          int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx, const int32_t *iy,
                          const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
-                         const uint8_t *view_zeroed_host, float *H, float *out, pcb_minmax_t *mm, cudaStream_t st) {
+                         const uint8_t *view_zeroed_host, float *H, const pcb_fanout_t &dst, cudaStream_t st) {
     const int E = T * 3;
     RefineHCtl ctl;
     memset(&ctl, 0, sizeof(ctl));
@@ -439,7 +444,7 @@ static int launch_refine(const float *coef, int M, int S, int T, int nb, const f
     }
     if (rc) return rc;
     const int Gy = (S + RF_GROUP - 1) / RF_GROUP;
-    refine_v_kernel<<<dim3(Gy, (E + 255) / 256, nb), 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, Kgy, iy, ctl, out, mm);
+    refine_v_kernel<<<dim3(Gy, (E + 255) / 256, nb), 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, Kgy, iy, ctl, dst);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }

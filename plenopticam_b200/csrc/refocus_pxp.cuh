@@ -45,6 +45,7 @@ struct PxpArgs {
     int rawOffset;   // byte offset of the raw buffer in dynamic shared memory (multiple of 16)
     int ntiles;      // nrows * S
     int nsl, n0;
+    size_t vpBytes;  // size of the light field in bytes: no access outside [vp, vp + vpBytes)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -93,25 +94,45 @@ __device__ __forceinline__ void pxp_tile(const PxpArgs &p, const PxpCtl &ctl, in
     j = ctl.rows[g * ctl.gsz + (rem - r * gn)];
 }
 
-// Elected thread: one bulk copy per active view row of tile (j, r): the 16-byte aligned superset of the row
-// (<= 15 bytes either side; they stay inside the allocation granule of any CUDA allocation).
+// Elected thread: one bulk copy per active view row of tile (j, r).  cp.async.bulk needs 16-byte aligned addresses and
+// sizes, so a row travels as the 16-byte aligned superset of its bytes (<= 15 bytes either side, which belong to the
+// neighbouring rows of the light field) - CLAMPED to the 16-byte lines that lie entirely inside the caller's buffer
+// [vp, vp + vpBytes): the few bytes of the first / last row that share a line with memory outside the buffer are
+// fetched with plain 2-byte loads instead, so the kernel never touches a byte the caller does not own.
 __device__ __forceinline__ void pxp_issue_tile(const PxpArgs &p, const PxpCtl &ctl, unsigned char *raw, uint64_t *bar,
                                                int j, int r) {
     const int nact = ctl.nact[j];
     const size_t rowB = (size_t)p.T * 6;
     const size_t g0 = (size_t)p.vp + (((size_t)j * p.M + ctl.first[j]) * p.S + r) * rowB;
     const size_t gstep = (size_t)p.S * rowB;
+    const size_t lo16 = ((size_t)p.vp + 15) & ~(size_t)15;                   // first / one-past-last whole line inside
+    const size_t hi16 = ((size_t)p.vp + p.vpBytes) & ~(size_t)15;
     uint32_t total = 0;
     for (int ii = 0; ii < nact; ++ii) {
         const size_t g = g0 + ii * gstep;
-        total += (uint32_t)(((g + rowB + 15) & ~(size_t)15) - (g & ~(size_t)15));
+        const size_t b = max(g & ~(size_t)15, lo16), e = min((g + rowB + 15) & ~(size_t)15, hi16);
+        if (e > b) total += (uint32_t)(e - b);
+    }
+    for (int ii = 0; ii < nact; ++ii) {                  // partial lines at the edges of the buffer (at most two rows)
+        const size_t g = g0 + ii * gstep;
+        const size_t ga = g & ~(size_t)15;
+        const size_t b = max(ga, lo16), e = min((g + rowB + 15) & ~(size_t)15, hi16);
+        if (b <= g && e >= g + rowB) continue;                               // the usual case: all of it by TMA
+        unsigned char *slot = raw + (size_t)ii * p.rawStride;               // slot + (address - ga) holds that byte
+        const size_t head_end = e > b ? min(b, g + rowB) : g + rowB;         // [g, head_end) and [tail_begin, g + rowB)
+        const size_t tail_begin = e > b ? max(e, g) : g + rowB;
+        for (size_t a = g; a < head_end; a += 2)
+            *reinterpret_cast<uint16_t *>(slot + (a - ga)) = *reinterpret_cast<const uint16_t *>(a);
+        for (size_t a = tail_begin; a < g + rowB; a += 2)
+            *reinterpret_cast<uint16_t *>(slot + (a - ga)) = *reinterpret_cast<const uint16_t *>(a);
     }
     mbar_expect_tx(bar, total);
     for (int ii = 0; ii < nact; ++ii) {
         const size_t g = g0 + ii * gstep;
-        const size_t src = g & ~(size_t)15;
-        tma_bulk_g2s(raw + (size_t)ii * p.rawStride, reinterpret_cast<const void *>(src),
-                     (uint32_t)(((g + rowB + 15) & ~(size_t)15) - src), bar);
+        const size_t b = max(g & ~(size_t)15, lo16), e = min((g + rowB + 15) & ~(size_t)15, hi16);
+        if (e > b)
+            tma_bulk_g2s(raw + (size_t)ii * p.rawStride + (b - (g & ~(size_t)15)), reinterpret_cast<const void *>(b),
+                         (uint32_t)(e - b), bar);
     }
 }
 
@@ -339,6 +360,7 @@ static PxpPlan plan_refocus_pxp(const PxPlan &px, int M, int S, int T, int N, in
     pl.a.rawStride = rawStride;
     pl.a.rawOffset = (int)rawOffset;
     pl.a.ntiles = c.nrows * S;
+    pl.a.vpBytes = (size_t)M * M * S * T * 6;
     pl.clamp = px.clamp;
     pl.exact24 = px.exact24;
     pl.ok = true;

@@ -36,6 +36,16 @@ class LfpCropper(LfpMicroLenses):
 
     @property
     def lfp_img_align(self):
+        if self.new_lfp_img is None and self._lfp_img_align is not None:
+            # main() did not run or had nothing to do (requested size above the aligned one): the reference hands out
+            # the zero image it pre-allocated in its constructor (lfp_cropper.py:37-43,65-66)
+            src = self._lfp_img_align
+            p = int(src.shape[-1]) if len(src.shape) == 3 else 1
+            shp = (int(self._size_pitch * self._LENS_Y_MAX), int(self._size_pitch * self._LENS_X_MAX), p)
+            if hasattr(src, 'is_cuda'):
+                import torch
+                return torch.zeros(shp, dtype=src.dtype, device=src.device)
+            return np.zeros(shp, dtype=src.dtype)
         if self.new_lfp_img is None:
             return None
         return self.new_lfp_img.clone() if hasattr(self.new_lfp_img, 'is_cuda') else np.array(self.new_lfp_img)

@@ -33,7 +33,7 @@ class LfpExtractor(object):
         obj.main()
         self._lfp_img_align = obj.lfp_img_align
         del obj
-        if self.cfg.params[self.cfg.opt_view] or self.cfg.params[self.cfg.opt_refo]:
+        if self.cfg.params[self.cfg.opt_view]:                     # lfp_extractor/top_level.py:68
             obj = LfpRearranger(self._lfp_img_align, cfg=self.cfg, sta=self.sta)
             obj.main()
             self.vp_img_linear = obj.vp_img_arr

@@ -277,8 +277,17 @@ def device_plan(S, T, M, a_list, view_zeroed, device):
     return plan
 
 
-def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None):
-    """Device evaluation: vp (M,M,S,T,3) CUDA tensor (uint16 / uint8 / float32) -> (N,S,T,3) float32 stack."""
+def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=None, coef=None, n_range=None):
+    """Device evaluation: vp (M,M,S,T,3) CUDA tensor (uint16 / uint8 / float32) -> (N,S,T,3) float32 stack.
+
+    out    : optional (N,S,T,3) float32 destination (e.g. this rank's block of a larger stack)
+    fanout : optional list of (address of the first slice, address of the min/max keys or None) - the finished slices
+             are stored into every listed buffer by the kernel that produces them (slice-sharded stacks: the peers'
+             stacks through peer-mapped pointers, see parallel.PeerStack); `out` / `mm` are then ignored
+    coef   : optional B-spline coefficients of the light field from an earlier call (`prefilter`)
+    n_range: (lo, hi) - evaluate only slices lo..hi-1 of `a_list` / `plan` (a rank's block of a sharded stack; the
+             operator tables are those of the whole range, so a block equals the same rows of the unsharded stack bit
+             for bit); `out` / `fanout` then address the first slice of the block"""
     import ctypes as C
     import torch
     from .. import _native as nat
@@ -288,28 +297,57 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None):
     if plan is None:
         plan = device_plan(S, T, M, a_list, view_zeroed, vp.device)
     dev = vp.device
-    N = plan.N
+    n_lo, n_hi = (0, plan.N) if n_range is None else (int(n_range[0]), int(n_range[1]))
+    if not 0 <= n_lo <= n_hi <= plan.N:
+        raise ValueError("n_range outside the plan")
+    N = n_hi - n_lo
     L, p, st = nat.lib(), ops._ptr, ops._stream()
-    coef = torch.empty((M, M, S, T, Cn), dtype=torch.float32, device=dev)     # B-spline coefficients of every view
-    tmp = torch.empty((M, M, S, T, Cn), dtype=torch.float32, device=dev)
+    if N == 0:
+        return out if out is not None else torch.empty((0, S, T, Cn), dtype=torch.float32, device=dev)
+    if coef is None:
+        coef = prefilter(vp, plan)
+    if fanout is None:
+        if out is None:
+            out = torch.empty((N, S, T, Cn), dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != (N, S, T, Cn) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 (N, S, T, C) tensor")
+        fanout = [(out.data_ptr(), mm.data_ptr() if mm is not None else None)]
+    if not 1 <= len(fanout) <= nat.PCB_MAX_PEERS:
+        raise ValueError("1..%d fan-out destinations" % nat.PCB_MAX_PEERS)
+    hbuf = torch.empty((min(plan.batch, N), M, S, T, Cn), dtype=torch.float32, device=dev)
+    z_ptr = plan.z_host.ctypes.data_as(C.c_void_p)
+    for n0 in range(0, N, plan.batch):
+        nb = min(plan.batch, N - n0)
+        lo, hi = plan.window(n_lo + n0, nb)
+        dst = nat.Fanout()
+        dst.n = len(fanout)
+        for d, (o_ptr, m_ptr) in enumerate(fanout):
+            dst.out[d] = int(o_ptr) + n0 * S * T * Cn * 4
+            dst.mm[d] = m_ptr if m_ptr else None
+        nat.check(L.pcb_refocus_refi_fanout(p(coef), M, S, T, Cn, nb,
+                                            p(plan.dy_v), p(plan.dy_f), plan.Kgy, p(plan.dx_v), p(plan.dx_f), plan.Kx,
+                                            C.c_void_p(plan.iy_d.data_ptr() + (n_lo + n0) * M * 4),
+                                            C.c_void_p(plan.ix_d.data_ptr() + (n_lo + n0) * M * 4),
+                                            lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), z_ptr,
+                                            p(plan.z_dev), p(hbuf), C.byref(dst), st))
+    return out
+
+
+def prefilter(vp, plan):
+    """B-spline coefficients of every unmasked view, float32 (M,M,S,T,3): the shift-independent half of the refinement,
+    done once per light field."""
+    import ctypes as C
+    import torch
+    from .. import _native as nat
+    from .. import ops
+    M, M2, S, T, Cn = vp.shape
+    L, p, st = nat.lib(), ops._ptr, ops._stream()
+    coef = torch.empty((M, M, S, T, Cn), dtype=torch.float32, device=vp.device)
+    tmp = torch.empty((M, M, S, T, Cn), dtype=torch.float32, device=vp.device)
     (hx, cx, xlo, xhi), (hy, cy, ylo, yhi) = plan.tx, plan.ty
     hptr = lambda h: h.ctypes.data_as(C.c_void_p) if h is not None else C.c_void_p(0)
     nat.check(L.pcb_refi_prefilter_toeplitz(p(vp), ops._pcb_dtype(vp), M, S, T, Cn, p(plan.py_v), p(plan.py_f), plan.Kpy,
                                             p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp), p(coef),
                                             hptr(hx), 0 if hx is None else int(hx.size), cx, xlo, xhi,
                                             hptr(hy), 0 if hy is None else int(hy.size), cy, ylo, yhi, st))
-    del tmp
-    out = torch.empty((N, S, T, Cn), dtype=torch.float32, device=dev)
-    hbuf = torch.empty((plan.batch, M, S, T, Cn), dtype=torch.float32, device=dev)
-    z_ptr = plan.z_host.ctypes.data_as(C.c_void_p)
-    for n0 in range(0, N, plan.batch):
-        nb = min(plan.batch, N - n0)
-        lo, hi = plan.window(n0, nb)
-        nat.check(L.pcb_refocus_refi(p(coef), M, S, T, Cn, nb,
-                                     p(plan.dy_v), p(plan.dy_f), plan.Kgy, p(plan.dx_v), p(plan.dx_f), plan.Kx,
-                                     C.c_void_p(plan.iy_d.data_ptr() + n0 * M * 4),
-                                     C.c_void_p(plan.ix_d.data_ptr() + n0 * M * 4),
-                                     lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), z_ptr,
-                                     p(plan.z_dev), p(hbuf), C.c_void_p(out.data_ptr() + n0 * S * T * Cn * 4),
-                                     p(mm) if mm is not None else C.c_void_p(0), st))
-    return out
+    return coef

@@ -3,15 +3,29 @@
 The path shards in two natural ways:
 
 * exposures  - independent raw images go to different ranks; no data-path collective at all;
-* slices     - the refocus parameters `a` of ONE light field are split over the ranks; every rank holds the
-               4-D light field, computes its share of the stack, and the finished slices are exchanged with a
-               single all-gather (NCCL over NVLink on GPUs, gloo in the CPU tests).  The contrast bounds come
-               from slice index 0 (lfp_refocuser/top_level.py:69), so the rank that owns it broadcasts two
-               float64 values before anybody applies the contrast/sRGB epilogue.
+* slices     - the refocus parameters `a` of ONE light field are split over the ranks in contiguous blocks; every rank
+               holds the 4-D light field and computes its block of the LINEAR stack.  The exchange of the finished
+               slices is the only data-path communication; it comes in two forms:
 
-Everything in this file is host logic on top of torch.distributed; it runs unchanged on the gloo backend with
-CPU tensors, which is how tests/test_dist_gloo.py covers it.
+               transport='p2p'   (the product, NVLink / NVSwitch): every rank owns a peer-mapped stack buffer
+                                 (`PeerStack`); the kernel that finishes a slice stores it into the stack of EVERY rank
+                                 (pcb_refocus_refi_fanout: compute and exchange in one kernel, the stores overlap the
+                                 arithmetic of the tiles still running), followed by one 1-element all-reduce as the
+                                 "all writes have landed" barrier;
+               transport='nccl'  (baseline; also what the gloo CPU tests drive): one `all_gather_into_tensor` of the
+                                 blocks.
+
+               The colour management of LfpRefocuser (lfp_refocuser/top_level.py:68-70) needs the percentile bounds of
+               slice 0 and, for Normalizer's falsy-bound fallback, the min / max of the whole stack.  Both are cheap
+               (0.1 ms for a 60-slice stack) next to a collective's latency, so every rank derives them itself from
+               the gathered linear stack (`finish_stack`) instead of exchanging them: no broadcast, no all-reduce.
+
+`local_block` / `finish_stack` are the per-rank halves without any communication; tests/test_sharded_gpu.py runs them
+for several world sizes on one GPU and compares with the unsharded stack.  The host logic (`shard_bounds`,
+`gather_slices`) runs unchanged on the gloo backend with CPU tensors (tests/test_dist_gloo.py).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -31,7 +45,7 @@ def shard_exposures(n, rank, world):
 
 def shard_slices(a_list, rank, world):
     """(indices, values) of the refocus parameters this rank computes (contiguous block of the stack, so the
-    all-gather reassembles the stack in order)."""
+    exchange reassembles the stack in order)."""
     a_list = list(a_list)
     lo, hi = shard_bounds(len(a_list), rank, world)
     return list(range(lo, hi)), a_list[lo:hi]
@@ -47,7 +61,8 @@ def owner_of(index, n, world):
 
 
 def broadcast_bounds(lohi, src, group=None):
-    """Share the two contrast bounds (float64 tensor of 2) computed on the owner of slice 0."""
+    """Share the two contrast bounds (float64 tensor of 2) computed on the owner of slice 0 (used by callers that
+    post-process before the exchange; `sharded_refocus_stack` does not need it)."""
     dist.broadcast(lohi, src=src, group=group)
     return lohi
 
@@ -76,42 +91,139 @@ def gather_slices(local, n_total, group=None):
     return torch.cat(parts, dim=0)
 
 
-def sharded_refocus_stack(vp, a_list, group=None, postprocess=True, refi=False, view_zeroed=None):
-    """Slice-sharded LfpRefocuser.shift_and_sum on device tensors: every rank passes the same light field
-    `vp` (M,M,S,T,3) and gets the full finished stack back.  One all-gather; two tiny broadcasts.
-    refi=True: `a_list` are the up-sampled-pixel parameters of the refinement path (range(M*r0, M*r1));
-    each rank prefilters the light field itself (shift independent, ~3 ms) and evaluates its own slices."""
+# ----------------------------------------------------------------------------------------------------------
+# per-rank halves (no communication)
+# ----------------------------------------------------------------------------------------------------------
+def local_block(vp, a_list, rank, world, refi=False, view_zeroed=None, out=None, fanout=None, coef=None):
+    """This rank's contiguous block of the LINEAR stack of light field `vp` (M,M,S,T,3): float32 (n_local,S,T,3).
+
+    out    : optional destination for the block (e.g. `stack[lo:hi]` of a full-size stack buffer)
+    fanout : refinement path only - [(address of slice `lo` in a destination stack, None), ...]: the kernel stores
+             every finished slice into all of them (see PeerStack.fanout)."""
     from . import ops
+    a_list = list(a_list)
+    lo, hi = shard_bounds(len(a_list), rank, world)
+    S, T, Cn = (int(v) for v in vp.shape[2:])
+    if hi == lo:
+        return torch.empty((0, S, T, Cn), dtype=torch.float32, device=vp.device)
+    if refi:
+        from .lfp_refocuser.refinement import device_plan, refocus_refi
+        mask = ops.aperture_mask(vp.shape[0]) if view_zeroed is None else view_zeroed
+        # the operator tables of the WHOLE range: a block is then bit-identical to the same slices of the unsharded stack
+        plan = device_plan(S, T, int(vp.shape[0]), a_list, mask, vp.device)
+        return refocus_refi(vp, a_list, mask, plan=plan, out=out, fanout=fanout, coef=coef, n_range=(lo, hi))
+    if fanout is not None:
+        raise NotImplementedError("the fan-out epilogue exists for the refinement path (BASELINE configs[3]); the "
+                                  "integer stack uses transport='nccl'")
+    return ops.refocus_int(vp, a_list[lo:hi], view_zeroed=view_zeroed, out=out)
+
+
+def finish_stack(stack, postprocess=True, out=None):
+    """LfpRefocuser's colour management on the COMPLETE linear stack, done by every rank for itself: bounds from slice 0
+    (lfp_refocuser/top_level.py:69), min / max of the whole stack for Normalizer's fallback, contrast + sRGB."""
+    from . import ops
+    if not postprocess:
+        return stack
+    return ops.refocuser_postprocess(stack, out=out)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# peer-mapped stack buffers (transport='p2p')
+# ----------------------------------------------------------------------------------------------------------
+class _CudaArray(object):
+    """Minimal __cuda_array_interface__ carrier so that torch can alias memory this library allocated."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+        self._owner = owner
+
+
+class PeerStack(object):
+    """One (N, S, T, C) float32 stack per rank, each mapped into every other rank of the group (CUDA IPC over
+    NVLink / NVSwitch peer access).  `fanout(lo)` lists, for the kernel's epilogue, the address of slice `lo` in every
+    rank's stack; `local` is this rank's stack as a torch tensor.  Collective: every rank of the group must construct
+    (and `close`) it together."""
+
+    def __init__(self, shape, group=None):
+        from . import _native as nat
+        self._nat = nat
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.shape = tuple(int(v) for v in shape)
+        if self.world > nat.PCB_MAX_PEERS:
+            raise ValueError("at most %d ranks per peer group" % nat.PCB_MAX_PEERS)
+        self.nbytes = int(np.prod(self.shape)) * 4
+        L = nat.lib()
+        ptr = C.c_void_p()
+        nat.check(L.pcb_peer_alloc(self.nbytes, C.byref(ptr)))
+        self._own = ptr.value
+        handle = C.create_string_buffer(64)
+        nat.check(L.pcb_peer_export(C.c_void_p(self._own), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self._own)
+            else:
+                p = C.c_void_p()
+                nat.check(L.pcb_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+                self.ptrs.append(p.value)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.local = torch.as_tensor(_CudaArray(self._own, self.shape, "<f4", self), device=dev)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._closed = False
+
+    def fanout(self, first_slice):
+        off = int(first_slice) * int(np.prod(self.shape[1:])) * 4
+        return [(p + off, None) for p in self.ptrs]
+
+    def barrier(self):
+        """Stream-ordered: returns at once on the host; the work queued after it on the current stream starts when every
+        rank's preceding kernels (and with them their peer stores) have completed."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)          # nobody unmaps while a peer may still be writing
+        L = self._nat.lib()
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                L.pcb_peer_close(C.c_void_p(p))
+        dist.barrier(group=self.group)
+        self.local = None
+        L.pcb_peer_free(C.c_void_p(self._own))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the sharded stack
+# ----------------------------------------------------------------------------------------------------------
+def sharded_refocus_stack(vp, a_list, group=None, postprocess=True, refi=False, view_zeroed=None, transport='nccl',
+                          peer_stack=None, coef=None):
+    """Slice-sharded LfpRefocuser.shift_and_sum on device tensors: every rank passes the same light field `vp`
+    (M,M,S,T,3) and gets the full finished stack back.
+    refi=True: `a_list` are the up-sampled-pixel parameters of the refinement path (range(M*r0, M*r1)); each rank
+    prefilters the light field itself (shift independent) and evaluates its own slices.
+    transport='p2p' needs a `PeerStack` of the stack's shape (reusable across light fields) and refi=True."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     a_list = list(a_list)
-    _, mine = shard_slices(a_list, rank, world)
-    mm = ops.new_minmax()
-    if not mine:
-        local = torch.empty((0,) + tuple(vp.shape[2:]), dtype=torch.float32, device=vp.device)
-    elif refi:
-        from .lfp_refocuser.refinement import refocus_refi
-        mask = ops.aperture_mask(vp.shape[0]) if view_zeroed is None else view_zeroed
-        local = refocus_refi(vp, mine, mask, mm=mm)
+    n_total = len(a_list)
+    lo, hi = shard_bounds(n_total, rank, world)
+    if transport == 'p2p':
+        if peer_stack is None:
+            raise ValueError("transport='p2p' needs a PeerStack")
+        local_block(vp, a_list, rank, world, refi=refi, view_zeroed=view_zeroed, fanout=peer_stack.fanout(lo), coef=coef)
+        peer_stack.barrier()
+        full = peer_stack.local
+    elif transport == 'nccl':
+        local = local_block(vp, a_list, rank, world, refi=refi, view_zeroed=view_zeroed, coef=coef)
+        full = gather_slices(local, n_total, group)
     else:
-        local = ops.refocus_int(vp, mine, view_zeroed=view_zeroed, mm=mm)
-    if postprocess:
-        src = owner_of(0, len(a_list), world)
-        lohi = torch.empty(2, dtype=torch.float64, device=vp.device)
-        if rank == src:
-            ops.contrast_bounds(local[0], 0.005, 99.9, lohi=lohi)
-        broadcast_bounds(lohi, src, group)
-        # Normalizer's falsy-bound fallback needs the min/max of the WHOLE stack (misc/normalizer.py:40-41)
-        keys = mm.view(torch.int32).clone()
-        kmin = (keys[0:1].to(torch.int64) & 0xFFFFFFFF)
-        kmax = (keys[1:2].to(torch.int64) & 0xFFFFFFFF)
-        if not mine:
-            kmin.fill_(0xFFFFFFFF)
-            kmax.fill_(0)
-        dist.all_reduce(kmin, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(kmax, op=dist.ReduceOp.MAX, group=group)
-        both = torch.cat([kmin, kmax])
-        mm_all = torch.where(both >= 2 ** 31, both - 2 ** 32, both).to(torch.int32)
-        if mine:
-            local = ops.contrast_srgb(local, lohi, mm=mm_all)
-    return gather_slices(local, len(a_list), group)
+        raise ValueError("transport must be 'p2p' or 'nccl'")
+    return finish_stack(full, postprocess)

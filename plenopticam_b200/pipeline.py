@@ -6,6 +6,7 @@ image, the viewpoint array and the stack never leave the GPU unless asked for.  
 entry point (pinned H2D of the raw exposure in, D2H of the finished stack out).
 """
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -13,6 +14,21 @@ import torch
 from . import _native as nat
 from . import ops
 from .lfp_aligner.lfp_microlenses import build_tables
+
+
+def _on_own_device(method):
+    """Run a launch entry point with the executor's GPU as the current CUDA device, whatever the caller's current
+    device is: the kernels go to `ops._stream()` (the current stream of the CURRENT device) and the library sizes its
+    grids for the current device, so launching cuda:1's buffers while cuda:0 is current would queue them on the wrong
+    GPU's stream."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        dev = self.device if hasattr(self, "device") else self.pipe.device
+        if torch.cuda.current_device() == dev.index:
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return method(self, *args, **kwargs)
+    return wrapper
 
 
 class LightFieldPipeline(object):
@@ -27,6 +43,8 @@ class LightFieldPipeline(object):
     def __init__(self, centroids, raw_shape, raw_dtype, M, pat_type, ran_refo=(0, 2), flip=False,
                  postprocess=True, device=None, fuse_post=True, wht_img=None):
         self.device = ops.require_cuda() if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.M = int(M)
         self.flip = bool(flip)
         self.postprocess = bool(postprocess)
@@ -77,6 +95,7 @@ class LightFieldPipeline(object):
         self.n_active_views = int((~ops.aperture_mask(self.M)).sum())
 
     # -- stage launches (enqueue only) ---------------------------------------------------------------------
+    @_on_own_device
     def align(self, raw=None):
         raw = self.raw if raw is None else raw
         if self.wn is not None:
@@ -84,16 +103,19 @@ class LightFieldPipeline(object):
         ops.resample_u16(raw, self.tabs, flip=self.flip, out=self.aligned, mm=self.mm_align)
         return self.aligned
 
+    @_on_own_device
     def viewpoints(self):
         ops.viewpoints(self.aligned, self.M, out=self.vp)
         return self.vp
 
+    @_on_own_device
     def refocus(self):
         L, p, st = nat.lib(), ops._ptr, ops._stream()
         nat.check(L.pcb_minmax_reset(p(self.mm_stack), st))
         self.refocus_plan.launch(self.vp, self.stack, self.mm_stack)
         return self.stack
 
+    @_on_own_device
     def post_process(self, out=None):
         out = self.post if out is None else out
         L, p, st = nat.lib(), ops._ptr, ops._stream()
@@ -102,6 +124,7 @@ class LightFieldPipeline(object):
                                       p(out), st))
         return out
 
+    @_on_own_device
     def refocus_post(self, out=None):
         """Stack + colour management with the fused epilogue (the linear stack is not materialised); False when the
         library has no fused form for this light field."""
@@ -109,6 +132,7 @@ class LightFieldPipeline(object):
         nat.check(nat.lib().pcb_minmax_reset(ops._ptr(self.mm_stack), ops._stream()))
         return out if self.refocus_plan.launch_srgb(self.vp, out, self.mm_stack, self.lohi, self.scratch) else False
 
+    @_on_own_device
     def run_device(self, raw=None, out=None):
         """All stages on the current stream; returns the final device tensor (sRGB stack, or the linear
         stack if postprocess=False)."""
@@ -127,6 +151,7 @@ class LightFieldPipeline(object):
         return self.stack
 
     # -- host-buffer entry point -----------------------------------------------------------------------------
+    @_on_own_device
     def _staging(self):
         if self._pin_in is None:
             tdt = ops._NP2TORCH[self.raw_dtype]
@@ -139,6 +164,7 @@ class LightFieldPipeline(object):
         pin_in, _ = self._staging()
         return pin_in.view(torch.int16).numpy().view(np.uint16) if pin_in.dtype == torch.uint16 else pin_in.numpy()
 
+    @_on_own_device
     def run(self, raw_host=None):
         """raw exposure (numpy, host) -> finished stack (numpy view of a pinned buffer, valid until next run)."""
         pin_in, pin_out = self._staging()
@@ -221,6 +247,7 @@ class ExposureStream(object):
         t = self.pin_in[s]
         return t.view(torch.int16).numpy().view(np.uint16) if t.dtype == torch.uint16 else t.numpy()
 
+    @_on_own_device
     def submit(self, raw_pinned=None):
         """Enqueue one exposure (a pinned host tensor, or the slot's own pinned_input buffer); returns its index."""
         k, s = self.k, self.k % self.depth
@@ -246,6 +273,7 @@ class ExposureStream(object):
         self.k += 1
         return k
 
+    @_on_own_device
     def result(self, k):
         """Block until exposure k has arrived on the host; numpy view valid until slot k % depth is resubmitted."""
         if not (self.k - self.depth <= k < self.k):

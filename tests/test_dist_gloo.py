@@ -46,6 +46,10 @@ def _worker(rank, world, port, n_slices, ret):
         full = par.gather_slices(torch.from_numpy(np.ascontiguousarray(post, dtype=np.float32)), len(a_list))
         ref = onp.refocuser_postprocess(np.asarray([onp.refocus_int_slice(vp64, a, M) for a in a_list]))
         ok = full.shape == ref.shape and np.array_equal(full.numpy(), ref)
+        # round-2 flow of parallel.sharded_refocus_stack: exchange the LINEAR blocks, every rank post-processes the whole
+        # stack itself (bounds from slice 0, no broadcast / all-reduce)
+        lin = par.gather_slices(torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)), len(a_list))
+        ok = ok and np.array_equal(onp.refocuser_postprocess(lin.numpy()), ref)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -60,11 +60,18 @@ def test_refocus_int_closed_form_equals_literal_pad_add():
         assert np.array_equal(onp.refocus_int_slice(vp64, a, M), onp.refocus_int_slice_padadd(vp64, a, M))
 
 
-def test_refocus_refi_matches_reference():
-    g = golden("refocus_refi_u16")
-    st = onp.refocus_refi(g["vp"], tuple(int(v) for v in g["ran_refo"]), int(g["M"]))
+@pytest.mark.parametrize("name", ["refocus_refi_u16", "refocus_refi_m7_neg_u16"])
+def test_refocus_refi_matches_reference(name):
+    g = golden(name)
+    ran, M = tuple(int(v) for v in g["ran_refo"]), int(g["M"])
+    st = onp.refocus_refi(g["vp"], ran, M)
     assert st.shape == g["stack"].shape
     assert np.abs(st - g["stack"]).max() <= 1e-11 * np.abs(g["stack"]).max()
+    # a subset of the range evaluates the same slices
+    full = list(range(M * ran[0], M * ran[1]))
+    sub = [full[0], full[len(full) // 2], full[-1]]
+    st_sub = onp.refocus_refi(g["vp"], ran, M, a_list=sub)
+    assert np.array_equal(st_sub, st[[full.index(a) for a in sub]])
 
 
 def test_refocuser_postprocess_matches_reference():
