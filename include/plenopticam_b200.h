@@ -142,6 +142,20 @@ int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C,
                     const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host,
                     void *scratch, int64_t scratch_bytes,
                     float *out, pcb_minmax_t *mm /* nullable: fused min/max of the stack */, void *stream);
+/* pcb_refocus_int / pcb_refocus_int_srgb reading the ALIGNED micro-image array (S*Ma, T*Ma, 3) of LfpResampler instead
+ * of the 4-D light field: view (j, i) is the sub-grid [ck + j :: Ma, ck + i :: Ma], ck = (Ma - M) / 2, i.e.
+ * LfpCropper.crop_micro_image (lfp_extractor/lfp_cropper.py:58-62) and LfpRearranger.compose_viewpoints
+ * (lfp_extractor/lfp_rearranger.py:93-101) are folded into the staging of the refocus tiles (one bulk copy per aligned
+ * row).  Same results bit for bit.  PCB_ERR_UNSUPPORTED when the persistent packed-pixel kernel does not apply
+ * (then: pcb_viewpoints + pcb_refocus_int). */
+int pcb_refocus_int_aligned(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
+                            const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host,
+                            void *scratch, int64_t scratch_bytes, float *out, pcb_minmax_t *mm, void *stream);
+int pcb_refocus_int_srgb_aligned(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
+                                 const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host,
+                                 void *scratch, int64_t scratch_bytes, double q_lo, double q_hi,
+                                 float *ref_slice, double *lohi, void *pscratch, float *out, pcb_minmax_t *mm,
+                                 void *stream);
 int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C,
                            const int32_t *a_list_dev, int N, const uint8_t *view_zeroed_dev,
                            float *out, pcb_minmax_t *mm, void *stream);

@@ -131,6 +131,9 @@ _SIGNATURES = {
     "pcb_refocus_int_scratch_bytes": (_i64, [_i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pcb_refocus_int": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "pcb_refocus_int_srgb": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcb_refocus_int_aligned": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "pcb_refocus_int_srgb_aligned": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, C.c_double, C.c_double, _vp,
+                                          _vp, _vp, _vp, _vp, _vp]),
     "pcb_refocus_int_direct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refi_prefilter": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refi_prefilter_toeplitz": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp,

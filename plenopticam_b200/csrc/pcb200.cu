@@ -88,6 +88,7 @@ static int make_resample_args(ResampleArgs &a, const void *raw, int H, int W, in
     a.hexcol = pattern == PCB_HEX ? hexcol : nullptr;
     a.Xs = Xs; a.hex_odd = hex_odd ? 1 : 0; a.flip = flip ? 1 : 0;
     a.ncols = Xs * M * C;
+    a.KT = 0; a.cap_floats = 0; a.skip = 0;
     return PCB_OK;
 }
 
@@ -210,7 +211,7 @@ static int refocus_force_kernel() {   // A/B knob: PCB_REFOCUS_KERNEL=rows|direc
 }
 
 static RefocusPlan refocus_plan(int dtype, int M, int S, int T, int C, const int32_t *a_list_host, int N,
-                                const uint8_t *view_zeroed_host, const void *vp = nullptr) {
+                                const uint8_t *view_zeroed_host, const void *vp = nullptr, int Ma = 0) {
     RefocusPlan none;
     memset(&none, 0, sizeof(none));
     if (dtype != PCB_U16 || M > 16 || refocus_force_kernel() == 2) return none;
@@ -231,7 +232,7 @@ static RefocusPlan refocus_plan(int dtype, int M, int S, int T, int C, const int
     RefocusPlan pl = none;
     if (C == 3 && refocus_force_kernel() != 1) pl.px = plan_refocus_px(M, S, T, N, max_abs_a, max_act, tot_act, view_zeroed_host);
     if (pl.px.ok && vp != nullptr && refocus_force_kernel() != 3)
-        pl.pxp = plan_refocus_pxp(pl.px, M, S, T, N, max_abs_a, view_zeroed_host, vp);
+        pl.pxp = plan_refocus_pxp(pl.px, M, S, T, N, max_abs_a, view_zeroed_host, vp, Ma);
     if (!pl.px.ok) pl.rows = plan_refocus_rows(M, S, T, C, N, max_abs_a, max_act, tot_act);
     return pl;
 }
@@ -297,6 +298,46 @@ int pcb_refocus_int_srgb(const void *vp, int dtype, int M, int S, int T, int C, 
     post.q_lo = q_lo; post.q_hi = q_hi; post.ref_slice = ref_slice; post.lohi = lohi; post.pscratch = pscratch;
     return launch_refocus_pxp(pl.px, pl.pxp, (const uint16_t *)vp, a_list_host, view_zeroed_host, scratch, out, mm,
                               as_stream(stream), &post);
+}
+
+// The same two entry points reading the ALIGNED micro-image array instead of the 4-D light field: the viewpoint gather
+// (and LfpCropper's central crop when M < Ma) is folded into the staging of the refocus tiles, so a pipeline that only
+// wants the stack never materialises vp[j,i,s,t,c].  Offered by the persistent packed-pixel kernel only.
+static int refocus_aligned_common(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
+                                  const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host, void *scratch,
+                                  int64_t scratch_bytes, float *out, pcb_minmax_t *mm, const PxpFusedPost *post,
+                                  cudaStream_t st, const char *who) {
+    PCB_REQUIRE(aligned != nullptr && a_list_host != nullptr && view_zeroed_host != nullptr && out != nullptr &&
+                scratch != nullptr, "pointers");
+    PCB_REQUIRE(M > 0 && S > 0 && T > 0 && C > 0 && N > 0 && N <= 65535, "sizes");
+    PCB_REQUIRE(M % 2 == 1, "odd M (even M changes the slice shape, lfp_shiftandsum.py:123-124)");
+    PCB_REQUIRE(Ma >= M && (Ma - M) % 2 == 0, "aligned pitch >= M with an even crop margin (lfp_cropper.py:34)");
+    PCB_REQUIRE(scratch_bytes >= pcb_refocus_int_scratch_bytes(dtype, M, S, T, C, a_list_host, N, view_zeroed_host),
+                "scratch_bytes >= pcb_refocus_int_scratch_bytes(...)");
+    const RefocusPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host, aligned, Ma);
+    if (!pl.pxp.ok)
+        return fail(PCB_ERR_UNSUPPORTED, "%s: reading the aligned image directly exists for the packed-pixel kernel only "
+                    "(uint16 RGB, M <= 16, row <= 2048 px, tiles that fit one SM); run pcb_viewpoints first", who);
+    return launch_refocus_pxp(pl.px, pl.pxp, (const uint16_t *)aligned, a_list_host, view_zeroed_host, scratch, out, mm,
+                              st, post);
+}
+
+int pcb_refocus_int_aligned(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
+                            const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host, void *scratch,
+                            int64_t scratch_bytes, float *out, pcb_minmax_t *mm, void *stream) {
+    return refocus_aligned_common(aligned, dtype, Ma, M, S, T, C, a_list_host, N, view_zeroed_host, scratch,
+                                  scratch_bytes, out, mm, nullptr, as_stream(stream), __func__);
+}
+
+int pcb_refocus_int_srgb_aligned(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
+                                 const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host, void *scratch,
+                                 int64_t scratch_bytes, double q_lo, double q_hi, float *ref_slice, double *lohi,
+                                 void *pscratch, float *out, pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(ref_slice != nullptr && lohi != nullptr && pscratch != nullptr && mm != nullptr, "pointers");
+    PxpFusedPost post;
+    post.q_lo = q_lo; post.q_hi = q_hi; post.ref_slice = ref_slice; post.lohi = lohi; post.pscratch = pscratch;
+    return refocus_aligned_common(aligned, dtype, Ma, M, S, T, C, a_list_host, N, view_zeroed_host, scratch,
+                                  scratch_bytes, out, mm, &post, as_stream(stream), __func__);
 }
 
 // The direct (slice-stationary) form only; kept addressable for A/B measurements and as the general path.

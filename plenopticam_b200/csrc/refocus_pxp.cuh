@@ -46,6 +46,11 @@ struct PxpArgs {
     int ntiles;      // nrows * S
     int nsl, n0;
     size_t vpBytes;  // size of the light field in bytes: no access outside [vp, vp + vpBytes)
+    int Ma;          // 0: `vp` is the 4-D array vp[j,i,s,t,c];  > 0: `vp` is the ALIGNED micro-image array
+                     //    (S*Ma, T*Ma, 3) of pitch Ma and view (j,i) is its sub-grid [ck+j :: Ma, ck+i :: Ma] - the
+                     //    viewpoint gather (lfp_extractor/lfp_rearranger.py:101) and the central crop
+                     //    (lfp_cropper.py:58-62) happen while the tile is staged
+    int ck;          // crop margin (Ma - M) / 2
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,9 +106,12 @@ __device__ __forceinline__ void pxp_tile(const PxpArgs &p, const PxpCtl &ctl, in
 // fetched with plain 2-byte loads instead, so the kernel never touches a byte the caller does not own.
 __device__ __forceinline__ void pxp_issue_tile(const PxpArgs &p, const PxpCtl &ctl, unsigned char *raw, uint64_t *bar,
                                                int j, int r) {
-    const int nact = ctl.nact[j];
-    const size_t rowB = (size_t)p.T * 6;
-    const size_t g0 = (size_t)p.vp + (((size_t)j * p.M + ctl.first[j]) * p.S + r) * rowB;
+    // 4-D layout: one copy per active view row.  Aligned layout: ONE copy, the aligned row r*Ma + ck + j, which holds
+    // row r of all M views of view-row j interleaved at pixel pitch Ma.
+    const int nact = p.Ma ? 1 : (int)ctl.nact[j];
+    const size_t rowB = p.Ma ? (size_t)p.T * p.Ma * 6 : (size_t)p.T * 6;
+    const size_t g0 = p.Ma ? (size_t)p.vp + ((size_t)r * p.Ma + p.ck + j) * rowB
+                           : (size_t)p.vp + (((size_t)j * p.M + ctl.first[j]) * p.S + r) * rowB;
     const size_t gstep = (size_t)p.S * rowB;
     const size_t lo16 = ((size_t)p.vp + 15) & ~(size_t)15;                   // first / one-past-last whole line inside
     const size_t hi16 = ((size_t)p.vp + p.vpBytes) & ~(size_t)15;
@@ -142,16 +150,19 @@ __device__ __forceinline__ void pxp_convert_tile(const PxpArgs &p, const PxpCtl 
     const int nact = ctl.nact[j];
     const int c0 = p.M / 2;
     const size_t rowB = (size_t)p.T * 6;
+    const size_t arow = p.Ma ? (size_t)p.vp + ((size_t)r * p.Ma + p.ck + j) * ((size_t)p.T * p.Ma * 6) : 0;
+    const int pitch = p.Ma ? p.Ma * 6 : 6;                                   // bytes between pixels of one view
     for (int ii = 0; ii < nact; ++ii) {
         const int col = ctl.first[j] + ii;
         const size_t g = (size_t)p.vp + (((size_t)j * p.M + col) * p.S + r) * rowB;
-        const unsigned char *src = raw + (size_t)ii * p.rawStride + (g & 15);
+        const unsigned char *src = p.Ma ? raw + (arow & 15) + (size_t)(p.ck + col) * 6
+                                        : raw + (size_t)ii * p.rawStride + (g & 15);
         const int pad = min(abs(c0 - col) * ctl.maxa, p.T);
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(packed + ctl.cb[j * PX_MAXV + ii]) - pad;
         const int npx = p.W + 2 * pad;
         for (int idx = tid; idx < npx; idx += THREADS) {
             const int x = min(max(idx - pad, 0), p.T - 1);
-            const uint16_t *px = reinterpret_cast<const uint16_t *>(src + x * 6);
+            const uint16_t *px = reinterpret_cast<const uint16_t *>(src + (size_t)x * pitch);
             dst[idx] = pack_px(px[0], px[1], px[2]);
         }
     }
@@ -308,7 +319,7 @@ static int pxp_sm_count() { return sm_count(); }
 
 // Host-side planning (no device access).  `px` supplies the accumulator / edge-table geometry.
 static PxpPlan plan_refocus_pxp(const PxPlan &px, int M, int S, int T, int N, int max_abs_a,
-                                const uint8_t *view_zeroed_host, const void *vp) {
+                                const uint8_t *view_zeroed_host, const void *vp, int Ma = 0) {
     PxpPlan pl;
     memset(&pl, 0, sizeof(pl));
     pl.ok = false;
@@ -350,9 +361,10 @@ static PxpPlan plan_refocus_pxp(const PxPlan &px, int M, int S, int T, int N, in
         if (gsz > c.nrows) gsz = c.nrows;
         c.gsz = gsz;
     }
-    const int rawStride = (T * 6 + 30 + 15) & ~15;
+    const int rawStride = Ma ? ((T * Ma * 6 + 30 + 15) & ~15) : ((T * 6 + 30 + 15) & ~15);
     const size_t rawOffset = (max_packed + 127) & ~(size_t)127;
-    pl.smem = rawOffset + (size_t)max_nact * rawStride;
+    pl.smem = rawOffset + (size_t)(Ma ? 1 : max_nact) * rawStride;
+    if (Ma && (size_t)T * Ma * 6 + 32 >= (1u << 20)) return pl;             // one bulk copy per row: mbarrier tx-count
     if (pl.smem > 227 * 1024 - 64) return pl;
     pl.a.M = M; pl.a.S = S; pl.a.T = T; pl.a.N = N;
     pl.a.Tp = px.a.Tp;
@@ -360,7 +372,9 @@ static PxpPlan plan_refocus_pxp(const PxPlan &px, int M, int S, int T, int N, in
     pl.a.rawStride = rawStride;
     pl.a.rawOffset = (int)rawOffset;
     pl.a.ntiles = c.nrows * S;
-    pl.a.vpBytes = (size_t)M * M * S * T * 6;
+    pl.a.vpBytes = Ma ? (size_t)S * Ma * T * Ma * 6 : (size_t)M * M * S * T * 6;
+    pl.a.Ma = Ma;
+    pl.a.ck = Ma ? (Ma - M) / 2 : 0;
     pl.clamp = px.clamp;
     pl.exact24 = px.exact24;
     pl.ok = true;

@@ -28,6 +28,7 @@ struct ResampleArgs {
     int ncols;                    // Xs*M*C elements per aligned row
     int KT;                       // output lens columns per CTA
     int cap_floats;               // shared-memory tile capacity
+    int skip;                     // min/max pass of resample_col: tiles that cannot move the bounds are skipped
 };
 
 enum { RS_MINMAX = 0, RS_F32 = 1, RS_U16 = 2 };

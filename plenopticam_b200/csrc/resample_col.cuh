@@ -28,6 +28,7 @@ constexpr int RC_KT = 17;            // output lens columns per CTA: 17 * 15 * 3
 constexpr int RC_TS = 736;           // tile row stride in floats
 constexpr int RC_ROWS = 19;          // tile rows (M + 1 + scatter allowance for M = 15)
 constexpr int RC_MAX_SRC = 32;       // source lenses per CTA
+constexpr float RC_SKIP_EPS = 4e-6f; // >> the rounding of 8 products of 3 factors + 7 FMAs (~16 * 2^-24 = 1e-6)
 
 __device__ __forceinline__ float u16_to_float_magic(uint32_t v16) {      // v16 < 65536
     return __uint_as_float(0x4B000000u | v16) - 8388608.0f;
@@ -37,8 +38,11 @@ __device__ __forceinline__ float u16_to_float_magic(uint32_t v16) {      // v16 
 // column of raw element xmin*3: rows are copied from the 32-bit word that contains their first element, so when
 // every row starts on the same half of a word (W*3 even and a 4-byte aligned image) the copy is whole words:
 // one LDG.32, two PRMT + FADD conversions and one 8-byte STS per two samples, no per-sample guards.
+// TRACK: also fold every staged sample into (smn, smx) - the min/max pass uses them to skip tiles that cannot move the
+// global bounds.
+template <bool TRACK>
 __device__ __forceinline__ int rc_stage(const uint16_t *__restrict__ raw, size_t total_elems, int W, float *tile,
-                                        int ymin, int xmin, int R, int Wt) {
+                                        int ymin, int xmin, int R, int Wt, float &smn, float &smx) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t gE0 = ((size_t)ymin * W + xmin) * 3;
     const bool words = ((reinterpret_cast<uintptr_t>(raw) & 3) == 0) && ((W * 3) & 1) == 0;
@@ -61,14 +65,21 @@ __device__ __forceinline__ int rc_stage(const uint16_t *__restrict__ raw, size_t
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int m = base + u * 32;
-                    if (m < nwr)
-                        dst[m] = make_float2(__uint_as_float(__byte_perm(v[u], 0x4B000000u, 0x7610)) - 8388608.0f,
-                                             __uint_as_float(__byte_perm(v[u], 0x4B000000u, 0x7632)) - 8388608.0f);
+                    if (m < nwr) {
+                        const float2 f2 = make_float2(__uint_as_float(__byte_perm(v[u], 0x4B000000u, 0x7610)) - 8388608.0f,
+                                                      __uint_as_float(__byte_perm(v[u], 0x4B000000u, 0x7632)) - 8388608.0f);
+                        dst[m] = f2;
+                        if (TRACK) {
+                            smn = fminf(smn, fminf(f2.x, f2.y));
+                            smx = fmaxf(smx, fmaxf(f2.x, f2.y));
+                        }
+                    }
                 }
             }
             if (nwr < nw && lane == 0) {                                  // last word of the image: its low half only
                 const float f = (float)__ldg(raw + gE + 2 * (size_t)nwr);
                 dst[nwr] = make_float2(f, f);
+                if (TRACK) { smn = fminf(smn, f); smx = fmaxf(smx, f); }
             }
         }
         return g;
@@ -76,7 +87,11 @@ __device__ __forceinline__ int rc_stage(const uint16_t *__restrict__ raw, size_t
     for (int rr = warp; rr < R; rr += RC_THREADS / 32) {
         const uint16_t *src = raw + gE0 + (size_t)rr * W * 3;
         float *dst = tile + rr * RC_TS;
-        for (int e = lane; e < Wt; e += 32) dst[e] = (float)__ldg(src + e);
+        for (int e = lane; e < Wt; e += 32) {
+            const float f = (float)__ldg(src + e);
+            dst[e] = f;
+            if (TRACK) { smn = fminf(smn, f); smx = fmaxf(smx, f); }
+        }
     }
     return 0;
 }
@@ -96,6 +111,8 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
     __shared__ pcb_lens_t s_lens[RC_MAX_SRC];
     __shared__ int s_box[4];      // ymin, ymax, xmin, xmax over the valid source lenses (oy / ox)
     __shared__ int s_src[2];      // first / last source lens column
+    __shared__ int s_smm[2];      // min / max of the staged samples (bit patterns of non-negative floats order like ints)
+    __shared__ int s_ninv;        // invalid source lenses of this CTA
 
     const int M = MT ? MT : p.M;
     const int ly = blockIdx.y;
@@ -108,6 +125,16 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
     out.f32 = out_f32; out.u16 = out_u16;
     out.qz.init(0.f, 0.f);
     if (MODE == RS_U16) out.qz.init(key_to_float(mm_ro->kmin), key_to_float(mm_ro->kmax));
+    // Min/max pass: the running global bounds as they are NOW (stale is fine: they only ever widen).  A tile whose staged
+    // raw samples lie strictly inside them cannot move them - every output is a convex combination of staged samples,
+    // up to float rounding (a few 2^-24, covered by RC_SKIP_EPS) - so its interpolation is skipped altogether.  The
+    // final min / max are exactly those of the full computation.  (NaN from freshly reset keys compares false: no skip.)
+    float g_mn = 0.f, g_mx = 0.f;
+    const bool may_skip = MODE == RS_MINMAX && mm_rw != nullptr && p.skip;
+    if (may_skip) {
+        g_mn = key_to_float(*reinterpret_cast<volatile uint32_t *>(&mm_rw->kmin));
+        g_mx = key_to_float(*reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax));
+    }
 
     if (tid == 0) {
         int xa = k0, xb = k0 + kn - 1;
@@ -119,6 +146,8 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
         s_src[0] = xa;
         s_src[1] = xb;
         s_box[0] = INT32_MAX; s_box[1] = INT32_MIN; s_box[2] = INT32_MAX; s_box[3] = INT32_MIN;
+        s_smm[0] = 0x7f800000; s_smm[1] = 0;
+        s_ninv = 0;
     }
     __syncthreads();
     const int xa = s_src[0];
@@ -130,6 +159,8 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
         if (L.oy != PCB_LENS_INVALID) {
             atomicMin(&s_box[0], L.oy); atomicMax(&s_box[1], L.oy);
             atomicMin(&s_box[2], L.ox); atomicMax(&s_box[3], L.ox);
+        } else {
+            atomicAdd(&s_ninv, 1);
         }
     }
     __syncthreads();
@@ -140,8 +171,27 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
     const bool use_tile = lens_in_smem && any_valid && R <= RC_ROWS && Wt + 2 <= RC_TS;
     const uint16_t *raw = reinterpret_cast<const uint16_t *>(p.raw);
     int shift = 0;
-    if (use_tile) shift = rc_stage(raw, (size_t)p.H * p.W * 3, p.W, tile, ymin, xmin, R, Wt);
+    float smn = INFINITY, smx = 0.f;
+    if (use_tile) {
+        if (may_skip) shift = rc_stage<true>(raw, (size_t)p.H * p.W * 3, p.W, tile, ymin, xmin, R, Wt, smn, smx);
+        else shift = rc_stage<false>(raw, (size_t)p.H * p.W * 3, p.W, tile, ymin, xmin, R, Wt, smn, smx);
+    }
+    if (may_skip && use_tile) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            smn = fminf(smn, __shfl_xor_sync(0xffffffffu, smn, o));
+            smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(&s_smm[0], __float_as_int(smn));
+            atomicMax(&s_smm[1], __float_as_int(smx));
+        }
+    }
     __syncthreads();
+    if (may_skip && use_tile && s_ninv == 0) {
+        const float tmn = __int_as_float(s_smm[0]), tmx = __int_as_float(s_smm[1]);
+        if (tmn * (1.f - RC_SKIP_EPS) > g_mn && tmx * (1.f + RC_SKIP_EPS) < g_mx) return;      // uniform over the CTA
+    }
 
     float mn = INFINITY, mx = -INFINITY;
     const int ncols_tile = kn * M * 3;
@@ -229,8 +279,10 @@ static bool resample_col_applies(const ResampleArgs &a, int raw_dtype) {
 }
 
 template <int MODE>
-static int launch_resample_col(const ResampleArgs &a, float *out_f32, uint16_t *out_u16, pcb_minmax_t *mm_rw,
+static int launch_resample_col(const ResampleArgs &a_in, float *out_f32, uint16_t *out_u16, pcb_minmax_t *mm_rw,
                                const pcb_minmax_t *mm_ro, cudaStream_t st) {
+    ResampleArgs a = a_in;
+    a.skip = (getenv("PCB_RESAMPLE_NOSKIP") && atoi(getenv("PCB_RESAMPLE_NOSKIP"))) ? 0 : 1;
     const size_t smem = (size_t)RC_ROWS * RC_TS * sizeof(float);
     dim3 block(RC_THREADS), grid((a.Xs + RC_KT - 1) / RC_KT, a.LY);
     if (a.M == 15) {

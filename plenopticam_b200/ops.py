@@ -252,10 +252,15 @@ def aperture_mask(M):
 
 
 class RefocusPlan(object):
-    """Host control arrays + device scratch for pcb_refocus_int; reusable across exposures of one camera."""
+    """Host control arrays + device scratch for pcb_refocus_int; reusable across exposures of one camera.
 
-    def __init__(self, vp_shape, vp_dtype, a_list, view_zeroed, device):
+    aligned_pitch: None - `launch*` take the 4-D light field vp[j,i,s,t,c];  Ma (>= M) - they take LfpResampler's aligned
+    micro-image array (S*Ma, T*Ma, 3) and the viewpoint gather / central crop is folded into the kernel's staging
+    (pcb_refocus_int_aligned); NotImplementedError when the library has no such form for the configuration."""
+
+    def __init__(self, vp_shape, vp_dtype, a_list, view_zeroed, device, aligned_pitch=None):
         M, M2, S, T, Cn = vp_shape
+        self.Ma = None if aligned_pitch is None else int(aligned_pitch)
         if M != M2:
             raise ValueError("square angular resolution expected")
         self.shape = (int(M), int(S), int(T), int(Cn))
@@ -278,9 +283,14 @@ class RefocusPlan(object):
 
     def launch(self, vp, out, mm=None):
         M, S, T, Cn = self.shape
+        mmp = _ptr(mm) if mm is not None else C.c_void_p(0)
+        if self.Ma is not None:
+            nat.check(nat.lib().pcb_refocus_int_aligned(_ptr(vp), self.dtype, self.Ma, M, S, T, Cn, self.a_ptr, self.N,
+                                                        self.z_ptr, _ptr(self.scratch), self.scratch.numel(), _ptr(out),
+                                                        mmp, _stream()))
+            return out
         nat.check(nat.lib().pcb_refocus_int(_ptr(vp), self.dtype, M, S, T, Cn, self.a_ptr, self.N, self.z_ptr,
-                                            _ptr(self.scratch), self.scratch.numel(), _ptr(out),
-                                            _ptr(mm) if mm is not None else C.c_void_p(0), _stream()))
+                                            _ptr(self.scratch), self.scratch.numel(), _ptr(out), mmp, _stream()))
         return out
 
 
@@ -293,10 +303,16 @@ def _refocus_plan_launch_srgb(self, vp, out, mm, lohi, pscratch, q_lo=0.005, q_h
     if self.ref_slice is None:
         self.ref_slice = torch.empty((S, T, Cn), dtype=torch.float32, device=self.scratch.device)
     try:
-        nat.check(nat.lib().pcb_refocus_int_srgb(_ptr(vp), self.dtype, M, S, T, Cn, self.a_ptr, self.N, self.z_ptr,
-                                                 _ptr(self.scratch), self.scratch.numel(), q_lo, q_hi,
-                                                 _ptr(self.ref_slice), _ptr(lohi), _ptr(pscratch), _ptr(out), _ptr(mm),
-                                                 _stream()))
+        if self.Ma is not None:
+            nat.check(nat.lib().pcb_refocus_int_srgb_aligned(_ptr(vp), self.dtype, self.Ma, M, S, T, Cn, self.a_ptr,
+                                                             self.N, self.z_ptr, _ptr(self.scratch), self.scratch.numel(),
+                                                             q_lo, q_hi, _ptr(self.ref_slice), _ptr(lohi), _ptr(pscratch),
+                                                             _ptr(out), _ptr(mm), _stream()))
+        else:
+            nat.check(nat.lib().pcb_refocus_int_srgb(_ptr(vp), self.dtype, M, S, T, Cn, self.a_ptr, self.N, self.z_ptr,
+                                                     _ptr(self.scratch), self.scratch.numel(), q_lo, q_hi,
+                                                     _ptr(self.ref_slice), _ptr(lohi), _ptr(pscratch), _ptr(out),
+                                                     _ptr(mm), _stream()))
     except NotImplementedError:
         self.fused = False
         return False
@@ -317,6 +333,22 @@ def refocus_int(vp, a_list, view_zeroed=None, out=None, mm=None, plan=None):
     if out is None:
         out = torch.empty((plan.N, S, T, Cn), dtype=torch.float32, device=vp.device)
     return plan.launch(vp, out, mm)
+
+
+def refocus_int_from_aligned(aligned, M_aligned, a_list, M=None, view_zeroed=None, out=None, mm=None, plan=None):
+    """refocus_int(viewpoints(aligned, M_aligned, M), a_list) without materialising the 4-D light field: the gather and
+    the central crop happen inside the refocus kernel's staging.  Raises NotImplementedError when the library has no
+    such form for the configuration (then gather first)."""
+    _chk_dev(aligned)
+    Ma = int(M_aligned)
+    M = Ma if M is None else int(M)
+    rows, cols, Cn = (int(v) for v in aligned.shape)
+    S, T = rows // Ma, cols // Ma
+    if plan is None:
+        plan = RefocusPlan((M, M, S, T, Cn), aligned.dtype, a_list, view_zeroed, aligned.device, aligned_pitch=Ma)
+    if out is None:
+        out = torch.empty((plan.N, S, T, Cn), dtype=torch.float32, device=aligned.device)
+    return plan.launch(aligned, out, mm)
 
 
 def refocus_int_direct(vp, a_list, view_zeroed=None, out=None, mm=None):

@@ -41,7 +41,7 @@ class LightFieldPipeline(object):
     """
 
     def __init__(self, centroids, raw_shape, raw_dtype, M, pat_type, ran_refo=(0, 2), flip=False,
-                 postprocess=True, device=None, fuse_post=True, wht_img=None):
+                 postprocess=True, device=None, fuse_post=True, wht_img=None, gather_fused=True):
         self.device = ops.require_cuda() if device is None else torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -73,6 +73,12 @@ class LightFieldPipeline(object):
             self.mm_stack = torch.empty(2, dtype=torch.int32, device=dev)
             self.refocus_plan = ops.RefocusPlan(tuple(self.vp.shape), self.vp.dtype, self.a_list,
                                                 ops.aperture_mask(self.M), dev)
+            # the same stack straight from the aligned image: the viewpoint gather rides in the refocus kernel's TMA
+            # staging and the 4-D array is materialised only for callers that ask for it (`viewpoints()`)
+            self.refocus_plan_al = ops.RefocusPlan(tuple(self.vp.shape), self.vp.dtype, self.a_list,
+                                                   ops.aperture_mask(self.M), dev, aligned_pitch=self.M)
+            self.refocus_plan_al.scratch = self.refocus_plan.scratch          # same geometry: share the accumulators
+            self.gather_fused = gather_fused
             self.lohi = torch.empty(2, dtype=torch.float64, device=dev)
             self.scratch = torch.empty(int(nat.lib().pcb_percentile_scratch_bytes()), dtype=torch.uint8, device=dev)
             self._q_lo = (C.c_double * 1)(0.005)
@@ -133,10 +139,34 @@ class LightFieldPipeline(object):
         return out if self.refocus_plan.launch_srgb(self.vp, out, self.mm_stack, self.lohi, self.scratch) else False
 
     @_on_own_device
+    def _refocus_from_aligned(self, out=None):
+        """Stack (+ colour management) read straight from `self.aligned`; False when the library cannot."""
+        pl = self.refocus_plan_al
+        nat.check(nat.lib().pcb_minmax_reset(ops._ptr(self.mm_stack), ops._stream()))
+        try:
+            if self.postprocess and self.fuse_post:
+                out = self.post if out is None else out
+                return out if pl.launch_srgb(self.aligned, out, self.mm_stack, self.lohi, self.scratch) else False
+            pl.launch(self.aligned, self.stack, self.mm_stack)
+        except NotImplementedError:
+            return False
+        if self.postprocess:
+            return self.post_process(out)
+        if out is not None:
+            out.copy_(self.stack)
+            return out
+        return self.stack
+
+    @_on_own_device
     def run_device(self, raw=None, out=None):
         """All stages on the current stream; returns the final device tensor (sRGB stack, or the linear
         stack if postprocess=False)."""
         self.align(raw)
+        if self.gather_fused:
+            res = self._refocus_from_aligned(out)
+            if res is not False:
+                return res
+            self.gather_fused = False             # no such kernel form for this camera: gather explicitly from now on
         self.viewpoints()
         if self.postprocess and self.fuse_post:
             res = self.refocus_post(out)

@@ -1,0 +1,107 @@
+"""Round-2 kernel forms, each checked against the form it replaces (which is itself pinned to the oracle / goldens):
+the refocus kernel reading the aligned image directly (viewpoint gather + central crop folded into its staging) and
+the min/max pass of the resampler that skips tiles which cannot move the global bounds."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+
+def _aligned(cuda, Ma, S, T, seed):
+    from plenopticam_b200 import ops
+    rng = np.random.default_rng(seed)
+    return ops.to_device(rng.integers(0, 65536, size=(S * Ma, T * Ma, 3), dtype=np.uint16))
+
+
+@pytest.mark.parametrize("Ma,M,S,T,ran", [(7, 7, 12, 14, (-3, 4)), (9, 7, 17, 23, (-5, 3)), (15, 15, 20, 31, (-32, 32)),
+                                          (15, 11, 9, 40, (-2, 9)), (5, 5, 33, 300, (-70, 71))])
+def test_refocus_from_aligned_equals_gather_then_refocus(cuda, Ma, M, S, T, ran):
+    import torch
+    from plenopticam_b200 import ops
+    al = _aligned(cuda, Ma, S, T, Ma * 100 + M)
+    a_list = list(range(*ran))
+    vp = ops.viewpoints(al, Ma, M)                       # LfpCropper + LfpRearranger
+    ref = ops.refocus_int(vp, a_list)
+    mm_ref = ops.new_minmax()
+    ops.refocus_int(vp, a_list, mm=mm_ref)
+    mm = ops.new_minmax()
+    got = ops.refocus_int_from_aligned(al, Ma, a_list, M=M, mm=mm)
+    assert torch.equal(got, ref)
+    assert ops.minmax_values(mm) == ops.minmax_values(mm_ref)
+    # and against the oracle on one slice
+    vp64 = onp._apply_aperture(ops.to_host(vp), M)
+    vp64 /= M
+    a = a_list[len(a_list) // 3]
+    assert np.array_equal(ops.to_host(got[a_list.index(a)]), onp.refocus_int_slice(vp64, a, M).astype(np.float32))
+
+
+def test_refocus_from_aligned_full_mask_and_unaligned_base(cuda):
+    """Every view active and the aligned image sub-allocated at odd 2-byte offsets: the first / last aligned rows share
+    their 16-byte lines with memory outside the buffer (clamped bulk copies + plain edge loads)."""
+    import torch
+    from plenopticam_b200 import ops
+    Ma, S, T = 5, 7, 13
+    n = S * Ma * T * Ma * 3
+    rng = np.random.default_rng(3)
+    host = rng.integers(0, 65536, size=(S * Ma, T * Ma, 3), dtype=np.uint16)
+    pool = torch.full((n + 64,), -1, dtype=torch.int16, device=cuda)
+    full = np.zeros((Ma, Ma), dtype=bool)
+    ref = None
+    for off in (0, 1, 5, 8, 11):
+        al = pool[off:off + n].view(torch.uint16).view(S * Ma, T * Ma, 3)
+        al.view(torch.int16).copy_(torch.from_numpy(host.view(np.int16)).to(cuda))
+        got = ops.refocus_int_from_aligned(al, Ma, range(-4, 5), view_zeroed=full)
+        if ref is None:
+            ref = ops.refocus_int(ops.viewpoints(al.clone(), Ma), range(-4, 5), view_zeroed=full)
+        assert torch.equal(got, ref), off
+
+
+def test_pipeline_gather_fused_equals_explicit_gather(cuda):
+    import torch
+    from plenopticam_b200.misc import synth
+    from plenopticam_b200.pipeline import LightFieldPipeline
+    w = synth.illum_workload(9, small=True)
+    cent = synth.illum_centroids(w)
+    raw = synth.synth_raw(w["H"], w["W"], 3, seed=4)
+    outs = []
+    for fused_gather in (True, False):
+        for fuse_post in (True, False):
+            pipe = LightFieldPipeline(cent, raw.shape, np.uint16, w["M"], w["pat"], ran_refo=w["ran_refo"],
+                                      gather_fused=fused_gather, fuse_post=fuse_post)
+            outs.append(torch.from_numpy(pipe.run(raw).copy()))
+            assert pipe.gather_fused is fused_gather
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+@pytest.mark.parametrize("pat", ["hex", "rec"])
+def test_minmax_pass_with_tile_skipping_is_exact(cuda, pat):
+    """The bounds of the skipping min/max pass == those of the pass that interpolates every tile == the min / max of the
+    float32 aligned image; with smooth data most tiles are skipped, with a saturated image none can be."""
+    import torch
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_aligner import build_tables
+    from plenopticam_b200.misc import synth
+    cent = synth.synth_centroids(40, 90, 14.25, pat, jitter=0.15, origin=(9.5, 9.5), seed=8)
+    H, W = int(cent[:, 0].max() + 11), int(cent[:, 1].max() + 11)
+    tabs = ops.LensTables(build_tables(cent, (H, W, 3), 15, pat))
+    raws = [synth.synth_raw(H, W, 3, seed=9), np.full((H, W, 3), 65535, dtype=np.uint16)]
+    raws.append(raws[0].copy())
+    raws[2][7, 11] = 0                               # a single black sample inside the very first tile
+    raws[2][H // 2, W // 2] = 65535
+    for raw in raws:
+        dev = ops.to_device(raw)
+        al32, mm32 = ops.resample_f32(dev, tabs, want_minmax=True)
+        res = []
+        for noskip in ("0", "1"):
+            os.environ["PCB_RESAMPLE_NOSKIP"] = noskip
+            try:
+                _, mm = ops.resample_u16(dev, tabs)
+                res.append(ops.minmax_values(mm))
+            finally:
+                os.environ.pop("PCB_RESAMPLE_NOSKIP", None)
+        assert res[0] == res[1] == ops.minmax_values(mm32) == (float(al32.min()), float(al32.max()))
