@@ -62,6 +62,10 @@ typedef struct { uint32_t kmin, kmax; } pcb_minmax_t;
 int         pcb_version(void);
 const char *pcb_last_error(void);
 float       pcb_key_to_float(uint32_t key);         /* host helper: decode a pcb_minmax_t key           */
+/* Measurement hook (bench.py's roofline): two cudaEvent_t (as void*; NULL, NULL switches it off) that the calling thread's
+ * next pcb_refocus_int* calls record on their stream right before / after the persistent shift-and-sum kernel, so that the
+ * dominant kernel can be timed inside the stage without a profiler. */
+int         pcb_debug_kernel_events(void *ev_begin, void *ev_end);
 
 /* Reset a pcb_minmax_t to (+inf, -inf). */
 int pcb_minmax_reset(pcb_minmax_t *mm, void *stream);

@@ -115,6 +115,7 @@ _SIGNATURES = {
     "pcb_version": (C.c_int, []),
     "pcb_last_error": (C.c_char_p, []),
     "pcb_key_to_float": (C.c_float, [C.c_uint32]),
+    "pcb_debug_kernel_events": (_i, [_vp, _vp]),
     "pcb_minmax_reset": (_i, [_vp, _vp]),
     "pcb_minmax_f32": (_i, [_vp, _i64, _vp, _vp]),
     "pcb_resample_minmax": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),

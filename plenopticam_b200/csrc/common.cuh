@@ -11,6 +11,8 @@
 namespace pcb {
 
 extern thread_local char g_err[512];
+// pcb_debug_kernel_events: optional pair of events recorded right before / after the dominant kernel of the next calls
+extern thread_local cudaEvent_t g_kev[2];
 
 inline int fail(int code, const char *fmt, const char *a = "", long long b = 0) {
     snprintf(g_err, sizeof(g_err), fmt, a, b);

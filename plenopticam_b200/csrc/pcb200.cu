@@ -19,6 +19,7 @@
 
 namespace pcb {
 thread_local char g_err[512] = "";
+thread_local cudaEvent_t g_kev[2] = {nullptr, nullptr};
 }
 
 using namespace pcb;
@@ -57,6 +58,12 @@ extern "C" {
 int pcb_version(void) { return PCB_ABI_VERSION; }
 
 const char *pcb_last_error(void) { return g_err; }
+
+int pcb_debug_kernel_events(void *ev_begin, void *ev_end) {
+    g_kev[0] = reinterpret_cast<cudaEvent_t>(ev_begin);
+    g_kev[1] = reinterpret_cast<cudaEvent_t>(ev_end);
+    return PCB_OK;
+}
 
 float pcb_key_to_float(uint32_t key) { return key_to_float(key); }
 

@@ -458,10 +458,12 @@ static int launch_refocus_pxp(const PxPlan &px, const PxpPlan &pl, const uint16_
             a.nsl = nloc;
             int rc = PCB_OK;
             if (pass == 0) {
+                if (g_kev[0]) cudaEventRecord(g_kev[0], st);
                 if (pl.maxt == 640)
                     rc = launch_pxp_variant<640, 1>(pl, a, ctl, st);
                 else
                     rc = pl.ppt == 1 ? launch_pxp_variant<1024, 1>(pl, a, ctl, st) : launch_pxp_variant<1024, 2>(pl, a, ctl, st);
+                if (g_kev[1]) cudaEventRecord(g_kev[1], st);
                 if (rc == PCB_OK && !post) rc = launch_pxp_finalize<0>(pl, a, fctl, out, n0, nloc, mm, nullptr, st);
             } else if (pass == 1) {
                 rc = launch_pxp_finalize<1>(pl, a, fctl, out, n0, nloc, mm, post->lohi, st);

@@ -1,6 +1,6 @@
 """Seeded synthetic inputs of BASELINE.json's configurations: centroid tables, raw exposures and
-white images.  Data generators only - shared by bench.py, the tests, the oracle's golden-vector scripts and the
-reference arm so that every party sees the same bytes.  No reference or oracle code is involved."""
+white images.  Data generators only - shared by bench.py, the tests, the golden-vector scripts and the benchmark's
+reference arm so that every party sees the same bytes.  No reference or checker code is involved."""
 import numpy as np
 
 ILLUM = dict(H=5368, W=7728, C=3, LY=434, LX=541, M=15, pitch=14.25, origin=(9.5, 9.5), pat='hex')

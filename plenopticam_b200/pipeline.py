@@ -222,6 +222,9 @@ class LightFieldPipeline(object):
             "resample_u16": b_raw + b_al,
             "viewpoints": 2 * b_al,
             "refocus_int": b_vp_active + self.N * b_sl,
+            # reading the aligned image moves whole aligned rows (masked views included); the ALGORITHMIC bytes stay those
+            # of the active views
+            "refocus_int_from_aligned": b_vp_active + self.N * b_sl,
             "post": 2 * self.N * b_sl + 2 * 4 * b_sl,
         }
 
