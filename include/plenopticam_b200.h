@@ -237,6 +237,15 @@ int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N,
  * ------------------------------------------------------------------------------------------------ */
 #define PCB_MAX_PEERS 16
 typedef struct { float *out[PCB_MAX_PEERS]; pcb_minmax_t *mm[PCB_MAX_PEERS]; int32_t n; int32_t reserved; } pcb_fanout_t;
+/* Horizontal operators of a batch of slices regrouped in QUADS of four consecutive slices (host struct; nullable in
+ * pcb_refocus_refi_fanout): per quad g, view column i and output pixel x ONE sample window [fu, fu + W[i]) covering the
+ * bands of the four slices, and their weights padded with zeros to that window,
+ *     wq[woff[i] + (g * W[i] + t) * T + x] = float4 { slice 4g, 4g+1, 4g+2, 4g+3 } of tap t      (device, float4 units)
+ *     fu[(g * M + i) * T + x]                                                                    (device)
+ * lo[i] / hi[i]: smallest / largest sample offset relative to x that any window of view column i touches.
+ * With it the horizontal pass loads every sample once per quad instead of once per slice (same sums, bit for bit). */
+typedef struct { const float *wq; const int32_t *fu; int32_t G; int32_t reserved;
+                 int32_t woff[32]; int32_t W[32]; int32_t lo[32]; int32_t hi[32]; } pcb_refi_quads_t;
 int pcb_peer_alloc(int64_t bytes, void **dptr_host);
 int pcb_peer_free(void *dptr);
 int pcb_peer_export(void *dptr, unsigned char handle_host[64]);
@@ -248,7 +257,8 @@ int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N
                             const int32_t *iy, const int32_t *ix,
                             const int32_t *xlo_host, const int32_t *xhi_host,
                             const uint8_t *view_zeroed_host, const uint8_t *view_zeroed,
-                            float *tmp, const pcb_fanout_t *dst_host, void *stream);
+                            float *tmp, const pcb_fanout_t *dst_host, const pcb_refi_quads_t *quads_host /* nullable */,
+                            void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Post-processing of the stack — replaces LfpContrast.auto_hist_align + GammaConverter.srgb_conv as used

@@ -35,6 +35,12 @@ class Fanout(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class RefiQuads(C.Structure):
+    """pcb_refi_quads_t"""
+    _fields_ = [("wq", C.c_void_p), ("fu", C.c_void_p), ("G", C.c_int32), ("reserved", C.c_int32),
+                ("woff", C.c_int32 * 32), ("W", C.c_int32 * 32), ("lo", C.c_int32 * 32), ("hi", C.c_int32 * 32)]
+
+
 LENS_DTYPE = np.dtype([("oy", "<i4"), ("ox", "<i4"), ("wy", "<f4"), ("wx", "<f4")])
 HEXCOL_DTYPE = np.dtype([("x0", "<i4"), ("x1", "<i4"), ("w", "<f4"), ("reserved", "<i4")])
 
@@ -142,7 +148,7 @@ _SIGNATURES = {
     "pcb_refocus_refi": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp]),
     "pcb_refocus_refi_fanout": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _vp]),
+                                     _vp, _vp, _vp]),
     "pcb_peer_alloc": (_i, [_i64, C.POINTER(C.c_void_p)]),
     "pcb_peer_free": (_i, [_vp]),
     "pcb_peer_export": (_i, [_vp, C.c_char_p]),

@@ -439,7 +439,7 @@ int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N
                             const int32_t *dy_first, int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx,
                             const int32_t *iy, const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
                             const uint8_t *view_zeroed_host, const uint8_t *view_zeroed, float *tmp,
-                            const pcb_fanout_t *dst_host, void *stream) {
+                            const pcb_fanout_t *dst_host, const pcb_refi_quads_t *quads_host, void *stream) {
     int rc = check_refocus_refi(coef, M, S, T, C, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host,
                                 xhi_host, view_zeroed_host, view_zeroed, tmp);
     if (rc) return rc;
@@ -455,7 +455,7 @@ int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N
         }
     }
     return launch_refine(coef, M, S, T, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host, xhi_host,
-                         view_zeroed_host, tmp, dst, as_stream(stream));
+                         view_zeroed_host, tmp, dst, as_stream(stream), quads_host);
 }
 
 // ---- peer-mapped buffers (slice-sharded stacks) --------------------------------------------------------------------

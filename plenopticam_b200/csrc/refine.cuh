@@ -292,6 +292,151 @@ refine_h_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, con
     }
 }
 
+// ---- horizontal pass, slice quads ----------------------------------------------------------------------------------
+// refine_h_kernel issues one shared-memory load per FMA (every tap of every slice fetches its own sample), so it runs at
+// the LDS rate, a quarter of the FMA rate.  Four CONSECUTIVE slices read almost the same samples of a view - their shifts
+// a (c - i) differ by |c - i| up-sampled pixels, i.e. by less than half a coarse pixel - so this form walks the slices in
+// quads: per view and output pixel the host prepares ONE window [fu, fu + W) that covers the bands of all four slices
+// (W = K + 0..3) and the four bands padded with zeros to that window, as float4 {slice 0..3} per tap
+// (lfp_refocuser/refinement.py::quad_tables).  A thread then loads each sample of the window once and feeds 4 slices x 3
+// channels from it, for RQ_ROWS image rows whose weights it shares: per tap 1 coalesced LDG.128 + 3 RQ_ROWS LDS for
+// 12 RQ_ROWS FMAs.  Adding the zero taps changes nothing in the sums (x + 0 * s = x), and the taps of one slice still
+// arrive in ascending sample order, view by view: the results equal refine_h_kernel's bit for bit.
+constexpr int RQ = 4;                // slices per quad
+constexpr int RQ_XC = 128;           // output pixels per CTA
+constexpr int RQ_ROWS = 6;           // image rows per CTA (and per thread)
+constexpr int RQ_SG = 4;             // thread groups per CTA; they take the quads round-robin
+constexpr int RQ_THREADS = RQ_XC * RQ_SG;
+constexpr int RQ_MAXW = 8;
+
+struct RefineQCtl {                  // per-launch control block, passed by value
+    int32_t lo[RF_MAXM];             // per view column: smallest / largest coefficient offset (relative to the output
+    int32_t hi[RF_MAXM];             //   pixel) any quad window touches
+    uint32_t active[RF_MAXM];        // bit i of active[j]: view (j, i) is not masked
+    int32_t woff[RF_MAXM];           // float4 offset of view column i's block [G][W_i][T] in the weight table
+    int32_t W[RF_MAXM];              // window length of view column i
+};
+
+template <int W>
+__device__ __forceinline__ void rq_view(float (&acc)[RQ_ROWS][RQ][3], const float4 *__restrict__ wrec, int T,
+                                        const float *__restrict__ px, int wE) {
+    float4 wt = __ldg(wrec);
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+        const float4 wn = t + 1 < W ? __ldg(wrec + (size_t)(t + 1) * T) : wt;     // next tap's weights in flight
+#pragma unroll
+        for (int rr = 0; rr < RQ_ROWS; ++rr) {
+            const float s0 = px[rr * wE + t * 3 + 0], s1 = px[rr * wE + t * 3 + 1], s2 = px[rr * wE + t * 3 + 2];
+            acc[rr][0][0] = fmaf(wt.x, s0, acc[rr][0][0]); acc[rr][0][1] = fmaf(wt.x, s1, acc[rr][0][1]);
+            acc[rr][0][2] = fmaf(wt.x, s2, acc[rr][0][2]);
+            acc[rr][1][0] = fmaf(wt.y, s0, acc[rr][1][0]); acc[rr][1][1] = fmaf(wt.y, s1, acc[rr][1][1]);
+            acc[rr][1][2] = fmaf(wt.y, s2, acc[rr][1][2]);
+            acc[rr][2][0] = fmaf(wt.z, s0, acc[rr][2][0]); acc[rr][2][1] = fmaf(wt.z, s1, acc[rr][2][1]);
+            acc[rr][2][2] = fmaf(wt.z, s2, acc[rr][2][2]);
+            acc[rr][3][0] = fmaf(wt.w, s0, acc[rr][3][0]); acc[rr][3][1] = fmaf(wt.w, s1, acc[rr][3][1]);
+            acc[rr][3][2] = fmaf(wt.w, s2, acc[rr][3][2]);
+        }
+        wt = wn;
+    }
+}
+
+__global__ void __launch_bounds__(RQ_THREADS, 1)
+refine_hq_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, int G, const float4 *__restrict__ wq,
+                 const int32_t *__restrict__ fu, RefineQCtl ctl, float *__restrict__ H) {
+    extern __shared__ __align__(16) float s_win[];         // [active view][row][width_i * 3]
+    __shared__ int s_act[RF_MAXM];                         // the unmasked view columns of this view-row
+    __shared__ int2 s_view[RF_MAXM];                       // per ACTIVE view: {float offset of pixel 0 in s_win, row pitch}
+    __shared__ int2 s_tab[RF_MAXM];                        // per ACTIVE view: {float4 offset of its weight block, W}
+    __shared__ int s_nact;
+    const int j = blockIdx.z;
+    const int r0 = blockIdx.y * RQ_ROWS;
+    const int xc0 = blockIdx.x * RQ_XC;
+    const int tid = threadIdx.x;
+    const int sg = tid / RQ_XC, tx = tid - sg * RQ_XC;
+    const uint32_t act = ctl.active[j];
+    if (act == 0u) return;
+    const int nrow = min(RQ_ROWS, S - r0);
+    const int xcn = min(RQ_XC, T - xc0);
+
+    if (tid == 0) {
+        int off = 0, na = 0;
+        for (int i = 0; i < M; ++i) {
+            if (!((act >> i) & 1u)) continue;
+            const int a = max(xc0 + ctl.lo[i], 0), b = min(xc0 + xcn - 1 + ctl.hi[i], T - 1);
+            s_view[na] = make_int2(off - a * 3, (b - a + 1) * 3);
+            s_tab[na] = make_int2(ctl.woff[i], ctl.W[i]);
+            off += (b - a + 1) * 3 * RQ_ROWS;
+            s_act[na++] = i;
+        }
+        s_nact = na;
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    // ---- stage the coefficient windows: one (view, row) pair per warp and turn, 4-byte cp.async so that every copy of
+    //      the CTA is in flight before the first is waited for; rows beyond S are zero (their sums are never stored)
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int pr = warp; pr < nact * RQ_ROWS; pr += RQ_THREADS / 32) {
+            const int ii = pr / RQ_ROWS, rr = pr - ii * RQ_ROWS;
+            const int i = s_act[ii];
+            const int2 vw = s_view[ii];
+            const int wE = vw.y;
+            const int a = max(xc0 + ctl.lo[i], 0);
+            float *dst = s_win + vw.x + a * 3 + rr * wE;
+            if (rr < nrow) {
+                const float *src = coef + (((size_t)(j * M + i) * S + r0 + rr) * T + a) * 3;
+                for (int e = lane; e < wE; e += 32) {
+                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + e);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + e) : "memory");
+                }
+            } else {
+                for (int e = lane; e < wE; e += 32) dst[e] = 0.f;
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+    if (tx >= xcn) return;
+    const int x = xc0 + tx;
+
+    for (int g = sg; g < G; g += RQ_SG) {                  // the RQ_SG thread groups take the quads round-robin
+        float acc[RQ_ROWS][RQ][3];
+#pragma unroll
+        for (int rr = 0; rr < RQ_ROWS; ++rr)
+#pragma unroll
+            for (int q = 0; q < RQ; ++q) acc[rr][q][0] = acc[rr][q][1] = acc[rr][q][2] = 0.f;
+        for (int ii = 0; ii < nact; ++ii) {
+            const int2 vw = s_view[ii], tb = s_tab[ii];
+            const int i = s_act[ii];
+            const int f = __ldg(fu + ((size_t)g * M + i) * T + x);
+            const float4 *wrec = wq + (size_t)tb.x + ((size_t)g * tb.y) * T + x;
+            const float *px = s_win + vw.x + f * 3;
+            switch (tb.y) {                                // uniform over the CTA
+            case 1: rq_view<1>(acc, wrec, T, px, vw.y); break;
+            case 2: rq_view<2>(acc, wrec, T, px, vw.y); break;
+            case 3: rq_view<3>(acc, wrec, T, px, vw.y); break;
+            case 4: rq_view<4>(acc, wrec, T, px, vw.y); break;
+            case 5: rq_view<5>(acc, wrec, T, px, vw.y); break;
+            case 6: rq_view<6>(acc, wrec, T, px, vw.y); break;
+            case 7: rq_view<7>(acc, wrec, T, px, vw.y); break;
+            default: rq_view<8>(acc, wrec, T, px, vw.y); break;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            const int n = g * RQ + q;
+            if (n >= nb) break;
+#pragma unroll
+            for (int rr = 0; rr < RQ_ROWS; ++rr) {
+                if (rr < nrow) {
+                    float *o = H + ((((size_t)n * M + j) * S + r0 + rr) * T + x) * 3;
+                    o[0] = acc[rr][q][0]; o[1] = acc[rr][q][1]; o[2] = acc[rr][q][2];
+                }
+            }
+        }
+    }
+}
+
 // ---- vertical pass -----------------------------------------------------------------------------------------------
 // grid (Gy, ceil(E/256), nb): thread = one (x, c) element of a group of 4 output rows of slice n.
 // The finished values go to every destination of `dst` (pcb_fanout_t): the local stack and, in a slice-sharded job, the
@@ -403,10 +548,60 @@ static int launch_refine_h(const float *coef, int M, int S, int T, int nb, const
     return PCB_OK;
 }
 
+// Horizontal pass in slice quads; returns PCB_ERR_UNSUPPORTED (without touching g_err's meaning for the caller) when the
+// tables do not fit this kernel, so that launch_refine falls back to refine_h_kernel.
+static int launch_refine_hq(const float *coef, int M, int S, int T, int nb, const pcb_refi_quads_t &qd,
+                            const uint8_t *view_zeroed_host, float *H, cudaStream_t st) {
+    if (M > RF_MAXM || qd.G * RQ < nb || qd.wq == nullptr || qd.fu == nullptr) return PCB_ERR_UNSUPPORTED;
+    RefineQCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    size_t max_px = 0;
+    for (int j = 0; j < M; ++j) {
+        size_t px = 0;
+        for (int i = 0; i < M; ++i) {
+            if (view_zeroed_host[j * M + i]) continue;
+            if (qd.W[i] < 1 || qd.W[i] > RQ_MAXW || qd.hi[i] < qd.lo[i]) return PCB_ERR_UNSUPPORTED;
+            ctl.active[j] |= 1u << i;
+            px += (size_t)RQ_XC + (size_t)(qd.hi[i] - qd.lo[i]);
+        }
+        if (px > max_px) max_px = px;
+    }
+    for (int i = 0; i < M; ++i) { ctl.lo[i] = qd.lo[i]; ctl.hi[i] = qd.hi[i]; ctl.woff[i] = qd.woff[i]; ctl.W[i] = qd.W[i]; }
+    const size_t smem = max_px * 3 * RQ_ROWS * sizeof(float);
+    if (smem > 220 * 1024 || (S + RQ_ROWS - 1) / RQ_ROWS > 65535) return PCB_ERR_UNSUPPORTED;
+    PCB_CUDA(cudaFuncSetAttribute(refine_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((T + RQ_XC - 1) / RQ_XC, (S + RQ_ROWS - 1) / RQ_ROWS, M);
+    refine_hq_kernel<<<grid, RQ_THREADS, smem, st>>>(coef, M, S, T, nb, qd.G, reinterpret_cast<const float4 *>(qd.wq), qd.fu,
+                                                     ctl, H);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+static int launch_refine_v(const float *H, int M, int S, int T, int nb, const float *dy_vals, const int32_t *dy_first,
+                           int Kgy, const int32_t *iy, const uint8_t *view_zeroed_host, const pcb_fanout_t &dst,
+                           cudaStream_t st) {
+    const int E = T * 3;
+    RefineHCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    for (int j = 0; j < M; ++j)
+        for (int i = 0; i < M; ++i)
+            if (!view_zeroed_host[j * M + i]) ctl.active[j] |= 1u << i;
+    const int Gy = (S + RF_GROUP - 1) / RF_GROUP;
+    refine_v_kernel<<<dim3(Gy, (E + 255) / 256, nb), 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, Kgy, iy, ctl, dst);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
 static int launch_refine(const float *coef, int M, int S, int T, int nb, const float *dy_vals, const int32_t *dy_first,
                          int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx, const int32_t *iy,
                          const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
-                         const uint8_t *view_zeroed_host, float *H, const pcb_fanout_t &dst, cudaStream_t st) {
+                         const uint8_t *view_zeroed_host, float *H, const pcb_fanout_t &dst, cudaStream_t st,
+                         const pcb_refi_quads_t *quads = nullptr) {
+    if (quads != nullptr && !(getenv("PCB_REFINE_KERNEL") && !strcmp(getenv("PCB_REFINE_KERNEL"), "taps"))) {
+        const int rq = launch_refine_hq(coef, M, S, T, nb, *quads, view_zeroed_host, H, st);
+        if (rq == PCB_OK) return launch_refine_v(H, M, S, T, nb, dy_vals, dy_first, Kgy, iy, view_zeroed_host, dst, st);
+        if (rq != PCB_ERR_UNSUPPORTED) return rq;
+    }
     const int E = T * 3;
     RefineHCtl ctl;
     memset(&ctl, 0, sizeof(ctl));

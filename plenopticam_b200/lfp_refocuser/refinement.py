@@ -206,6 +206,56 @@ class AxisOperators(object):
         return self.apply_coef(s, self.prefilter(f, axis), axis)
 
 
+QUAD = 4            # consecutive slices that share one sample window in the horizontal device pass
+QUAD_MAXW = 8       # longest shared window the quad kernel is built for
+
+
+def quad_tables(Bx, ix, M):
+    """Horizontal operators of the slices `ix` (n, M: operator index per slice and view column) regrouped in quads of
+    four consecutive slices (csrc/refine.cuh::refine_hq_kernel, pcb_refi_quads_t).
+
+    For quad g, view column i and output pixel x:  fu = min over the quad of the band starts (kept <= T - W_i),
+    W_i = K + the largest spread of band starts seen for that view column, and the four bands written into the common
+    window with zeros around them.  Returns dict(wq (float32, flat, float4 units of woff), fu (G, M, T) int32,
+    woff (M,), W (M,), lo (M,), hi (M,), G) or None when a window would exceed QUAD_MAXW."""
+    ix = np.asarray(ix)
+    n, T, K = ix.shape[0], Bx.n, Bx.K
+    G = (n + QUAD - 1) // QUAD
+    pad = np.minimum(np.arange(G * QUAD), n - 1)
+    live = (np.arange(G * QUAD) < n).reshape(G, QUAD)
+    idx = ix[pad]                                               # (G*4, M)
+    f = Bx.first[idx].astype(np.int64).reshape(G, QUAD, M, T)   # band start per slice, view column, pixel
+    fu = f.min(axis=1)                                          # (G, M, T)
+    W = (f.max(axis=1) + K - fu).max(axis=(0, 2))               # (M,)
+    W = np.maximum(W, min(K, T)).astype(np.int64)
+    if W.max() > QUAD_MAXW or W.max() > T:
+        return None
+    fu = np.minimum(fu, (T - W)[None, :, None])
+    off = f - fu[:, None]                                       # (G, 4, M, T) >= 0, off + K <= W
+    vals = Bx.vals[idx].reshape(G, QUAD, M, T, K).copy()        # float32
+    vals[~live] = 0.0
+    woff = np.zeros(M, dtype=np.int64)
+    blocks = []
+    pos = 0
+    gi, xi = np.meshgrid(np.arange(G), np.arange(T), indexing='ij')
+    for i in range(M):
+        Wi = int(W[i])
+        blk = np.zeros((G, Wi, T, QUAD), dtype=np.float32)      # [g][t][x] -> float4 {slice 0..3}
+        for q in range(QUAD):
+            for k in range(K):
+                t = off[:, q, i, :] + k                         # (G, T)
+                ok = t < Wi                                     # taps beyond the window are the band's zero padding
+                assert np.all(vals[:, q, i, :, k][~ok] == 0.0)
+                blk[gi[ok], t[ok], xi[ok], q] = vals[:, q, i, :, k][ok]
+        woff[i] = pos
+        pos += G * Wi * T
+        blocks.append(blk.reshape(-1))
+    rel = fu - np.arange(T)[None, None, :]
+    return dict(wq=np.concatenate(blocks), fu=np.ascontiguousarray(fu.astype(np.int32)), woff=woff.astype(np.int32),
+                W=W.astype(np.int32), lo=rel.min(axis=(0, 2)).astype(np.int32),
+                hi=(rel.max(axis=(0, 2)) + W - 1).astype(np.int32), G=int(G))
+
+
 _PLAN_CACHE = {}
 
 
@@ -250,9 +300,35 @@ class RefinementPlan(object):
         self.ix = np.array([[Bx.index[a * (c - i)] for i in range(M)] for a in self.a_list], dtype=np.int32)
         self.iy_d, self.ix_d = t(self.iy), t(self.ix)
         self._xlo, self._xhi = xlo, xhi
+        self._Bx = Bx
+        self._quads = {}
         per_slice = M * S * T * 3 * 4                       # horizontal pass of one slice: (M, S, T, 3) float32
         self.batch = int(max(1, min(self.N, tmp_budget_bytes // per_slice, 1024 // M)))
         self.device = device
+
+    def quads(self, n0, nb):
+        """pcb_refi_quads_t of slices n0 .. n0+nb-1 (device tables, cached per slice range), or None."""
+        import ctypes as C
+        import torch
+        from .. import _native as nat
+        key = (int(n0), int(nb))
+        if key not in self._quads:
+            if len(self._quads) >= 4:
+                self._quads.pop(next(iter(self._quads)))
+            tab = quad_tables(self._Bx, self.ix[n0:n0 + nb], self.M) if self._Bx.K <= QUAD_MAXW else None
+            if tab is None:
+                self._quads[key] = None
+            else:
+                wq = torch.from_numpy(tab["wq"]).to(self.device)
+                fu = torch.from_numpy(tab["fu"]).to(self.device)
+                st = nat.RefiQuads()
+                st.wq, st.fu, st.G = wq.data_ptr(), fu.data_ptr(), tab["G"]
+                for i in range(self.M):
+                    st.woff[i], st.W[i], st.lo[i], st.hi[i] = (int(tab["woff"][i]), int(tab["W"][i]), int(tab["lo"][i]),
+                                                               int(tab["hi"][i]))
+                self._quads[key] = (st, wq, fu)
+        ent = self._quads[key]
+        return None if ent is None else ent[0]
 
     def window(self, n0, nb):
         """Per view column: smallest / largest sample offset any slice of the batch reads, relative to x."""
@@ -319,6 +395,7 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=N
     for n0 in range(0, N, plan.batch):
         nb = min(plan.batch, N - n0)
         lo, hi = plan.window(n_lo + n0, nb)
+        qd = plan.quads(n_lo + n0, nb)
         dst = nat.Fanout()
         dst.n = len(fanout)
         for d, (o_ptr, m_ptr) in enumerate(fanout):
@@ -329,7 +406,8 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=N
                                             C.c_void_p(plan.iy_d.data_ptr() + (n_lo + n0) * M * 4),
                                             C.c_void_p(plan.ix_d.data_ptr() + (n_lo + n0) * M * 4),
                                             lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), z_ptr,
-                                            p(plan.z_dev), p(hbuf), C.byref(dst), st))
+                                            p(plan.z_dev), p(hbuf), C.byref(dst),
+                                            C.byref(qd) if qd is not None else None, st))
     return out
 
 

@@ -152,3 +152,51 @@ def test_prefilter_register_window_kernels_equal_table_kernels(cuda):
         outs.append((tmp, coef))
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+def test_quad_tables_reproduce_the_bands():
+    """Slice quads (refine_hq_kernel): the shared window + zero-padded float4 weights give the same sums as the plain
+    per-slice bands, for a ragged number of slices, at the borders, and for masked / unmasked view columns."""
+    from plenopticam_b200.lfp_refocuser import refinement as rf
+    M, T = 9, 57
+    a_list = list(range(-13, 10))                           # 23 slices: last quad has 3 live members
+    c = M // 2
+    Bx = rf.AxisOperators(T, M, sorted(set(a * d for a in a_list for d in range(-c, c + 1))))
+    ix = np.array([[Bx.index[a * (c - i)] for i in range(M)] for a in a_list], dtype=np.int32)
+    tab = rf.quad_tables(Bx, ix, M)
+    assert tab is not None and tab["G"] == 6 and tab["W"].min() >= Bx.K and tab["W"].max() <= rf.QUAD_MAXW
+    coef = np.random.default_rng(0).random(T)
+    for n in (0, 5, 11, 22):
+        g, q = divmod(n, rf.QUAD)
+        for i in range(M):
+            W = int(tab["W"][i])
+            blk = tab["wq"][tab["woff"][i] * 4:(tab["woff"][i] + tab["G"] * W * T) * 4].reshape(tab["G"], W, T, 4)
+            fu = tab["fu"][g, i]
+            assert fu.min() >= 0 and (fu + W).max() <= T
+            assert (fu - np.arange(T)).min() >= tab["lo"][i] and (fu - np.arange(T)).max() + W - 1 <= tab["hi"][i]
+            out = np.array([sum(float(blk[g, t, x, q]) * coef[fu[x] + t] for t in range(W)) for x in range(T)])
+            assert np.abs(out - Bx.apply_coef(a_list[n] * (c - i), coef)).max() < 1e-6
+    # the padding members of the last quad carry zero weights
+    W0 = int(tab["W"][0])
+    last = tab["wq"][tab["woff"][0] * 4:(tab["woff"][0] + tab["G"] * W0 * T) * 4].reshape(tab["G"], W0, T, 4)[5]
+    assert np.all(last[..., 3] == 0.0) and np.any(last[..., 2] != 0.0)
+
+
+@pytest.mark.gpu
+def test_quad_kernel_equals_tap_kernel_bit_for_bit(cuda):
+    """refine_hq_kernel (slice quads) vs refine_h_kernel (one slice at a time): identical stacks."""
+    import os
+    import torch
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_refocuser.refinement import refocus_refi
+    rng = np.random.default_rng(21)
+    for M, S, T, a_list in ((7, 23, 140, list(range(-7, 8))), (15, 14, 300, list(range(-30, 30, 1))[:22])):
+        vp = ops.to_device((rng.random((M, M, S, T, 3)) * 65535).astype(np.uint16))
+        mask = ops.aperture_mask(M)
+        got = refocus_refi(vp, a_list, mask)
+        os.environ["PCB_REFINE_KERNEL"] = "taps"
+        try:
+            ref = refocus_refi(vp, a_list, mask)
+        finally:
+            os.environ.pop("PCB_REFINE_KERNEL", None)
+        assert torch.equal(got, ref)
