@@ -189,7 +189,8 @@ int pcb_refocus_int_srgb(const void *vp, int dtype, int M, int S, int T, int C, 
  *       px_vals[Kpx][T], px_first[T];  view_zeroed[M*M] (device)
  *       tmp, coef: float32 (M,M,S,T,3)
  *   pcb_refocus_refi   : a batch of N slices from the coefficients
- *       dy_vals[nsy][ceil(S/4)][Kgy][4], dy_first[nsy][ceil(S/4)]  (groups of 4 output rows share a window)
+ *       dy_vals[nsy][ceil(S/8)][Kgy][8], dy_first[nsy][ceil(S/8)]  (groups of 8 output rows share a window of Kgy
+ *                                 sample rows that lies inside the image: dy_first + Kgy <= S)
  *       dx_vals[nsx][Kx][T], dx_first[nsx][T]
  *       iy[N][M], ix[N][M]: operator index for slice n and view-row j / view-column i (device)
  *       xlo_host[M], xhi_host[M]: per view column, smallest / largest coefficient offset relative to the output

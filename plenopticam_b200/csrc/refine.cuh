@@ -19,7 +19,7 @@
 
 namespace pcb {
 
-constexpr int RF_GROUP = 4;
+constexpr int RF_GROUP = 8;          // output rows that share one sample window in the vertical pass
 constexpr int RF_MAXM = 32;          // view columns per row supported by the control block
 
 // ---- prefilter -------------------------------------------------------------------------------------------------
@@ -438,37 +438,73 @@ refine_hq_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, in
 }
 
 // ---- vertical pass -----------------------------------------------------------------------------------------------
-// grid (Gy, ceil(E/256), nb): thread = one (x, c) element of a group of 4 output rows of slice n.
+// out[n][y][e] = (1/M) sum_{j active} sum_m Dy[s(n,j)][g(y)][m][q(y)] * H[n][j][first + m][e]
+// grid (Gy, ceil(E/256), nb): thread = one (x, c) element of a group of RF_GROUP = 8 output rows of slice n that share
+// one window of KG sample rows per view row (KG = K + spread of the band starts inside a group, compile time; the host
+// tables keep every window inside the image, so there is no clamping).  The pass is bound by the latency of the H loads
+// (2.9 GB read once from DRAM), so: wide groups (13 rows loaded for 8 outputs instead of 9 for 4), the weights of the
+// whole CTA staged once in shared memory (they are the same for every thread: broadcast LDS.128 instead of global
+// loads), and the samples of the next view row requested before the current ones are used.
 // The finished values go to every destination of `dst` (pcb_fanout_t): the local stack and, in a slice-sharded job, the
 // peer-mapped stacks of the other GPUs - the exchange is these stores, issued as soon as a tile is done, so the NVLink
 // traffic overlaps the arithmetic of the CTAs that are still running.
+template <int KG>
 __global__ void __launch_bounds__(256)
 refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *__restrict__ dy_vals,
-                const int32_t *__restrict__ dy_first, int Kg, const int32_t *__restrict__ iy, RefineHCtl ctl,
-                pcb_fanout_t dst) {
-    const int gy = blockIdx.x;
-    const int Gy = gridDim.x;
-    const int n = blockIdx.z;
+                const int32_t *__restrict__ dy_first, const int32_t *__restrict__ iy, RefineHCtl ctl, pcb_fanout_t dst) {
+    __shared__ __align__(16) float s_w[RF_MAXM * KG * RF_GROUP];      // [active view row][tap][output row of the group]
+    __shared__ int s_j[RF_MAXM];           // active view rows
+    __shared__ int s_f[RF_MAXM];           // first sample row of this group for each of them
+    __shared__ int s_n;
+    const int gy = blockIdx.x, Gy = gridDim.x, n = blockIdx.z;
     const int e = blockIdx.y * blockDim.x + threadIdx.x;
-    const int32_t *iy_n = iy + (size_t)n * M;
+    if (threadIdx.x < 32) {                // M <= 32: one lane per view row, compacted with a ballot
+        const int j = threadIdx.x;
+        const bool on = j < M && ctl.active[j] != 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            const int k = __popc(m & ((1u << j) - 1u));
+            const int sidx = __ldg(iy + (size_t)n * M + j);
+            s_j[k] = j;
+            s_f[k] = __ldg(dy_first + (size_t)sidx * Gy + gy);
+            // the weights of this (slice, group): KG * RF_GROUP consecutive floats per view row
+            const float *src = dy_vals + ((size_t)sidx * Gy + gy) * (KG * RF_GROUP);
+            for (int t = 0; t < KG * RF_GROUP; ++t) s_w[k * KG * RF_GROUP + t] = __ldg(src + t);
+        }
+        if (j == 0) s_n = __popc(m);
+    }
+    __syncthreads();
+    const int na = s_n;
     float mn = INFINITY, mx = -INFINITY;
     if (e < E) {
-        float acc[RF_GROUP] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < M; ++j) {
-            if (ctl.active[j] == 0u) continue;
-            const int sidx = __ldg(iy_n + j);
-            const int f = __ldg(dy_first + (size_t)sidx * Gy + gy);
-            const float4 *w = reinterpret_cast<const float4 *>(dy_vals) + ((size_t)sidx * Gy + gy) * Kg;
-            const float *col = H + (((size_t)n * M + j) * S) * E + e;
-#pragma unroll 3
-            for (int m = 0; m < Kg; ++m) {
-                const float4 w4 = __ldg(w + m);                      // same address for the whole CTA: broadcast
-                const float v = __ldg(col + (size_t)min(f + m, S - 1) * E);
-                acc[0] = fmaf(w4.x, v, acc[0]);
-                acc[1] = fmaf(w4.y, v, acc[1]);
-                acc[2] = fmaf(w4.z, v, acc[2]);
-                acc[3] = fmaf(w4.w, v, acc[3]);
+        float acc[RF_GROUP];
+#pragma unroll
+        for (int q = 0; q < RF_GROUP; ++q) acc[q] = 0.f;
+        const size_t sE = (size_t)E;
+        const float *base = H + ((size_t)n * M) * S * sE + e;
+        float v[KG], vn[KG];
+        if (na > 0) {
+            const float *col = base + ((size_t)s_j[0] * S + s_f[0]) * sE;
+#pragma unroll
+            for (int m = 0; m < KG; ++m) v[m] = __ldg(col + m * sE);
+        }
+        for (int k = 0; k < na; ++k) {
+            if (k + 1 < na) {
+                const float *col = base + ((size_t)s_j[k + 1] * S + s_f[k + 1]) * sE;
+#pragma unroll
+                for (int m = 0; m < KG; ++m) vn[m] = __ldg(col + m * sE);
             }
+            const float4 *w = reinterpret_cast<const float4 *>(s_w + k * KG * RF_GROUP);
+#pragma unroll
+            for (int m = 0; m < KG; ++m) {
+                const float4 wa = w[2 * m], wb = w[2 * m + 1];       // same address for the whole CTA: broadcast
+                acc[0] = fmaf(wa.x, v[m], acc[0]); acc[1] = fmaf(wa.y, v[m], acc[1]);
+                acc[2] = fmaf(wa.z, v[m], acc[2]); acc[3] = fmaf(wa.w, v[m], acc[3]);
+                acc[4] = fmaf(wb.x, v[m], acc[4]); acc[5] = fmaf(wb.y, v[m], acc[5]);
+                acc[6] = fmaf(wb.z, v[m], acc[6]); acc[7] = fmaf(wb.w, v[m], acc[7]);
+            }
+#pragma unroll
+            for (int m = 0; m < KG; ++m) v[m] = vn[m];
         }
         const float invM = 1.0f / (float)M;
         const size_t o_n = (size_t)n * S * E + e;
@@ -476,12 +512,12 @@ refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *_
         for (int q = 0; q < RF_GROUP; ++q) {
             const int y = gy * RF_GROUP + q;
             if (y < S) {
-                const float v = acc[q] * invM;
+                const float val = acc[q] * invM;
 #pragma unroll
                 for (int d = 0; d < PCB_MAX_PEERS; ++d)
-                    if (d < dst.n) dst.out[d][o_n + (size_t)y * E] = v;
-                mn = fminf(mn, v);
-                mx = fmaxf(mx, v);
+                    if (d < dst.n) dst.out[d][o_n + (size_t)y * E] = val;
+                mn = fminf(mn, val);
+                mx = fmaxf(mx, val);
             }
         }
     }
@@ -587,7 +623,15 @@ static int launch_refine_v(const float *H, int M, int S, int T, int nb, const fl
         for (int i = 0; i < M; ++i)
             if (!view_zeroed_host[j * M + i]) ctl.active[j] |= 1u << i;
     const int Gy = (S + RF_GROUP - 1) / RF_GROUP;
-    refine_v_kernel<<<dim3(Gy, (E + 255) / 256, nb), 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, Kgy, iy, ctl, dst);
+    const dim3 grid(Gy, (E + 255) / 256, nb);
+    if (Kgy > S) return fail(PCB_ERR_INVALID, "%s: vertical window of %lld rows exceeds the image", "pcb_refocus_refi", Kgy);
+#define PCB_RV(K) case K: refine_v_kernel<K><<<grid, 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, iy, ctl, dst); break;
+    switch (Kgy) {
+        PCB_RV(1) PCB_RV(2) PCB_RV(3) PCB_RV(4) PCB_RV(5) PCB_RV(6) PCB_RV(7) PCB_RV(8) PCB_RV(9) PCB_RV(10)
+        PCB_RV(11) PCB_RV(12) PCB_RV(13) PCB_RV(14) PCB_RV(15) PCB_RV(16) PCB_RV(17) PCB_RV(18) PCB_RV(19) PCB_RV(20)
+    default: return fail(PCB_ERR_UNSUPPORTED, "%s: vertical window of %lld rows (1..20 supported)", "pcb_refocus_refi", Kgy);
+    }
+#undef PCB_RV
     PCB_LAUNCH_OK();
     return PCB_OK;
 }
@@ -638,10 +682,7 @@ static int launch_refine(const float *coef, int M, int S, int T, int nb, const f
     default: return fail(PCB_ERR_UNSUPPORTED, "%s: band of %lld taps (1..12 supported)", "pcb_refocus_refi", Kx);
     }
     if (rc) return rc;
-    const int Gy = (S + RF_GROUP - 1) / RF_GROUP;
-    refine_v_kernel<<<dim3(Gy, (E + 255) / 256, nb), 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, Kgy, iy, ctl, dst);
-    PCB_LAUNCH_OK();
-    return PCB_OK;
+    return launch_refine_v(H, M, S, T, nb, dy_vals, dy_first, Kgy, iy, view_zeroed_host, dst, st);
 }
 
 }  // namespace pcb

@@ -27,7 +27,7 @@ import scipy.sparse.linalg as spla
 from scipy.interpolate import BSpline
 
 BAND_EPS = 1e-8
-GROUP = 4           # output rows that share one sample window in the vertical device pass
+GROUP = 8           # output rows that share one sample window in the vertical device pass (RF_GROUP)
 
 
 def spline_factors(n_in, n_out):
@@ -174,16 +174,18 @@ class AxisOperators(object):
         fg = self.first[:, idx]                                                   # (ns, G, GROUP)
         start = fg.min(axis=2)
         spread = int((fg - start[:, :, None]).max())
-        Kg = K + spread
+        Kg = min(K + spread, n)
+        # keep every window inside [0, n): the device pass then reads rows start .. start+Kg-1 without clamping
+        start = np.minimum(start, n - Kg)
         vals = np.zeros((ns, G, Kg, GROUP), dtype=np.float32)
-        off = fg - start[:, :, None]                                              # (ns, G, GROUP)
+        off = fg - start[:, :, None]                                              # (ns, G, GROUP), off + K <= Kg
         valid = (np.arange(G * GROUP).reshape(G, GROUP) < n)
         for q in range(GROUP):
             for d in range(spread + 1):
                 sel = (off[:, :, q] == d) & valid[None, :, q]
                 if sel.any():
                     si, gi = np.nonzero(sel)
-                    vals[si, gi, d:d + K, q] = self.vals[si, idx[gi, q]]
+                    vals[si, gi, d:d + K, q] = self.vals[si, idx[gi, q]][:, :Kg - d]
         return vals, start.astype(np.int32), Kg
 
     # -- numpy evaluation of the truncated float32 bands (CPU tests) ---------------------------------------

@@ -36,14 +36,15 @@ def test_band_operators_reproduce_reference_refinement():
         assert np.abs(acc / M - g["stack"][n]).max() <= 1e-6 * np.abs(g["stack"]).max()
     # device layouts == plain band (applied to B-spline coefficients)
     rng = np.random.default_rng(0)
-    vals, first, Kg = Ay.grouped()                              # vertical pass: groups of 4 outputs share a window
+    vals, first, Kg = Ay.grouped()                              # vertical pass: groups of GROUP outputs share a window
     f = rng.random(S)
     for s in Ay.shifts[::7]:
         k = Ay.index[s]
-        out = np.zeros(vals.shape[1] * 4)
+        out = np.zeros(vals.shape[1] * rf.GROUP)
         for gi in range(vals.shape[1]):
+            assert first[k, gi] >= 0 and first[k, gi] + Kg <= S             # windows inside the image: no clamping on the device
             for m in range(Kg):
-                out[4 * gi:4 * gi + 4] += vals[k, gi, m] * f[min(first[k, gi] + m, S - 1)]
+                out[rf.GROUP * gi:rf.GROUP * (gi + 1)] += vals[k, gi, m] * f[first[k, gi] + m]
         assert np.abs(out[:S] - Ay.apply_coef(s, f)).max() < 1e-6
     tv, tf, lo, hi = Bx.tap_major()                             # horizontal pass: one thread per output, tap-major weights
     f = rng.random(T)
