@@ -317,24 +317,32 @@ struct RefineQCtl {                  // per-launch control block, passed by valu
     int32_t W[RF_MAXM];              // window length of view column i
 };
 
+constexpr int RQ_PIX = 20;           // floats per staged pixel: RQ_ROWS x 3 channels + 2 pad.  5 float4 = an ODD number of
+                                     //   16-byte units, so the LDS.128 of a quarter-warp (lane stride 80 B) hit 8 distinct
+                                     //   bank groups: conflict free
+static_assert(RQ_ROWS * 3 <= RQ_PIX && RQ_PIX % 4 == 0 && (RQ_PIX / 4) % 2 == 1, "pixel record layout");
+
+// One view: W taps; per tap one float4 of weights {slice 0..3} and the pixel record of the window sample (6 rows x 3
+// channels in 5 LDS.128 off ONE base register with immediate offsets).
 template <int W>
 __device__ __forceinline__ void rq_view(float (&acc)[RQ_ROWS][RQ][3], const float4 *__restrict__ wrec, int T,
-                                        const float *__restrict__ px, int wE) {
+                                        const float4 *__restrict__ px) {
     float4 wt = __ldg(wrec);
 #pragma unroll
     for (int t = 0; t < W; ++t) {
         const float4 wn = t + 1 < W ? __ldg(wrec + (size_t)(t + 1) * T) : wt;     // next tap's weights in flight
+        const float4 v0 = px[t * 5 + 0], v1 = px[t * 5 + 1], v2 = px[t * 5 + 2], v3 = px[t * 5 + 3], v4 = px[t * 5 + 4];
+        const float s[RQ_ROWS][3] = {{v0.x, v0.y, v0.z}, {v0.w, v1.x, v1.y}, {v1.z, v1.w, v2.x},
+                                     {v2.y, v2.z, v2.w}, {v3.x, v3.y, v3.z}, {v3.w, v4.x, v4.y}};
 #pragma unroll
         for (int rr = 0; rr < RQ_ROWS; ++rr) {
-            const float s0 = px[rr * wE + t * 3 + 0], s1 = px[rr * wE + t * 3 + 1], s2 = px[rr * wE + t * 3 + 2];
-            acc[rr][0][0] = fmaf(wt.x, s0, acc[rr][0][0]); acc[rr][0][1] = fmaf(wt.x, s1, acc[rr][0][1]);
-            acc[rr][0][2] = fmaf(wt.x, s2, acc[rr][0][2]);
-            acc[rr][1][0] = fmaf(wt.y, s0, acc[rr][1][0]); acc[rr][1][1] = fmaf(wt.y, s1, acc[rr][1][1]);
-            acc[rr][1][2] = fmaf(wt.y, s2, acc[rr][1][2]);
-            acc[rr][2][0] = fmaf(wt.z, s0, acc[rr][2][0]); acc[rr][2][1] = fmaf(wt.z, s1, acc[rr][2][1]);
-            acc[rr][2][2] = fmaf(wt.z, s2, acc[rr][2][2]);
-            acc[rr][3][0] = fmaf(wt.w, s0, acc[rr][3][0]); acc[rr][3][1] = fmaf(wt.w, s1, acc[rr][3][1]);
-            acc[rr][3][2] = fmaf(wt.w, s2, acc[rr][3][2]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                acc[rr][0][c] = fmaf(wt.x, s[rr][c], acc[rr][0][c]);
+                acc[rr][1][c] = fmaf(wt.y, s[rr][c], acc[rr][1][c]);
+                acc[rr][2][c] = fmaf(wt.z, s[rr][c], acc[rr][2][c]);
+                acc[rr][3][c] = fmaf(wt.w, s[rr][c], acc[rr][3][c]);
+            }
         }
         wt = wn;
     }
@@ -343,9 +351,9 @@ __device__ __forceinline__ void rq_view(float (&acc)[RQ_ROWS][RQ][3], const floa
 __global__ void __launch_bounds__(RQ_THREADS, 1)
 refine_hq_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, int G, const float4 *__restrict__ wq,
                  const int32_t *__restrict__ fu, RefineQCtl ctl, float *__restrict__ H) {
-    extern __shared__ __align__(16) float s_win[];         // [active view][row][width_i * 3]
+    extern __shared__ __align__(16) float s_win[];         // [active view][pixel of the window][RQ_PIX]
     __shared__ int s_act[RF_MAXM];                         // the unmasked view columns of this view-row
-    __shared__ int2 s_view[RF_MAXM];                       // per ACTIVE view: {float offset of pixel 0 in s_win, row pitch}
+    __shared__ int2 s_view[RF_MAXM];                       // per ACTIVE view: {float offset of pixel 0's record, pixels}
     __shared__ int2 s_tab[RF_MAXM];                        // per ACTIVE view: {float4 offset of its weight block, W}
     __shared__ int s_nact;
     const int j = blockIdx.z;
@@ -363,34 +371,39 @@ refine_hq_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, in
         for (int i = 0; i < M; ++i) {
             if (!((act >> i) & 1u)) continue;
             const int a = max(xc0 + ctl.lo[i], 0), b = min(xc0 + xcn - 1 + ctl.hi[i], T - 1);
-            s_view[na] = make_int2(off - a * 3, (b - a + 1) * 3);
+            s_view[na] = make_int2(off - a * RQ_PIX, b - a + 1);
             s_tab[na] = make_int2(ctl.woff[i], ctl.W[i]);
-            off += (b - a + 1) * 3 * RQ_ROWS;
+            off += (b - a + 1) * RQ_PIX;
             s_act[na++] = i;
         }
         s_nact = na;
     }
     __syncthreads();
     const int nact = s_nact;
-    // ---- stage the coefficient windows: one (view, row) pair per warp and turn, 4-byte cp.async so that every copy of
-    //      the CTA is in flight before the first is waited for; rows beyond S are zero (their sums are never stored)
+    // ---- stage the coefficient windows, transposed to pixel records [x][row][channel]: one (view, row) pair per warp
+    //      and turn, 4-byte cp.async so that every copy of the CTA is in flight before the first is waited for; rows
+    //      beyond S are zero (their sums are never stored)
     {
         const int warp = tid >> 5, lane = tid & 31;
         for (int pr = warp; pr < nact * RQ_ROWS; pr += RQ_THREADS / 32) {
             const int ii = pr / RQ_ROWS, rr = pr - ii * RQ_ROWS;
             const int i = s_act[ii];
             const int2 vw = s_view[ii];
-            const int wE = vw.y;
             const int a = max(xc0 + ctl.lo[i], 0);
-            float *dst = s_win + vw.x + a * 3 + rr * wE;
+            float *dst = s_win + vw.x + a * RQ_PIX + rr * 3;
+            const int nE = vw.y * 3;
             if (rr < nrow) {
                 const float *src = coef + (((size_t)(j * M + i) * S + r0 + rr) * T + a) * 3;
-                for (int e = lane; e < wE; e += 32) {
-                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + e);
+                for (int e = lane; e < nE; e += 32) {
+                    const int p = e / 3, c = e - p * 3;
+                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + p * RQ_PIX + c);
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + e) : "memory");
                 }
             } else {
-                for (int e = lane; e < wE; e += 32) dst[e] = 0.f;
+                for (int e = lane; e < nE; e += 32) {
+                    const int p = e / 3, c = e - p * 3;
+                    dst[p * RQ_PIX + c] = 0.f;
+                }
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -410,16 +423,16 @@ refine_hq_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, in
             const int i = s_act[ii];
             const int f = __ldg(fu + ((size_t)g * M + i) * T + x);
             const float4 *wrec = wq + (size_t)tb.x + ((size_t)g * tb.y) * T + x;
-            const float *px = s_win + vw.x + f * 3;
+            const float4 *px = reinterpret_cast<const float4 *>(s_win + vw.x + f * RQ_PIX);
             switch (tb.y) {                                // uniform over the CTA
-            case 1: rq_view<1>(acc, wrec, T, px, vw.y); break;
-            case 2: rq_view<2>(acc, wrec, T, px, vw.y); break;
-            case 3: rq_view<3>(acc, wrec, T, px, vw.y); break;
-            case 4: rq_view<4>(acc, wrec, T, px, vw.y); break;
-            case 5: rq_view<5>(acc, wrec, T, px, vw.y); break;
-            case 6: rq_view<6>(acc, wrec, T, px, vw.y); break;
-            case 7: rq_view<7>(acc, wrec, T, px, vw.y); break;
-            default: rq_view<8>(acc, wrec, T, px, vw.y); break;
+            case 1: rq_view<1>(acc, wrec, T, px); break;
+            case 2: rq_view<2>(acc, wrec, T, px); break;
+            case 3: rq_view<3>(acc, wrec, T, px); break;
+            case 4: rq_view<4>(acc, wrec, T, px); break;
+            case 5: rq_view<5>(acc, wrec, T, px); break;
+            case 6: rq_view<6>(acc, wrec, T, px); break;
+            case 7: rq_view<7>(acc, wrec, T, px); break;
+            default: rq_view<8>(acc, wrec, T, px); break;
             }
         }
 #pragma unroll
@@ -603,7 +616,7 @@ static int launch_refine_hq(const float *coef, int M, int S, int T, int nb, cons
         if (px > max_px) max_px = px;
     }
     for (int i = 0; i < M; ++i) { ctl.lo[i] = qd.lo[i]; ctl.hi[i] = qd.hi[i]; ctl.woff[i] = qd.woff[i]; ctl.W[i] = qd.W[i]; }
-    const size_t smem = max_px * 3 * RQ_ROWS * sizeof(float);
+    const size_t smem = max_px * RQ_PIX * sizeof(float);
     if (smem > 220 * 1024 || (S + RQ_ROWS - 1) / RQ_ROWS > 65535) return PCB_ERR_UNSUPPORTED;
     PCB_CUDA(cudaFuncSetAttribute(refine_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((T + RQ_XC - 1) / RQ_XC, (S + RQ_ROWS - 1) / RQ_ROWS, M);
