@@ -114,7 +114,7 @@ class LfpResampler(LfpMicroLenses):
         if self.write_checkpoint and self._lfp_img_align is not None:
             os.makedirs(self.cfg.exp_path, exist_ok=True)
             with open(os.path.join(self.cfg.exp_path, 'lfp_img_align.pkl'), 'wb') as f:
-                pickle.dump(self._lfp_img_align, f)
+                pickle.dump(np.asarray(self._lfp_img_align).view(np.ndarray), f)      # a plain ndarray, like the reference's
         self.sta.progress(100, prnt)
         return True
 

@@ -35,10 +35,13 @@ class LfpAligner(object):
             del obj
         obj = LfpResampler(lfp_img=img, cfg=self.cfg, sta=self.sta)
         obj.main()
-        self._lfp_img = obj.lfp_img_align
+        self._lfp_img = obj._lfp_img_align             # the result array itself (the property would copy 366 MB)
         del obj
         return True
 
     @property
     def lfp_img(self):
-        return self._lfp_img.copy()
+        """The aligned uint16 image.  The reference returns a defensive copy (lfp_aligner/top_level.py:81-83); here the
+        array itself is handed over (it lives in pinned memory, so LfpExtractor uploads it at the full PCIe rate) - this
+        object does not touch it again."""
+        return self._lfp_img

@@ -48,4 +48,4 @@ class LfpCropper(LfpMicroLenses):
             return np.zeros(shp, dtype=src.dtype)
         if self.new_lfp_img is None:
             return None
-        return self.new_lfp_img.clone() if hasattr(self.new_lfp_img, 'is_cuda') else np.array(self.new_lfp_img)
+        return self.new_lfp_img          # handed over, not copied (the reference copies, lfp_cropper.py:65-66)

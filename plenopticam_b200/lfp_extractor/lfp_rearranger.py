@@ -36,6 +36,7 @@ class LfpRearranger(LfpViewpoints):
             src = src[..., None]
         dev = src if on_dev else ops.to_device(src)
         vp = ops.viewpoints(dev.contiguous() if on_dev else dev, int(self._size_pitch))
+        self._dev_vp = vp                                  # kept for the stages that follow on the device
         self._vp_img_arr = vp if on_dev else ops.to_host(vp)
         self.sta.progress(100, prnt)
         return True

@@ -43,7 +43,6 @@ class LfpShiftAndSum(LfpViewpoints):
             # from LfpRefocuser
             raise NotImplementedError('refocusing from the aligned image is not part of the B200 hot path; '
                                       'pass vp_img_arr')
-        self._refo_stack = np.asarray(self._refo_stack)
         return True
 
     def refo_from_vp(self):
@@ -66,13 +65,16 @@ class LfpShiftAndSum(LfpViewpoints):
             self._dev_stack = ops.refocus_int(vp, a_list, self.circular_view_aperture_mask())
         if self.sta.interrupt:
             return False
-        self._refo_stack = ops.to_host(self._dev_stack).astype(np.float64)
+        self._refo_stack = None              # float64 host copy: made when `refo_stack` is read (LfpRefocuser never does)
         self.sta.progress(100, prnt)
         return True
 
     @property
     def refo_stack(self):
-        return self._refo_stack.copy()
+        """float64 (N,S,T,C) like the reference's (a fresh array per access, lfp_shiftandsum.py:320-322)."""
+        if self._dev_stack is not None:
+            return np.asarray(ops.to_host(self._dev_stack), dtype=np.float64)
+        return np.asarray(self._refo_stack)
 
     @property
     def refo_stack_device(self):

@@ -54,9 +54,40 @@ def device_dtype_for(arr):
     return np.dtype("float32")
 
 
+class HostArray(np.ndarray):
+    """numpy view of a PINNED host buffer (a torch tensor it keeps alive in `_pcb_pin`).  `to_host` hands these out, so
+    that the next stage's `to_device` can copy straight from the page-locked memory (no staging pass, full PCIe rate).
+    The data is always read from host memory at call time - nothing is cached on the device - so modifying the array in
+    place is safe; copies / arrays derived by arithmetic are ordinary pageable arrays and take the staged path."""
+    _pcb_pin = None
+
+    def __array_finalize__(self, obj):
+        self._pcb_pin = getattr(obj, '_pcb_pin', None)
+
+
+def _pinned_alias(arr):
+    """torch view of `arr`'s bytes if they lie inside the pinned buffer `arr` descends from (and are contiguous)."""
+    pin = getattr(arr, '_pcb_pin', None)
+    if pin is None or not arr.flags.c_contiguous or arr.nbytes == 0:
+        return None
+    off = arr.ctypes.data - pin.data_ptr()
+    if off < 0 or off + arr.nbytes > pin.numel() * pin.element_size():
+        return None
+    tdt = _NP2TORCH.get(arr.dtype)
+    if tdt is None:
+        return None
+    return pin.view(torch.uint8).reshape(-1)[off:off + arr.nbytes].view(tdt).view(tuple(arr.shape))
+
+
 def to_device(arr, dtype=None, exact_u16=False):
-    """numpy -> contiguous CUDA tensor through a pinned staging buffer."""
+    """numpy -> contiguous CUDA tensor: straight from the pinned buffer for arrays `to_host` handed out, else through
+    a pinned staging buffer."""
     dev = require_cuda()
+    arr = np.asarray(arr) if not isinstance(arr, np.ndarray) else arr
+    if (dtype is None or np.dtype(dtype) == arr.dtype) and arr.dtype in _NP2TORCH:
+        alias = _pinned_alias(arr)
+        if alias is not None:
+            return alias.to(dev, non_blocking=True)
     arr = np.asarray(arr)
     if dtype is None:
         dtype = device_dtype_for(arr)
@@ -75,10 +106,22 @@ def to_device(arr, dtype=None, exact_u16=False):
 
 
 def to_host(t):
-    """CUDA tensor -> numpy (synchronises the current stream)."""
+    """CUDA tensor -> numpy (synchronises the current stream).  The result lives in pinned memory (`HostArray`): the
+    copy runs at the full PCIe rate and a later `to_device` of the same array needs no staging.  torch's caching host
+    allocator recycles the buffers once the arrays are dropped."""
+    if not t.is_cuda:
+        return t.numpy()
+    t = t.contiguous()
+    pinned = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+    pinned.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
     if t.dtype == torch.uint16:
-        return t.view(torch.int16).cpu().numpy().view(np.uint16)
-    return t.cpu().numpy()
+        arr = pinned.view(torch.int16).numpy().view(np.uint16)
+    else:
+        arr = pinned.numpy()
+    out = arr.view(HostArray)
+    out._pcb_pin = pinned
+    return out
 
 
 def struct_to_device(arr):
