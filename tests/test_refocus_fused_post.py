@@ -91,5 +91,6 @@ def test_pipeline_fused_equals_unfused(cuda):
     for fuse in (True, False):
         pipe = LightFieldPipeline(cent, (H, W, 3), np.uint16, 9, 'hex', ran_refo=(-4, 4), fuse_post=fuse)
         outs.append(torch.from_numpy(pipe.run(raw).copy()))
-        assert pipe.refocus_plan.fused is (True if fuse else None)
+        assert pipe.gather_fused is True                      # the stack is read straight from the aligned image
+        assert pipe.refocus_plan_al.fused is (True if fuse else None)
     assert torch.equal(outs[0], outs[1])
