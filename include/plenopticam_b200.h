@@ -163,6 +163,13 @@ int pcb_refocus_int_srgb_aligned(const void *aligned, int dtype, int Ma, int M, 
 int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C,
                            const int32_t *a_list_dev, int N, const uint8_t *view_zeroed_dev,
                            float *out, pcb_minmax_t *mm, void *stream);
+/* LfpShiftAndSum.refo_from_scratch (lfp_refocuser/lfp_shiftandsum.py:141-221; the alternate entry taken when the class
+ * is given the aligned image instead of the viewpoints and opt_refi is off): the same shifts a (c0 - j), a (c0 - i), but
+ * samples outside the light field count as ZERO ("leave pixel empty", :180-186,:203-206) and, as that method never calls
+ * circular_view_aperture, the caller passes an all-zero mask.  Direct kernel, device-resident control arrays. */
+int pcb_refocus_int_zero(const void *vp, int dtype, int M, int S, int T, int C,
+                         const int32_t *a_list_dev, int N, const uint8_t *view_zeroed_dev,
+                         float *out, pcb_minmax_t *mm, void *stream);
 
 /* pcb_refocus_int with LfpRefocuser.shift_and_sum's colour management (lfp_refocuser/top_level.py:68-70) fused into the
  * epilogue — the "fused normalisation and contrast clipping" form of the stack: out receives

@@ -385,6 +385,39 @@ def refocus_int(vp, ran_refo, M):
     return np.asarray([refocus_int_slice(vp64, a, M) for a in range(*ran_refo)])
 
 
+def refocus_from_scratch(aligned, ran_refo, M):
+    """lfp_shiftandsum.py:141-221 (`refo_from_scratch`, the alternate used when only the aligned image is given and
+    opt_refi is off).  Horizontal pass :168-186: hor[y, j] = sum_u img[y, u + s M] with s = j + a (c - i) [- overlap if
+    a >= 0], i = u - c, EMPTY (zero) where the index leaves the image; vertical pass :189-206 likewise; symmetric crop by
+    overlap / 2 (:209-210).  After the crop, output pixel (h, j) sums img[(h + a (c - v)) M + v, (j + a (c - u)) M + u]
+    over ALL views (u, v) - no circular aperture (main() only applies it when vp_img_arr is given, :59) - i.e. the shifts
+    of refo_from_vp with zeros instead of edge replication.  Returns float64 (N, H, J, P)."""
+    img = np.asarray(aligned)
+    if img.ndim == 2:
+        img = img[..., None]
+    H, J = img.shape[0] // M, img.shape[1] // M
+    img = img[:H * M, :J * M] / M                                   # :159 (a float32 image is divided in float32)
+    vp = compose_viewpoints(img, M)                                 # vp[v, u, h, j] = img[h M + v, j M + u]
+    c = int((M - 1) / 2)
+    stack = []
+    for a in range(*ran_refo):
+        hor = np.zeros((M, H, J, img.shape[2]))                     # per view row v: sum over u (the reference's order)
+        for v in range(M):
+            for u in range(M):
+                d = a * (c - u)
+                lo, hi = max(0, -d), min(J, J - d)
+                if hi > lo:
+                    hor[v, :, lo:hi] += vp[v, u, :, lo + d:hi + d]
+        acc = np.zeros((H, J, img.shape[2]))
+        for v in range(M):
+            d = a * (c - v)
+            lo, hi = max(0, -d), min(H, H - d)
+            if hi > lo:
+                acc[lo:hi] += hor[v, lo + d:hi + d]
+        stack.append(acc)
+    return np.asarray(stack)
+
+
 def spline_resize_matrix(n_in, n_out):
     """misc/data_proc.py:57-92 — `interp2d(kind='cubic')` == FITPACK interpolating bicubic spline (s=0)
     == separable not-a-knot cubic spline.  Returns the (n_out, n_in) matrix W such that

@@ -142,6 +142,7 @@ _SIGNATURES = {
     "pcb_refocus_int_srgb_aligned": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, C.c_double, C.c_double, _vp,
                                           _vp, _vp, _vp, _vp, _vp]),
     "pcb_refocus_int_direct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "pcb_refocus_int_zero": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refi_prefilter": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refi_prefilter_toeplitz": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp,
                                          _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),

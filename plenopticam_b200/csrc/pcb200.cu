@@ -361,6 +361,20 @@ int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
 
+// LfpShiftAndSum.refo_from_scratch (lfp_shiftandsum.py:141-221): zero outside the light field, every view.
+int pcb_refocus_int_zero(const void *vp, int dtype, int M, int S, int T, int C, const int32_t *a_list_dev, int N,
+                         const uint8_t *view_zeroed_dev, float *out, pcb_minmax_t *mm, void *stream) {
+    PCB_REQUIRE(vp != nullptr && a_list_dev != nullptr && view_zeroed_dev != nullptr && out != nullptr, "pointers");
+    PCB_REQUIRE(M > 0 && S > 0 && T > 0 && C > 0 && N > 0 && N <= 65535 && M % 2 == 1, "sizes, odd M");
+    cudaStream_t st = as_stream(stream);
+    switch (dtype) {
+    case PCB_U16: return launch_refocus_int<uint16_t>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st, true);
+    case PCB_F32: return launch_refocus_int<float>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st, true);
+    case PCB_U8:  return launch_refocus_int<uint8_t>(vp, M, S, T, C, a_list_dev, N, view_zeroed_dev, out, mm, st, true);
+    }
+    return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
+}
+
 int pcb_refi_prefilter(const void *vp, int dtype, int M, int S, int T, int C, const float *py_vals,
                        const int32_t *py_first, int Kpy, const float *px_vals, const int32_t *px_first, int Kpx,
                        const uint8_t *view_zeroed, float *tmp, float *coef, void *stream) {

@@ -20,7 +20,11 @@ __device__ __forceinline__ float finish_acc(float acc, int M) { return acc / (fl
 constexpr int RF_THREADS = 256;
 constexpr int RF_EPT = 8;   // elements per thread: one CTA covers 2048 consecutive (x,c) elements of a row
 
-template <typename T, int CT>
+// ZERO: samples outside the light field count as 0 instead of replicating the edge - the boundary rule of
+// LfpShiftAndSum.refo_from_scratch (lfp_refocuser/lfp_shiftandsum.py:141-221: "if index exceeds image boundaries, leave
+// pixel empty"), which also sums every view (no circular aperture) and crops the result symmetrically, so that its
+// output pixel (h, j) gathers exactly the shifts a (c0 - v), a (c0 - u) of refo_from_vp.
+template <typename T, int CT, bool ZERO = false>
 __global__ void __launch_bounds__(RF_THREADS)
 refocus_int_kernel(const T *__restrict__ vp, const int32_t *__restrict__ a_list,
                    const uint8_t *__restrict__ view_zeroed, float *__restrict__ out,
@@ -47,6 +51,7 @@ refocus_int_kernel(const T *__restrict__ vp, const int32_t *__restrict__ a_list,
     const size_t view_stride = (size_t)S * Tn * C;
     for (int j = 0; j < M; ++j) {
         int r = y + a * (c0 - j);
+        if (ZERO && (r < 0 || r > S - 1)) continue;
         r = max(0, min(S - 1, r));
         for (int i = 0; i < M; ++i) {
             if (view_zeroed[j * M + i]) continue;
@@ -54,8 +59,10 @@ refocus_int_kernel(const T *__restrict__ vp, const int32_t *__restrict__ a_list,
             const T *rowp = vp + (size_t)(j * M + i) * view_stride + (size_t)r * Tn * C;
 #pragma unroll
             for (int k = 0; k < RF_EPT; ++k) {
-                const int xs = max(0, min(Tn - 1, xk[k] + dx));
-                acc[k] += (Acc)__ldg(rowp + xs * C + ck[k]);
+                const int xr = xk[k] + dx;
+                const int xs = max(0, min(Tn - 1, xr));
+                const Acc v = (Acc)__ldg(rowp + xs * C + ck[k]);
+                acc[k] += (ZERO && xr != xs) ? (Acc)0 : v;
             }
         }
     }
@@ -77,9 +84,18 @@ refocus_int_kernel(const T *__restrict__ vp, const int32_t *__restrict__ a_list,
 
 template <typename T>
 static int launch_refocus_int(const void *vp, int M, int S, int Tn, int C, const int32_t *a_list, int N,
-                              const uint8_t *view_zeroed, float *out, pcb_minmax_t *mm, cudaStream_t st) {
+                              const uint8_t *view_zeroed, float *out, pcb_minmax_t *mm, cudaStream_t st,
+                              bool zero_boundary = false) {
     const int ne = Tn * C;
     dim3 grid(S, N, (ne + RF_THREADS * RF_EPT - 1) / (RF_THREADS * RF_EPT)), block(RF_THREADS);
+    if (zero_boundary) {
+        if (C == 3)
+            refocus_int_kernel<T, 3, true><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C, mm);
+        else
+            refocus_int_kernel<T, 0, true><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C, mm);
+        PCB_LAUNCH_OK();
+        return PCB_OK;
+    }
     if (C == 3)
         refocus_int_kernel<T, 3><<<grid, block, 0, st>>>((const T *)vp, a_list, view_zeroed, out, M, S, Tn, C, mm);
     else if (C == 1)

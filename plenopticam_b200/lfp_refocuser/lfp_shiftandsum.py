@@ -39,10 +39,14 @@ class LfpShiftAndSum(LfpViewpoints):
             if self.refo_from_vp() is False:
                 return False
         elif self.lfp_img_align is not None:
-            # refo_from_scratch* (lfp_shiftandsum.py:141-304) are `pragma: no cover` alternates never reached
-            # from LfpRefocuser
-            raise NotImplementedError('refocusing from the aligned image is not part of the B200 hot path; '
-                                      'pass vp_img_arr')
+            # the alternates taken when only the aligned image is given (lfp_shiftandsum.py:62-68; `pragma: no cover`
+            # upstream, never reached from LfpRefocuser: SURVEY §8a row a11)
+            if self.cfg.params[self.cfg.opt_refi]:
+                raise NotImplementedError('refo_from_scratch_upsample (lfp_shiftandsum.py:223-304: linear ramps between '
+                                          'neighbouring micro-image pixels) is not offered; pass vp_img_arr for the '
+                                          'refinement path')
+            if self.refo_from_scratch() is False:
+                return False
         return True
 
     def refo_from_vp(self):
@@ -66,6 +70,27 @@ class LfpShiftAndSum(LfpViewpoints):
         if self.sta.interrupt:
             return False
         self._refo_stack = None              # float64 host copy: made when `refo_stack` is read (LfpRefocuser never does)
+        self.sta.progress(100, prnt)
+        return True
+
+    def refo_from_scratch(self):
+        """lfp_shiftandsum.py:141-221: every view, zeros outside the light field (no aperture mask, no edge replication)."""
+        prnt = self.cfg.params[self.cfg.opt_prnt]
+        self.sta.progress(0, prnt)
+        M = int(self.cfg.params[self.cfg.ptc_leng])
+        img = self.lfp_img_align
+        on_dev = hasattr(img, 'is_cuda')
+        if not on_dev:
+            img = np.asarray(img)
+            img = ops.to_device(img if img.ndim == 3 else img[..., None], exact_u16=True)
+        elif img.dim() == 2:
+            img = img[..., None].contiguous()
+        rows, cols = int(img.shape[0]), int(img.shape[1])
+        img = img[:(rows // M) * M, :(cols // M) * M].contiguous()       # J = int(n / patch_len), H = int(m / patch_len)
+        self._dev_stack = ops.refocus_from_scratch(img, M, range(*self.cfg.params[self.cfg.ran_refo]))
+        if self.sta.interrupt:
+            return False
+        self._refo_stack = None
         self.sta.progress(100, prnt)
         return True
 

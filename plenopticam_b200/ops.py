@@ -411,6 +411,22 @@ def refocus_int_direct(vp, a_list, view_zeroed=None, out=None, mm=None):
     return out
 
 
+def refocus_from_scratch(aligned, M, a_list, out=None):
+    """LfpShiftAndSum.refo_from_scratch (lfp_refocuser/lfp_shiftandsum.py:141-221) for an aligned image (H*M, J*M, P):
+    shift-and-sum over ALL views with zeros outside the light field; float32 (N, H, J, P)."""
+    _chk_dev(aligned)
+    vp = viewpoints(aligned, int(M))
+    Mi, _, S, T, Cn = (int(v) for v in vp.shape)
+    a_host = np.ascontiguousarray(np.asarray(list(a_list), dtype=np.int32))
+    a_dev = torch.from_numpy(a_host).to(vp.device)
+    z_dev = torch.zeros(Mi * Mi, dtype=torch.uint8, device=vp.device)
+    if out is None:
+        out = torch.empty((int(a_host.size), S, T, Cn), dtype=torch.float32, device=vp.device)
+    nat.check(nat.lib().pcb_refocus_int_zero(_ptr(vp), _pcb_dtype(vp), Mi, S, T, Cn, _ptr(a_dev), int(a_host.size),
+                                             _ptr(z_dev), _ptr(out), C.c_void_p(0), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 # post-processing
 # ------------------------------------------------------------------------------------------------------

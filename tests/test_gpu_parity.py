@@ -419,3 +419,24 @@ def test_contrast_bounds_single_launch_equals_numpy_percentiles(cuda):
         two = np.array([ops.percentile(ops.to_device(x), [0.005], luma=True).cpu().numpy()[0],
                         ops.percentile(ops.to_device(x), [99.9]).cpu().numpy()[0]])
         assert np.array_equal(got, two)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["refocus_scratch_u16", "refocus_scratch_m7_u16", "refocus_scratch_f32"])
+def test_shiftandsum_from_scratch_vs_reference_golden(cuda, name):
+    """LfpShiftAndSum given the aligned image instead of the viewpoints (refo_from_scratch,
+    lfp_shiftandsum.py:141-221): every view, zeros outside the light field."""
+    from plenopticam_b200.lfp_refocuser import LfpShiftAndSum
+    g = golden(name)
+    cfg, sta = make_cfg(M=int(g["M"]), ran_refo=[int(v) for v in g["ran_refo"]])
+    obj = LfpShiftAndSum(lfp_img_align=g["aligned"], cfg=cfg, sta=sta)
+    assert obj.main() is True
+    got = obj.refo_stack
+    assert got.dtype == np.float64 and got.shape == g["stack"].shape
+    if g["aligned"].dtype == np.uint16:
+        assert np.array_equal(got, g["stack"].astype(np.float32).astype(np.float64))       # integer path: exact
+    else:
+        assert np.abs(got - g["stack"]).max() <= 2e-6 * np.abs(g["stack"]).max()
+    cfg.params[cfg.opt_refi] = True
+    with pytest.raises(NotImplementedError):
+        LfpShiftAndSum(lfp_img_align=g["aligned"], cfg=cfg, sta=sta).main()

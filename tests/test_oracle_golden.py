@@ -84,3 +84,12 @@ def test_refocuser_postprocess_matches_reference():
 def test_aperture_mask_counts():
     assert int((~onp.aperture_mask(15)).sum()) == 177                     # 177 of 225 views kept
     assert int((~onp.aperture_mask(9)).sum()) == 69
+
+
+@pytest.mark.parametrize("name", ["refocus_scratch_u16", "refocus_scratch_m7_u16", "refocus_scratch_f32"])
+def test_refocus_from_scratch_matches_reference(name):
+    """LfpShiftAndSum.refo_from_scratch of the unmodified reference (oracle/gen_golden_scratch.py)."""
+    g = golden(name)
+    st = onp.refocus_from_scratch(g["aligned"], tuple(int(v) for v in g["ran_refo"]), int(g["M"]))
+    assert st.shape == g["stack"].shape
+    assert np.abs(st - g["stack"]).max() <= 1e-12 * np.abs(g["stack"]).max()
