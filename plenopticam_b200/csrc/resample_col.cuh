@@ -59,16 +59,16 @@ __device__ __forceinline__ int rc_stage(const uint16_t *__restrict__ raw, size_t
                 uint32_t v[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int m = base + u * 32;
-                    if (m < nwr) v[u] = __ldg(wsrc + m);
+                    const int mm_ = base + u * 32;
+                    if (mm_ < nwr) v[u] = __ldg(wsrc + mm_);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int m = base + u * 32;
-                    if (m < nwr) {
+                    const int mm_ = base + u * 32;
+                    if (mm_ < nwr) {
                         const float2 f2 = make_float2(__uint_as_float(__byte_perm(v[u], 0x4B000000u, 0x7610)) - 8388608.0f,
                                                       __uint_as_float(__byte_perm(v[u], 0x4B000000u, 0x7632)) - 8388608.0f);
-                        dst[m] = f2;
+                        dst[mm_] = f2;
                         if (TRACK) {
                             smn = fminf(smn, fminf(f2.x, f2.y));
                             smx = fmaxf(smx, fmaxf(f2.x, f2.y));
@@ -136,34 +136,59 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
         g_mx = key_to_float(*reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax));
     }
 
-    if (tid == 0) {
+    // Tables of the tile, by warp 0, in ONE global-memory latency: the two hex-column entries that bound the source
+    // lenses and, speculatively, the 32 lenses starting just below where the first one must be (x0(k) = floor(k LX /
+    // (Xs - 1) + parity / 2), so a float estimate is off by one at most); the exact window is then picked out of the
+    // speculative one with shuffles.  One barrier instead of two dependent load-and-barrier rounds.
+    if (tid < 32) {
+        const int lane = tid;
         int xa = k0, xb = k0 + kn - 1;
+        int xa_est = k0;
+        pcb_hexcol_t h;
+        h.x0 = h.x1 = 0; h.w = 0.f; h.reserved = 0;
         if (hc) {
-            xa = hc[k0].x0;
-            xb = hc[k0 + kn - 1].x1;
-            if (hc[k0 + kn - 1].w == 0.f) xb = hc[k0 + kn - 1].x0;
+            xa_est = max((int)floorf((float)k0 * (float)p.LX / (float)max(p.Xs - 1, 1)) - 1, 0);
+            if (lane < 2) h = hc[lane == 0 ? k0 : k0 + kn - 1];
         }
-        s_src[0] = xa;
-        s_src[1] = xb;
-        s_box[0] = INT32_MAX; s_box[1] = INT32_MIN; s_box[2] = INT32_MAX; s_box[3] = INT32_MIN;
-        s_smm[0] = 0x7f800000; s_smm[1] = 0;
-        s_ninv = 0;
+        const int xs = min(xa_est + lane, p.LX - 1);
+        pcb_lens_t Ls = p.lens[ly * p.LX + xs];                      // in flight together with the hex entries
+        if (hc) {
+            xa = __shfl_sync(0xffffffffu, h.x0, 0);
+            const int bx0 = __shfl_sync(0xffffffffu, h.x0, 1), bx1 = __shfl_sync(0xffffffffu, h.x1, 1);
+            const float bw = __shfl_sync(0xffffffffu, h.w, 1);
+            xb = bw == 0.f ? bx0 : bx1;
+        }
+        const int nsrc_w = xb - xa + 1;
+        // lane l owns source lens xa + l: held by lane (xa + l - xa_est) of the speculative load when that is in range
+        const int from = xa + lane - xa_est;
+        pcb_lens_t L;
+        L.oy = __shfl_sync(0xffffffffu, Ls.oy, from & 31);
+        L.ox = __shfl_sync(0xffffffffu, Ls.ox, from & 31);
+        L.wy = __shfl_sync(0xffffffffu, Ls.wy, from & 31);
+        L.wx = __shfl_sync(0xffffffffu, Ls.wx, from & 31);
+        const bool mine = lane < nsrc_w && nsrc_w <= RC_MAX_SRC;
+        if (mine && (from < 0 || from > 31 || xa_est + from > p.LX - 1)) L = p.lens[ly * p.LX + xa + lane];
+        const bool valid = mine && L.oy != PCB_LENS_INVALID;
+        int b0 = valid ? L.oy : INT32_MAX, b1 = valid ? L.oy : INT32_MIN;
+        int b2 = valid ? L.ox : INT32_MAX, b3 = valid ? L.ox : INT32_MIN;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            b0 = min(b0, __shfl_xor_sync(0xffffffffu, b0, o)); b1 = max(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+            b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o)); b3 = max(b3, __shfl_xor_sync(0xffffffffu, b3, o));
+        }
+        const unsigned inv = __ballot_sync(0xffffffffu, mine && !valid);
+        if (mine) s_lens[lane] = L;
+        if (lane == 0) {
+            s_src[0] = xa; s_src[1] = xb;
+            s_box[0] = b0; s_box[1] = b1; s_box[2] = b2; s_box[3] = b3;
+            s_smm[0] = 0x7f800000; s_smm[1] = 0;
+            s_ninv = __popc(inv);
+        }
     }
     __syncthreads();
     const int xa = s_src[0];
     const int nsrc = s_src[1] - xa + 1;
     const bool lens_in_smem = nsrc <= RC_MAX_SRC;
-    if (lens_in_smem && tid < nsrc) {
-        const pcb_lens_t L = p.lens[ly * p.LX + xa + tid];
-        s_lens[tid] = L;
-        if (L.oy != PCB_LENS_INVALID) {
-            atomicMin(&s_box[0], L.oy); atomicMax(&s_box[1], L.oy);
-            atomicMin(&s_box[2], L.ox); atomicMax(&s_box[3], L.ox);
-        } else {
-            atomicAdd(&s_ninv, 1);
-        }
-    }
-    __syncthreads();
     const int ymin = s_box[0], xmin = s_box[2];
     const int R = s_box[1] - ymin + M + 1;               // staged rows
     const int Wt = (s_box[3] - xmin + M + 1) * 3;        // staged elements per row
