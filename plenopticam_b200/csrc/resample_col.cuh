@@ -96,6 +96,49 @@ __device__ __forceinline__ int rc_stage(const uint16_t *__restrict__ raw, size_t
     return 0;
 }
 
+// ---- pre-pass of the min/max pass: min / max of the raw exposure per block of RB_ROWS x RB_PX pixels -----------------
+// A pure streaming pass (packed 16-bit min / max, one entry per warp).  With the table a tile of the min/max pass that
+// cannot move the global bounds is recognised from <= 12 table entries, before any of its raw rows is staged.
+constexpr int RB_ROWS = 16;
+constexpr int RB_PX = 128;
+constexpr int RB_WORDS = RB_PX * 3 / 2;       // 32-bit words per block row (uint16 RGB)
+
+__global__ void __launch_bounds__(256)
+rc_block_minmax_kernel(const uint16_t *__restrict__ raw, int H, int W, uint32_t *__restrict__ blk, int nbx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bx = blockIdx.x * 8 + warp, by = blockIdx.y;
+    if (bx >= nbx) return;
+    const int y0 = by * RB_ROWS, x0 = bx * RB_PX;
+    const int nrow = min(RB_ROWS, H - y0);
+    const int nwords = min(RB_PX, W - x0) * 3 / 2;         // W * 3 even and x0 * 3 even: whole words
+    const int tail = (min(RB_PX, W - x0) * 3) & 1;         // an odd element count leaves one trailing half word
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int r = 0; r < nrow; ++r) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + ((size_t)(y0 + r) * W + x0) * 3);
+#pragma unroll
+        for (int u = 0; u < RB_WORDS / 32; ++u) {
+            const int m = lane + u * 32;
+            if (m < nwords) {
+                const uint32_t v = __ldg(src + m);
+                mn = __vminu2(mn, v);
+                mx = __vmaxu2(mx, v);
+            }
+        }
+        if (tail && lane == 0) {
+            const uint32_t v = (uint32_t)__ldg(raw + ((size_t)(y0 + r) * W + x0) * 3 + 2 * nwords) * 0x10001u;
+            mn = __vminu2(mn, v);
+            mx = __vmaxu2(mx, v);
+        }
+    }
+    uint32_t lo = min(mn & 0xffffu, mn >> 16), hi = max(mx & 0xffffu, mx >> 16);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) blk[(size_t)by * nbx + bx] = lo | (hi << 16);
+}
+
 template <int MODE>
 __device__ __forceinline__ void rc_emit(const ResampleOut<MODE> &out, size_t o, float val, float &mn, float &mx) {
     out.put(o, val);
@@ -113,6 +156,7 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
     __shared__ int s_src[2];      // first / last source lens column
     __shared__ int s_smm[2];      // min / max of the staged samples (bit patterns of non-negative floats order like ints)
     __shared__ int s_ninv;        // invalid source lenses of this CTA
+    __shared__ int s_skip;        // min/max pass: the raw block table already shows that this tile cannot matter
 
     const int M = MT ? MT : p.M;
     const int ly = blockIdx.y;
@@ -178,14 +222,35 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
         }
         const unsigned inv = __ballot_sync(0xffffffffu, mine && !valid);
         if (mine) s_lens[lane] = L;
+        int skip_now = 0;
+        if (may_skip && p.blk != nullptr && inv == 0u && b1 != INT32_MIN && nsrc_w <= RC_MAX_SRC) {
+            // raw blocks the tile's box [b0, b1 + M] x [b2, b3 + M] touches (a superset of what would be staged)
+            const int by0 = b0 / RB_ROWS, by1 = min((b1 + M + 1) / RB_ROWS, p.nby - 1);
+            const int bx0 = b2 / RB_PX, bx1 = min((b3 + M + 1) / RB_PX, p.nbx - 1);
+            const int nbw = bx1 - bx0 + 1, nb = (by1 - by0 + 1) * nbw;
+            uint32_t lo = 0xffffu, hi = 0u;
+            for (int e = lane; e < nb; e += 32) {
+                const uint32_t v = __ldg(p.blk + (size_t)(by0 + e / nbw) * p.nbx + bx0 + e % nbw);
+                lo = min(lo, v & 0xffffu);
+                hi = max(hi, v >> 16);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            skip_now = ((float)lo * (1.f - RC_SKIP_EPS) > g_mn && (float)hi * (1.f + RC_SKIP_EPS) < g_mx) ? 1 : 0;
+        }
         if (lane == 0) {
             s_src[0] = xa; s_src[1] = xb;
             s_box[0] = b0; s_box[1] = b1; s_box[2] = b2; s_box[3] = b3;
             s_smm[0] = 0x7f800000; s_smm[1] = 0;
             s_ninv = __popc(inv);
+            s_skip = skip_now;
         }
     }
     __syncthreads();
+    if (MODE == RS_MINMAX && s_skip) return;                 // uniform over the CTA
     const int xa = s_src[0];
     const int nsrc = s_src[1] - xa + 1;
     const bool lens_in_smem = nsrc <= RC_MAX_SRC;
@@ -308,6 +373,14 @@ static int launch_resample_col(const ResampleArgs &a_in, float *out_f32, uint16_
                                const pcb_minmax_t *mm_ro, cudaStream_t st) {
     ResampleArgs a = a_in;
     a.skip = (getenv("PCB_RESAMPLE_NOSKIP") && atoi(getenv("PCB_RESAMPLE_NOSKIP"))) ? 0 : 1;
+    if (MODE == RS_MINMAX && a.skip && a.blk != nullptr && (reinterpret_cast<uintptr_t>(a.raw) & 3) == 0 &&
+        ((a.W * 3) & 1) == 0 && !(getenv("PCB_RESAMPLE_NOBLOCKS") && atoi(getenv("PCB_RESAMPLE_NOBLOCKS")))) {
+        rc_block_minmax_kernel<<<dim3((a.nbx + 7) / 8, a.nby), 256, 0, st>>>(reinterpret_cast<const uint16_t *>(a.raw), a.H,
+                                                                            a.W, const_cast<uint32_t *>(a.blk), a.nbx);
+        PCB_LAUNCH_OK();
+    } else {
+        a.blk = nullptr;
+    }
     const size_t smem = (size_t)RC_ROWS * RC_TS * sizeof(float);
     dim3 block(RC_THREADS), grid((a.Xs + RC_KT - 1) / RC_KT, a.LY);
     if (a.M == 15) {
