@@ -348,9 +348,7 @@ def main():
             k = 0
             if ev: ev[k].record(stream); k += 1
             _native.check(L.pcb_minmax_reset(p(pipe.mm_align), st))
-            prune = pipe.tabs.prune_scratch(raw)
-            _native.check(L.pcb_resample_minmax_pruned(*(pipe.tabs._args(raw, pipe.flip) +
-                                                         [p(pipe.mm_align), p(prune), prune.numel(), st])))
+            _native.check(L.pcb_resample_minmax(*(pipe.tabs._args(raw, pipe.flip) + [p(pipe.mm_align), st])))
             if ev: ev[k].record(stream); k += 1
             _native.check(L.pcb_resample_u16(*(pipe.tabs._args(raw, pipe.flip) + [p(pipe.mm_align), p(pipe.aligned), st])))
             if ev: ev[k].record(stream); k += 1
@@ -404,7 +402,7 @@ def main():
     if fuse_gather:
         abytes["refocus_int"] = abytes["refocus_int_from_aligned"]
     stage_gbs = {nm: abytes[nm] / (stage_ms[nm] * 1e-3) / 1e9 for nm in stage_names}
-    launches_per_step = 2 + 3 + (0 if fuse_gather else 1) + (5 if fuse_post else 2 + 2)     # resets, block min/max + 2 resample passes, ...
+    launches_per_step = 2 + 2 + (0 if fuse_gather else 1) + (5 if fuse_post else 2 + 2)
 
     extras = {}
     if not args.no_extras:

@@ -88,15 +88,6 @@ int pcb_resample_minmax(const void *raw, int raw_dtype, int H, int W, int C,
                         const pcb_lens_t *lens, int LY, int LX, int M,
                         int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,
                         pcb_minmax_t *mm, void *stream);
-/* pcb_resample_minmax with a pre-pass: the min / max of the raw exposure per block of 16 x 128 pixels goes to `scratch`
- * (>= pcb_resample_prune_scratch_bytes(H, W, C) bytes), and a tile of the min/max pass whose blocks lie strictly inside
- * the running bounds is dropped before any of its raw rows is read (every output is a convex combination of raw
- * samples).  The bounds are exactly those of pcb_resample_minmax. */
-int64_t pcb_resample_prune_scratch_bytes(int H, int W, int C);
-int pcb_resample_minmax_pruned(const void *raw, int raw_dtype, int H, int W, int C,
-                               const pcb_lens_t *lens, int LY, int LX, int M, int pattern,
-                               const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,
-                               pcb_minmax_t *mm, void *scratch, int64_t scratch_bytes, void *stream);
 int pcb_resample_f32(const void *raw, int raw_dtype, int H, int W, int C,
                      const pcb_lens_t *lens, int LY, int LX, int M,
                      int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,

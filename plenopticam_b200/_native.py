@@ -125,8 +125,6 @@ _SIGNATURES = {
     "pcb_minmax_reset": (_i, [_vp, _vp]),
     "pcb_minmax_f32": (_i, [_vp, _i64, _vp, _vp]),
     "pcb_resample_minmax": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
-    "pcb_resample_prune_scratch_bytes": (_i64, [_i, _i, _i]),
-    "pcb_resample_minmax_pruned": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "pcb_resample_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pcb_resample_u16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pcb_quantize_u16": (_i, [_vp, _i64, _vp, _vp, _vp]),

@@ -96,7 +96,6 @@ static int make_resample_args(ResampleArgs &a, const void *raw, int H, int W, in
     a.Xs = Xs; a.hex_odd = hex_odd ? 1 : 0; a.flip = flip ? 1 : 0;
     a.ncols = Xs * M * C;
     a.KT = 0; a.cap_floats = 0; a.skip = 0;
-    a.blk = nullptr; a.nbx = 0; a.nby = 0;
     return PCB_OK;
 }
 
@@ -107,29 +106,6 @@ int pcb_resample_minmax(const void *raw, int raw_dtype, int H, int W, int C, con
     int rc = make_resample_args(a, raw, H, W, C, lens, LY, LX, M, pattern, hexcol, Xs, hex_odd, flip);
     if (rc) return rc;
     PCB_REQUIRE(mm != nullptr, "mm");
-    return dispatch_resample<RS_MINMAX>(a, raw_dtype, nullptr, nullptr, mm, nullptr, as_stream(stream));
-}
-
-// pcb_resample_minmax with a scratch table for the raw block min / max pre-pass: tiles that cannot move the bounds are
-// then dropped before their raw rows are staged.  Same result, exactly.
-int64_t pcb_resample_prune_scratch_bytes(int H, int W, int C) {
-    if (H <= 0 || W <= 0 || C <= 0) return -1;
-    return (int64_t)((H + RB_ROWS - 1) / RB_ROWS) * ((W + RB_PX - 1) / RB_PX) * 4;
-}
-
-int pcb_resample_minmax_pruned(const void *raw, int raw_dtype, int H, int W, int C, const pcb_lens_t *lens, int LY,
-                               int LX, int M, int pattern, const pcb_hexcol_t *hexcol, int Xs, int hex_odd, int flip,
-                               pcb_minmax_t *mm, void *scratch, int64_t scratch_bytes, void *stream) {
-    ResampleArgs a;
-    int rc = make_resample_args(a, raw, H, W, C, lens, LY, LX, M, pattern, hexcol, Xs, hex_odd, flip);
-    if (rc) return rc;
-    PCB_REQUIRE(mm != nullptr && scratch != nullptr, "mm, scratch");
-    PCB_REQUIRE(scratch_bytes >= pcb_resample_prune_scratch_bytes(H, W, C), "scratch_bytes >= pcb_resample_prune_scratch_bytes");
-    if (raw_dtype == PCB_U16 && C == 3) {
-        a.blk = reinterpret_cast<const uint32_t *>(scratch);
-        a.nby = (H + RB_ROWS - 1) / RB_ROWS;
-        a.nbx = (W + RB_PX - 1) / RB_PX;
-    }
     return dispatch_resample<RS_MINMAX>(a, raw_dtype, nullptr, nullptr, mm, nullptr, as_stream(stream));
 }
 

@@ -52,13 +52,22 @@ quantize_u8_kernel(const float *__restrict__ in, int64_t n, const pcb_minmax_t *
 // `inv` = 1/(hi-lo) in float64: x*inv - lo*inv differs from the reference's float64 division by a few ulp(double)
 // of the [0, 1] result, invisible after the float32 cast.  y^(5/12) = exp2(5/12 * log2 y) on the SFU (ex2/lg2.approx, ~2 ulp of
 // float32 on [0.003, 1]): |error| < 3e-7 on the [0,1] result, far inside the 1e-4 parity tolerance.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float contrast_srgb_one(float x, double lo, double inv, bool scale) {
     // the clip runs after the (monotone) cast to float32: same result, two float64 instructions fewer — the float64
     // pipe is what the fused refocus epilogue waits for
     // x*inv - lo*inv in one FMA (lo*inv is loop-invariant): within 2 ulp(double) of the reference's float64 quotient
     const float y = fminf(fmaxf(scale ? (float)fma((double)x, inv, -(lo * inv)) : x, 0.f), 1.f);
-    return y >= 0.0031308f ? __fsub_rn(__fmul_rn(1.055f, exp2f((float)(5.0 / 12.0) * __log2f(y))), 0.055f)
-                           : __fmul_rn(y, 12.92f);
+    // both branches are a handful of instructions: evaluate both and select (no divergent branch).  For y in
+    // [0.0031308, 1] the exponent lies in [-3.5, 0]: ex2.approx needs none of exp2f's range handling.
+    const float pw = __fsub_rn(__fmul_rn(1.055f, ex2_approx(__fmul_rn((float)(5.0 / 12.0), __log2f(fmaxf(y, 0.0031308f))))), 0.055f);
+    const float ln = __fmul_rn(y, 12.92f);
+    return y >= 0.0031308f ? pw : ln;
 }
 
 // four consecutive samples as float4 (uint16 / uint8 inputs are integer-valued, exact in float32 like the

@@ -29,8 +29,6 @@ struct ResampleArgs {
     int KT;                       // output lens columns per CTA
     int cap_floats;               // shared-memory tile capacity
     int skip;                     // min/max pass of resample_col: tiles that cannot move the bounds are skipped
-    const uint32_t *blk;          // optional raw block table (rc_block_minmax_kernel): min | max << 16 per block of
-    int nbx, nby;                 //   RB_ROWS x RB_PX raw pixels, nby x nbx entries; lets a tile be skipped BEFORE staging
 };
 
 enum { RS_MINMAX = 0, RS_F32 = 1, RS_U16 = 2 };

@@ -96,49 +96,6 @@ __device__ __forceinline__ int rc_stage(const uint16_t *__restrict__ raw, size_t
     return 0;
 }
 
-// ---- pre-pass of the min/max pass: min / max of the raw exposure per block of RB_ROWS x RB_PX pixels -----------------
-// A pure streaming pass (packed 16-bit min / max, one entry per warp).  With the table a tile of the min/max pass that
-// cannot move the global bounds is recognised from <= 12 table entries, before any of its raw rows is staged.
-constexpr int RB_ROWS = 16;
-constexpr int RB_PX = 128;
-constexpr int RB_WORDS = RB_PX * 3 / 2;       // 32-bit words per block row (uint16 RGB)
-
-__global__ void __launch_bounds__(256)
-rc_block_minmax_kernel(const uint16_t *__restrict__ raw, int H, int W, uint32_t *__restrict__ blk, int nbx) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bx = blockIdx.x * 8 + warp, by = blockIdx.y;
-    if (bx >= nbx) return;
-    const int y0 = by * RB_ROWS, x0 = bx * RB_PX;
-    const int nrow = min(RB_ROWS, H - y0);
-    const int nwords = min(RB_PX, W - x0) * 3 / 2;         // W * 3 even and x0 * 3 even: whole words
-    const int tail = (min(RB_PX, W - x0) * 3) & 1;         // an odd element count leaves one trailing half word
-    uint32_t mn = 0xffffffffu, mx = 0u;
-    for (int r = 0; r < nrow; ++r) {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + ((size_t)(y0 + r) * W + x0) * 3);
-#pragma unroll
-        for (int u = 0; u < RB_WORDS / 32; ++u) {
-            const int m = lane + u * 32;
-            if (m < nwords) {
-                const uint32_t v = __ldg(src + m);
-                mn = __vminu2(mn, v);
-                mx = __vmaxu2(mx, v);
-            }
-        }
-        if (tail && lane == 0) {
-            const uint32_t v = (uint32_t)__ldg(raw + ((size_t)(y0 + r) * W + x0) * 3 + 2 * nwords) * 0x10001u;
-            mn = __vminu2(mn, v);
-            mx = __vmaxu2(mx, v);
-        }
-    }
-    uint32_t lo = min(mn & 0xffffu, mn >> 16), hi = max(mx & 0xffffu, mx >> 16);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if (lane == 0) blk[(size_t)by * nbx + bx] = lo | (hi << 16);
-}
-
 template <int MODE>
 __device__ __forceinline__ void rc_emit(const ResampleOut<MODE> &out, size_t o, float val, float &mn, float &mx) {
     out.put(o, val);
@@ -156,7 +113,7 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
     __shared__ int s_src[2];      // first / last source lens column
     __shared__ int s_smm[2];      // min / max of the staged samples (bit patterns of non-negative floats order like ints)
     __shared__ int s_ninv;        // invalid source lenses of this CTA
-    __shared__ int s_skip;        // min/max pass: the raw block table already shows that this tile cannot matter
+    __shared__ float s_g[2];      // min/max pass: the global bounds as lane 0 saw them at the start of this CTA
 
     const int M = MT ? MT : p.M;
     const int ly = blockIdx.y;
@@ -173,12 +130,11 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
     // raw samples lie strictly inside them cannot move them - every output is a convex combination of staged samples,
     // up to float rounding (a few 2^-24, covered by RC_SKIP_EPS) - so its interpolation is skipped altogether.  The
     // final min / max are exactly those of the full computation.  (NaN from freshly reset keys compares false: no skip.)
+    // The bounds are read ONCE per CTA (lane 0 of warp 0) and handed to everybody through shared memory: they change
+    // under the kernel's feet, and a skip decision taken by some warps only would leave block_minmax_commit reading
+    // partial results that were never written.
     float g_mn = 0.f, g_mx = 0.f;
     const bool may_skip = MODE == RS_MINMAX && mm_rw != nullptr && p.skip;
-    if (may_skip) {
-        g_mn = key_to_float(*reinterpret_cast<volatile uint32_t *>(&mm_rw->kmin));
-        g_mx = key_to_float(*reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax));
-    }
 
     // Tables of the tile, by warp 0, in ONE global-memory latency: the two hex-column entries that bound the source
     // lenses and, speculatively, the 32 lenses starting just below where the first one must be (x0(k) = floor(k LX /
@@ -186,6 +142,15 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
     // speculative one with shuffles.  One barrier instead of two dependent load-and-barrier rounds.
     if (tid < 32) {
         const int lane = tid;
+        if (may_skip) {
+            uint32_t kmn = 0u, kmx = 0u;
+            if (lane == 0) {
+                kmn = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmin);
+                kmx = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax);
+            }
+            g_mn = key_to_float(__shfl_sync(0xffffffffu, kmn, 0));
+            g_mx = key_to_float(__shfl_sync(0xffffffffu, kmx, 0));
+        }
         int xa = k0, xb = k0 + kn - 1;
         int xa_est = k0;
         pcb_hexcol_t h;
@@ -222,35 +187,16 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
         }
         const unsigned inv = __ballot_sync(0xffffffffu, mine && !valid);
         if (mine) s_lens[lane] = L;
-        int skip_now = 0;
-        if (may_skip && p.blk != nullptr && inv == 0u && b1 != INT32_MIN && nsrc_w <= RC_MAX_SRC) {
-            // raw blocks the tile's box [b0, b1 + M] x [b2, b3 + M] touches (a superset of what would be staged)
-            const int by0 = b0 / RB_ROWS, by1 = min((b1 + M + 1) / RB_ROWS, p.nby - 1);
-            const int bx0 = b2 / RB_PX, bx1 = min((b3 + M + 1) / RB_PX, p.nbx - 1);
-            const int nbw = bx1 - bx0 + 1, nb = (by1 - by0 + 1) * nbw;
-            uint32_t lo = 0xffffu, hi = 0u;
-            for (int e = lane; e < nb; e += 32) {
-                const uint32_t v = __ldg(p.blk + (size_t)(by0 + e / nbw) * p.nbx + bx0 + e % nbw);
-                lo = min(lo, v & 0xffffu);
-                hi = max(hi, v >> 16);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-            }
-            skip_now = ((float)lo * (1.f - RC_SKIP_EPS) > g_mn && (float)hi * (1.f + RC_SKIP_EPS) < g_mx) ? 1 : 0;
-        }
         if (lane == 0) {
             s_src[0] = xa; s_src[1] = xb;
             s_box[0] = b0; s_box[1] = b1; s_box[2] = b2; s_box[3] = b3;
             s_smm[0] = 0x7f800000; s_smm[1] = 0;
             s_ninv = __popc(inv);
-            s_skip = skip_now;
+            s_g[0] = g_mn; s_g[1] = g_mx;
         }
     }
     __syncthreads();
-    if (MODE == RS_MINMAX && s_skip) return;                 // uniform over the CTA
+    if (may_skip) { g_mn = s_g[0]; g_mx = s_g[1]; }
     const int xa = s_src[0];
     const int nsrc = s_src[1] - xa + 1;
     const bool lens_in_smem = nsrc <= RC_MAX_SRC;
@@ -373,14 +319,6 @@ static int launch_resample_col(const ResampleArgs &a_in, float *out_f32, uint16_
                                const pcb_minmax_t *mm_ro, cudaStream_t st) {
     ResampleArgs a = a_in;
     a.skip = (getenv("PCB_RESAMPLE_NOSKIP") && atoi(getenv("PCB_RESAMPLE_NOSKIP"))) ? 0 : 1;
-    if (MODE == RS_MINMAX && a.skip && a.blk != nullptr && (reinterpret_cast<uintptr_t>(a.raw) & 3) == 0 &&
-        ((a.W * 3) & 1) == 0 && !(getenv("PCB_RESAMPLE_NOBLOCKS") && atoi(getenv("PCB_RESAMPLE_NOBLOCKS")))) {
-        rc_block_minmax_kernel<<<dim3((a.nbx + 7) / 8, a.nby), 256, 0, st>>>(reinterpret_cast<const uint16_t *>(a.raw), a.H,
-                                                                            a.W, const_cast<uint32_t *>(a.blk), a.nbx);
-        PCB_LAUNCH_OK();
-    } else {
-        a.blk = nullptr;
-    }
     const size_t smem = (size_t)RC_ROWS * RC_TS * sizeof(float);
     dim3 block(RC_THREADS), grid((a.Xs + RC_KT - 1) / RC_KT, a.LY);
     if (a.M == 15) {

@@ -178,16 +178,6 @@ class LensTables:
     def out_shape(self, raw):
         return (self.LY * self.M, self.Xs * self.M, raw.shape[2])
 
-    def prune_scratch(self, raw):
-        """Table of the raw block min / max pre-pass of the min/max pass (kept with the camera's tables)."""
-        H, W, Cn = (int(v) for v in raw.shape)
-        key = (H, W, Cn, str(raw.device))
-        if getattr(self, "_prune_key", None) != key:
-            n = max(int(nat.lib().pcb_resample_prune_scratch_bytes(H, W, Cn)), 4)
-            self._prune = torch.empty(n, dtype=torch.uint8, device=raw.device)
-            self._prune_key = key
-        return self._prune
-
 
 def resample_f32(raw, tabs, flip=False, want_minmax=False):
     """float32 aligned image (LY*M, Xs*M, C) [+ running min/max keys]."""
@@ -209,8 +199,7 @@ def resample_u16(raw, tabs, flip=False, out=None, mm=None):
         mm = torch.empty(2, dtype=torch.int32, device=raw.device)
     L = nat.lib()
     nat.check(L.pcb_minmax_reset(_ptr(mm), _stream()))
-    prune = tabs.prune_scratch(raw)
-    nat.check(L.pcb_resample_minmax_pruned(*(tabs._args(raw, flip) + [_ptr(mm), _ptr(prune), prune.numel(), _stream()])))
+    nat.check(L.pcb_resample_minmax(*(tabs._args(raw, flip) + [_ptr(mm), _stream()])))
     nat.check(L.pcb_resample_u16(*(tabs._args(raw, flip) + [_ptr(mm), _ptr(out), _stream()])))
     return out, mm
 

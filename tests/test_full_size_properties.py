@@ -38,6 +38,23 @@ def test_resampling_is_a_convex_combination_and_minmax_is_exact(illum):
     assert int(al16.view(torch.int16).to(torch.int32).bitwise_and(0xffff).min()) == 0
 
 
+def test_skipping_minmax_pass_is_deterministic_at_full_size(illum):
+    """Regression (round 2): the min/max pass drops tiles that cannot move the global bounds; the bounds it compares with
+    change while the kernel runs, so every CTA must take ONE snapshot of them - with per-warp snapshots some warps of a CTA
+    left and the block reduction folded shared memory they never wrote (garbage bounds, seen with these seeds)."""
+    import torch
+    import bench
+    from plenopticam_b200 import ops
+    w, pipe, _ = illum
+    for seed in (77, 1):
+        raw = bench.synth_raw_device(torch, w["H"], w["W"], w["C"], seed=seed, device=pipe.device)
+        _, mm32 = ops.resample_f32(raw, pipe.tabs, want_minmax=True)
+        want = ops.minmax_values(mm32)
+        for _ in range(4):
+            _, mm = ops.resample_u16(raw, pipe.tabs)
+            assert ops.minmax_values(mm) == want
+
+
 def test_gather_round_trip_and_checksum(illum):
     import torch
     from plenopticam_b200 import ops
