@@ -464,11 +464,12 @@ def main():
         if world > 1:
             sharded = {"slices": len(a_refi), "single_gpu_ms": single_ms}
             peer = None
-            for transport in ("p2p", "nccl"):
+            for tag, transport, shard in (("p2p_rows", "p2p", "rows"), ("p2p", "p2p", "slices"), ("nccl", "nccl", "slices")):
                 try:
                     if transport == "p2p" and peer is None:
                         peer = par.PeerStack((len(a_refi),) + tuple(vp.shape[2:]))
-                    run = lambda: par.sharded_refocus_stack(vp, a_refi, refi=True, transport=transport, peer_stack=peer)
+                    run = lambda: par.sharded_refocus_stack(vp, a_refi, refi=True, transport=transport, peer_stack=peer,
+                                                            shard=shard)
                     full = run()
                     torch.cuda.synchronize()
                     ok = bool(torch.equal(full, ref_stack))
@@ -484,16 +485,17 @@ def main():
                         torch.cuda.synchronize()
                         ts.append(_maxed(torch, dist, world, device, e0.elapsed_time(e1)))
                     ms = float(np.median(ts))
-                    sharded[transport] = {"ms_per_stack": ms, "slices_per_s": len(a_refi) / (ms * 1e-3),
+                    sharded[tag] = {"ms_per_stack": ms, "slices_per_s": len(a_refi) / (ms * 1e-3),
                                           "equals_unsharded_on_every_rank": bool(int(okt.item())),
                                           "speedup_vs_one_gpu": single_ms / ms}
                 except Exception as exc:                                   # e.g. no peer access on this box
-                    sharded[transport] = {"error": "%s: %s" % (type(exc).__name__, exc)}
-            sharded["what"] = ("one light field, 60 refined slices split over the ranks in contiguous blocks; every rank "
-                               "prefilters (replicated, shift independent), evaluates its block and ends with the whole "
-                               "sRGB stack.  p2p: the kernel that finishes a slice stores it into every rank's stack through "
-                               "peer-mapped pointers (NVLink), one 4-byte all-reduce as the barrier; nccl: all_gather of the "
-                               "blocks.  CUDA events, max over ranks, median of 7")
+                    sharded[tag] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            sharded["what"] = ("one light field, 60 refined slices, every rank ends with the whole sRGB stack.  p2p_rows: each "
+                               "rank computes a band of image rows of ALL slices (prefilter and horizontal pass restricted to "
+                               "the band + halo) and the kernel that finishes a tile stores it into every rank's stack through "
+                               "peer-mapped pointers (NVLink), 4-byte all-reduces as barriers; p2p: the same exchange with a "
+                               "contiguous block of SLICES per rank (every rank prefilters everything); nccl: slice blocks + "
+                               "all_gather.  CUDA events, max over ranks, median of 7")
             if peer is not None:
                 peer.close()
         del vp, ref_stack

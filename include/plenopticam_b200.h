@@ -205,6 +205,11 @@ int pcb_refocus_int_srgb(const void *vp, int dtype, int M, int S, int T, int C, 
  *       view_zeroed_host / view_zeroed: the M*M mask on the host and on the device
  *       tmp: float32 scratch (N,M,S,T,3); out: float32 (N,S,T,3); mm: nullable fused min/max of the stack.
  * ------------------------------------------------------------------------------------------------ */
+/* Row restriction of the refinement passes (host struct, nullable everywhere: NULL = the whole image).  For a ROW-sharded
+ * stack a rank produces the output rows [out_lo, out_hi) of every slice (out_lo a multiple of 8; out_hi too unless it is S);
+ * for that it needs the rows [h_lo, h_hi) of the horizontal pass = of the B-spline coefficients, and the prefilter's x pass
+ * for the rows [tmp_lo, tmp_hi) (plenopticam_b200/lfp_refocuser/refinement.py::RefinementPlan.rows derives all three). */
+typedef struct { int32_t out_lo, out_hi, h_lo, h_hi, tmp_lo, tmp_hi; } pcb_refi_rows_t;
 int pcb_refi_prefilter(const void *vp, int dtype, int M, int S, int T, int C,
                        const float *py_vals, const int32_t *py_first, int Kpy,
                        const float *px_vals, const int32_t *px_first, int Kpx,
@@ -219,7 +224,8 @@ int pcb_refi_prefilter_toeplitz(const void *vp, int dtype, int M, int S, int T, 
                                 const float *px_vals, const int32_t *px_first, int Kpx,
                                 const uint8_t *view_zeroed, float *tmp, float *coef,
                                 const float *hx_host, int ntx, int cx, int x_lo, int x_hi,
-                                const float *hy_host, int nty, int cyy, int y_lo, int y_hi, void *stream);
+                                const float *hy_host, int nty, int cyy, int y_lo, int y_hi,
+                                const pcb_refi_rows_t *rows_host /* nullable: see below */, void *stream);
 int pcb_refocus_refi(const float *coef, int M, int S, int T, int C, int N,
                      const float *dy_vals, const int32_t *dy_first, int Kgy,
                      const float *dx_vals, const int32_t *dx_first, int Kx,
@@ -266,7 +272,7 @@ int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N
                             const int32_t *xlo_host, const int32_t *xhi_host,
                             const uint8_t *view_zeroed_host, const uint8_t *view_zeroed,
                             float *tmp, const pcb_fanout_t *dst_host, const pcb_refi_quads_t *quads_host /* nullable */,
-                            void *stream);
+                            const pcb_refi_rows_t *rows_host /* nullable */, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Post-processing of the stack — replaces LfpContrast.auto_hist_align + GammaConverter.srgb_conv as used

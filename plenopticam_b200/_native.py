@@ -35,6 +35,12 @@ class Fanout(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class RefiRows(C.Structure):
+    """pcb_refi_rows_t"""
+    _fields_ = [("out_lo", C.c_int32), ("out_hi", C.c_int32), ("h_lo", C.c_int32), ("h_hi", C.c_int32),
+                ("tmp_lo", C.c_int32), ("tmp_hi", C.c_int32)]
+
+
 class RefiQuads(C.Structure):
     """pcb_refi_quads_t"""
     _fields_ = [("wq", C.c_void_p), ("fu", C.c_void_p), ("G", C.c_int32), ("reserved", C.c_int32),
@@ -145,11 +151,11 @@ _SIGNATURES = {
     "pcb_refocus_int_zero": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refi_prefilter": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refi_prefilter_toeplitz": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp,
-                                         _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+                                         _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pcb_refocus_refi": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp]),
     "pcb_refocus_refi_fanout": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _vp, _vp]),
+                                     _vp, _vp, _vp, _vp]),
     "pcb_peer_alloc": (_i, [_i64, C.POINTER(C.c_void_p)]),
     "pcb_peer_free": (_i, [_vp]),
     "pcb_peer_export": (_i, [_vp, C.c_char_p]),

@@ -396,7 +396,7 @@ int pcb_refi_prefilter_toeplitz(const void *vp, int dtype, int M, int S, int T, 
                                 const int32_t *py_first, int Kpy, const float *px_vals, const int32_t *px_first, int Kpx,
                                 const uint8_t *view_zeroed, float *tmp, float *coef, const float *hx_host, int ntx, int cx,
                                 int x_lo, int x_hi, const float *hy_host, int nty, int cyy, int y_lo, int y_hi,
-                                void *stream) {
+                                const pcb_refi_rows_t *rows_host, void *stream) {
     PCB_REQUIRE(vp && py_vals && py_first && px_vals && px_first && view_zeroed && tmp && coef, "pointers");
     PCB_REQUIRE(M > 0 && M * M <= 65535 && S >= 4 && T >= 4 && S <= 65535 && Kpy > 0 && Kpx > 0, "sizes");
     PCB_REQUIRE(C == 3, "3 colour channels (lfp_shiftandsum.py:97)");
@@ -411,9 +411,9 @@ int pcb_refi_prefilter_toeplitz(const void *vp, int dtype, int M, int S, int T, 
     }
     cudaStream_t st = as_stream(stream);
     switch (dtype) {
-    case PCB_U16: return launch_refi_prefilter<uint16_t>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty);
-    case PCB_F32: return launch_refi_prefilter<float>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty);
-    case PCB_U8:  return launch_refi_prefilter<uint8_t>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty);
+    case PCB_U16: return launch_refi_prefilter<uint16_t>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty, rows_host);
+    case PCB_F32: return launch_refi_prefilter<float>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty, rows_host);
+    case PCB_U8:  return launch_refi_prefilter<uint8_t>(vp, M, S, T, py_vals, py_first, Kpy, px_vals, px_first, Kpx, view_zeroed, tmp, coef, st, &tx, &ty, rows_host);
     }
     return fail(PCB_ERR_INVALID, "%s: unsupported dtype %lld", __func__, dtype);
 }
@@ -453,7 +453,8 @@ int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N
                             const int32_t *dy_first, int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx,
                             const int32_t *iy, const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
                             const uint8_t *view_zeroed_host, const uint8_t *view_zeroed, float *tmp,
-                            const pcb_fanout_t *dst_host, const pcb_refi_quads_t *quads_host, void *stream) {
+                            const pcb_fanout_t *dst_host, const pcb_refi_quads_t *quads_host,
+                            const pcb_refi_rows_t *rows_host, void *stream) {
     int rc = check_refocus_refi(coef, M, S, T, C, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host,
                                 xhi_host, view_zeroed_host, view_zeroed, tmp);
     if (rc) return rc;
@@ -469,7 +470,7 @@ int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N
         }
     }
     return launch_refine(coef, M, S, T, N, dy_vals, dy_first, Kgy, dx_vals, dx_first, Kx, iy, ix, xlo_host, xhi_host,
-                         view_zeroed_host, tmp, dst, as_stream(stream), quads_host);
+                         view_zeroed_host, tmp, dst, as_stream(stream), quads_host, rows_host);
 }
 
 // ---- peer-mapped buffers (slice-sharded stacks) --------------------------------------------------------------------

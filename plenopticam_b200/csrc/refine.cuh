@@ -30,9 +30,9 @@ template <typename TIn>
 __global__ void __launch_bounds__(RP_THREADS)
 refi_prefilter_x_kernel(const TIn *__restrict__ vp, int S, int T, const float *__restrict__ px_vals,
                         const int32_t *__restrict__ px_first, int Kp, const uint8_t *__restrict__ view_zeroed,
-                        float *__restrict__ tmp) {
+                        float *__restrict__ tmp, int r_off = 0) {
     extern __shared__ __align__(16) float s_row[];        // [T*3]
-    const int r = blockIdx.x, view = blockIdx.y;
+    const int r = r_off + blockIdx.x, view = blockIdx.y;
     if (view_zeroed[view]) return;
     const int E = T * 3;
     const TIn *src = vp + ((size_t)view * S + r) * E;
@@ -99,9 +99,9 @@ template <typename TIn>
 __global__ void __launch_bounds__(RP_THREADS)
 refi_prefilter_x3_kernel(const TIn *__restrict__ vp, int S, int T, const float *__restrict__ px_vals,
                          const int32_t *__restrict__ px_first, int Kp, RpTaps tp,
-                         const uint8_t *__restrict__ view_zeroed, float *__restrict__ tmp) {
+                         const uint8_t *__restrict__ view_zeroed, float *__restrict__ tmp, int r_off = 0) {
     extern __shared__ __align__(16) float s_buf[];        // [T*3] samples, [T*3] results
-    const int r = blockIdx.x, view = blockIdx.y;
+    const int r = r_off + blockIdx.x, view = blockIdx.y;
     if (view_zeroed[view]) return;
     const int E = T * 3;
     float *s_row = s_buf, *s_out = s_buf + E;
@@ -350,14 +350,14 @@ __device__ __forceinline__ void rq_view(float (&acc)[RQ_ROWS][RQ][3], const floa
 
 __global__ void __launch_bounds__(RQ_THREADS, 1)
 refine_hq_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, int G, const float4 *__restrict__ wq,
-                 const int32_t *__restrict__ fu, RefineQCtl ctl, float *__restrict__ H) {
+                 const int32_t *__restrict__ fu, RefineQCtl ctl, float *__restrict__ H, int rb_off) {
     extern __shared__ __align__(16) float s_win[];         // [active view][pixel of the window][RQ_PIX]
     __shared__ int s_act[RF_MAXM];                         // the unmasked view columns of this view-row
     __shared__ int2 s_view[RF_MAXM];                       // per ACTIVE view: {float offset of pixel 0's record, pixels}
     __shared__ int2 s_tab[RF_MAXM];                        // per ACTIVE view: {float4 offset of its weight block, W}
     __shared__ int s_nact;
     const int j = blockIdx.z;
-    const int r0 = blockIdx.y * RQ_ROWS;
+    const int r0 = (rb_off + blockIdx.y) * RQ_ROWS;
     const int xc0 = blockIdx.x * RQ_XC;
     const int tid = threadIdx.x;
     const int sg = tid / RQ_XC, tx = tid - sg * RQ_XC;
@@ -464,12 +464,13 @@ refine_hq_kernel(const float *__restrict__ coef, int M, int S, int T, int nb, in
 template <int KG>
 __global__ void __launch_bounds__(256)
 refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *__restrict__ dy_vals,
-                const int32_t *__restrict__ dy_first, const int32_t *__restrict__ iy, RefineHCtl ctl, pcb_fanout_t dst) {
+                const int32_t *__restrict__ dy_first, const int32_t *__restrict__ iy, RefineHCtl ctl, pcb_fanout_t dst,
+                int Gy, int g_off) {
     __shared__ __align__(16) float s_w[RF_MAXM * KG * RF_GROUP];      // [active view row][tap][output row of the group]
     __shared__ int s_j[RF_MAXM];           // active view rows
     __shared__ int s_f[RF_MAXM];           // first sample row of this group for each of them
     __shared__ int s_n;
-    const int gy = blockIdx.x, Gy = gridDim.x, n = blockIdx.z;
+    const int gy = g_off + blockIdx.x, n = blockIdx.z;
     const int e = blockIdx.y * blockDim.x + threadIdx.x;
     if (threadIdx.x < 32) {                // M <= 32: one lane per view row, compacted with a ballot
         const int j = threadIdx.x;
@@ -539,26 +540,34 @@ refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *_
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
 // tx / ty: interior Toeplitz description of the two axes (lo > hi: none)
+// rows: optional restriction (row-sharded stacks): the x pass runs for rows [tmp_lo, tmp_hi) only and the y pass produces
+// coefficient rows [h_lo, h_hi) (whole strips / groups that intersect it).
 template <typename TIn>
 static int launch_refi_prefilter(const void *vp, int M, int S, int T, const float *py_vals, const int32_t *py_first,
                                  int Kpy, const float *px_vals, const int32_t *px_first, int Kpx,
                                  const uint8_t *view_zeroed, float *tmp, float *coef, cudaStream_t st,
-                                 const RpTaps *tx = nullptr, const RpTaps *ty = nullptr) {
+                                 const RpTaps *tx = nullptr, const RpTaps *ty = nullptr,
+                                 const pcb_refi_rows_t *rows = nullptr) {
     const int E = T * 3;
     const size_t smem = (size_t)E * sizeof(float);
     if (2 * smem > 200 * 1024) return fail(PCB_ERR_UNSUPPORTED, "%s: image row does not fit shared memory", "pcb_refi_prefilter");
+    const int xr0 = rows ? max(rows->tmp_lo, 0) : 0, xr1 = rows ? min(rows->tmp_hi, S) : S;
+    const int ca = rows ? max(rows->h_lo, 0) : 0, cb = rows ? min(rows->h_hi, S) : S;
+    if (xr1 <= xr0 || cb <= ca) return fail(PCB_ERR_INVALID, "%s: empty row range", "pcb_refi_prefilter");
     if (tx && tx->hi - tx->lo + 1 >= 2 * RPX_P) {
         PCB_CUDA(cudaFuncSetAttribute(refi_prefilter_x3_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem)));
-        refi_prefilter_x3_kernel<TIn><<<dim3(S, M * M), RP_THREADS, 2 * smem, st>>>((const TIn *)vp, S, T, px_vals, px_first,
-                                                                                  Kpx, *tx, view_zeroed, tmp);
+        refi_prefilter_x3_kernel<TIn><<<dim3(xr1 - xr0, M * M), RP_THREADS, 2 * smem, st>>>((const TIn *)vp, S, T, px_vals,
+                                                                                          px_first, Kpx, *tx, view_zeroed,
+                                                                                          tmp, xr0);
     } else {
         PCB_CUDA(cudaFuncSetAttribute(refi_prefilter_x_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        refi_prefilter_x_kernel<TIn><<<dim3(S, M * M), RP_THREADS, smem, st>>>((const TIn *)vp, S, T, px_vals, px_first, Kpx,
-                                                                             view_zeroed, tmp);
+        refi_prefilter_x_kernel<TIn><<<dim3(xr1 - xr0, M * M), RP_THREADS, smem, st>>>((const TIn *)vp, S, T, px_vals, px_first,
+                                                                                     Kpx, view_zeroed, tmp, xr0);
     }
     PCB_LAUNCH_OK();
     const int G = (S + RP_GY - 1) / RP_GY;
     const dim3 gx((E + 255) / 256);
+    const int ga = ca / RP_GY, gb = (cb + RP_GY - 1) / RP_GY;            // table groups that intersect [ca, cb)
     // interior rows in strips of RPY_R, aligned to the row groups of the table kernel; the groups before / after keep it
     int ya = 0, strips = 0;
     if (ty && ty->hi >= ty->lo) {
@@ -567,21 +576,29 @@ static int launch_refi_prefilter(const void *vp, int M, int S, int T, const floa
         if (strips < 1) strips = 0;
     }
     if (strips > 0) {
-        refi_prefilter_yt_kernel<<<dim3(gx.x, strips, M * M), 256, 0, st>>>(tmp, S, E, *ty, ya, view_zeroed, coef);
-        PCB_LAUNCH_OK();
-        const int g_before = ya / RP_GY, g_after0 = (ya + strips * RPY_R) / RP_GY;
-        if (g_before > 0) {
-            refi_prefilter_y_kernel<<<dim3(gx.x, g_before, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
-                                                                                view_zeroed, coef, 0);
+        const int s_lo = ca > ya ? (ca - ya) / RPY_R : 0;
+        const int s_hi = min(strips, cb > ya ? (cb - ya + RPY_R - 1) / RPY_R : 0);
+        if (s_hi > s_lo) {
+            refi_prefilter_yt_kernel<<<dim3(gx.x, s_hi - s_lo, M * M), 256, 0, st>>>(tmp, S, E, *ty, ya + s_lo * RPY_R,
+                                                                                    view_zeroed, coef);
             PCB_LAUNCH_OK();
         }
-        if (g_after0 < G) {
-            refi_prefilter_y_kernel<<<dim3(gx.x, G - g_after0, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
-                                                                                    view_zeroed, coef, g_after0);
+        const int g_before = ya / RP_GY, g_after0 = (ya + strips * RPY_R) / RP_GY;
+        const int b0 = ga, b1 = min(gb, g_before);                           // border groups before the interior
+        if (b1 > b0) {
+            refi_prefilter_y_kernel<<<dim3(gx.x, b1 - b0, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
+                                                                               view_zeroed, coef, b0);
+            PCB_LAUNCH_OK();
+        }
+        const int a0 = max(ga, g_after0), a1 = min(gb, G);                   // ... and after it
+        if (a1 > a0) {
+            refi_prefilter_y_kernel<<<dim3(gx.x, a1 - a0, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
+                                                                               view_zeroed, coef, a0);
             PCB_LAUNCH_OK();
         }
     } else {
-        refi_prefilter_y_kernel<<<dim3(gx.x, G, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy, view_zeroed, coef, 0);
+        refi_prefilter_y_kernel<<<dim3(gx.x, min(gb, G) - ga, M * M), 256, 0, st>>>(tmp, S, E, py_vals, py_first, Kpy,
+                                                                                  view_zeroed, coef, ga);
         PCB_LAUNCH_OK();
     }
     return PCB_OK;
@@ -600,7 +617,8 @@ static int launch_refine_h(const float *coef, int M, int S, int T, int nb, const
 // Horizontal pass in slice quads; returns PCB_ERR_UNSUPPORTED (without touching g_err's meaning for the caller) when the
 // tables do not fit this kernel, so that launch_refine falls back to refine_h_kernel.
 static int launch_refine_hq(const float *coef, int M, int S, int T, int nb, const pcb_refi_quads_t &qd,
-                            const uint8_t *view_zeroed_host, float *H, cudaStream_t st) {
+                            const uint8_t *view_zeroed_host, float *H, cudaStream_t st,
+                            const pcb_refi_rows_t *rows = nullptr) {
     if (M > RF_MAXM || qd.G * RQ < nb || qd.wq == nullptr || qd.fu == nullptr) return PCB_ERR_UNSUPPORTED;
     RefineQCtl ctl;
     memset(&ctl, 0, sizeof(ctl));
@@ -619,16 +637,20 @@ static int launch_refine_hq(const float *coef, int M, int S, int T, int nb, cons
     const size_t smem = max_px * RQ_PIX * sizeof(float);
     if (smem > 220 * 1024 || (S + RQ_ROWS - 1) / RQ_ROWS > 65535) return PCB_ERR_UNSUPPORTED;
     PCB_CUDA(cudaFuncSetAttribute(refine_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((T + RQ_XC - 1) / RQ_XC, (S + RQ_ROWS - 1) / RQ_ROWS, M);
+    const int nblk = (S + RQ_ROWS - 1) / RQ_ROWS;
+    const int b0 = rows ? max(rows->h_lo, 0) / RQ_ROWS : 0;
+    const int b1 = rows ? min((min(rows->h_hi, S) + RQ_ROWS - 1) / RQ_ROWS, nblk) : nblk;
+    if (b1 <= b0) return fail(PCB_ERR_INVALID, "%s: empty row range", "pcb_refocus_refi");
+    dim3 grid((T + RQ_XC - 1) / RQ_XC, b1 - b0, M);
     refine_hq_kernel<<<grid, RQ_THREADS, smem, st>>>(coef, M, S, T, nb, qd.G, reinterpret_cast<const float4 *>(qd.wq), qd.fu,
-                                                     ctl, H);
+                                                     ctl, H, b0);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }
 
 static int launch_refine_v(const float *H, int M, int S, int T, int nb, const float *dy_vals, const int32_t *dy_first,
                            int Kgy, const int32_t *iy, const uint8_t *view_zeroed_host, const pcb_fanout_t &dst,
-                           cudaStream_t st) {
+                           cudaStream_t st, const pcb_refi_rows_t *rows = nullptr) {
     const int E = T * 3;
     RefineHCtl ctl;
     memset(&ctl, 0, sizeof(ctl));
@@ -636,9 +658,17 @@ static int launch_refine_v(const float *H, int M, int S, int T, int nb, const fl
         for (int i = 0; i < M; ++i)
             if (!view_zeroed_host[j * M + i]) ctl.active[j] |= 1u << i;
     const int Gy = (S + RF_GROUP - 1) / RF_GROUP;
-    const dim3 grid(Gy, (E + 255) / 256, nb);
+    int g0 = 0, g1 = Gy;
+    if (rows) {
+        if (rows->out_lo % RF_GROUP != 0 || (rows->out_hi % RF_GROUP != 0 && rows->out_hi < S))
+            return fail(PCB_ERR_INVALID, "%s: output row range must start / end on multiples of %lld", "pcb_refocus_refi", RF_GROUP);
+        g0 = max(rows->out_lo, 0) / RF_GROUP;
+        g1 = min((min(rows->out_hi, S) + RF_GROUP - 1) / RF_GROUP, Gy);
+        if (g1 <= g0) return fail(PCB_ERR_INVALID, "%s: empty row range", "pcb_refocus_refi");
+    }
+    const dim3 grid(g1 - g0, (E + 255) / 256, nb);
     if (Kgy > S) return fail(PCB_ERR_INVALID, "%s: vertical window of %lld rows exceeds the image", "pcb_refocus_refi", Kgy);
-#define PCB_RV(K) case K: refine_v_kernel<K><<<grid, 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, iy, ctl, dst); break;
+#define PCB_RV(K) case K: refine_v_kernel<K><<<grid, 256, 0, st>>>(H, M, S, E, dy_vals, dy_first, iy, ctl, dst, Gy, g0); break;
     switch (Kgy) {
         PCB_RV(1) PCB_RV(2) PCB_RV(3) PCB_RV(4) PCB_RV(5) PCB_RV(6) PCB_RV(7) PCB_RV(8) PCB_RV(9) PCB_RV(10)
         PCB_RV(11) PCB_RV(12) PCB_RV(13) PCB_RV(14) PCB_RV(15) PCB_RV(16) PCB_RV(17) PCB_RV(18) PCB_RV(19) PCB_RV(20)
@@ -653,10 +683,11 @@ static int launch_refine(const float *coef, int M, int S, int T, int nb, const f
                          int Kgy, const float *dx_vals, const int32_t *dx_first, int Kx, const int32_t *iy,
                          const int32_t *ix, const int32_t *xlo_host, const int32_t *xhi_host,
                          const uint8_t *view_zeroed_host, float *H, const pcb_fanout_t &dst, cudaStream_t st,
-                         const pcb_refi_quads_t *quads = nullptr) {
+                         const pcb_refi_quads_t *quads = nullptr, const pcb_refi_rows_t *rows = nullptr) {
     if (quads != nullptr && !(getenv("PCB_REFINE_KERNEL") && !strcmp(getenv("PCB_REFINE_KERNEL"), "taps"))) {
-        const int rq = launch_refine_hq(coef, M, S, T, nb, *quads, view_zeroed_host, H, st);
-        if (rq == PCB_OK) return launch_refine_v(H, M, S, T, nb, dy_vals, dy_first, Kgy, iy, view_zeroed_host, dst, st);
+        const int rq = launch_refine_hq(coef, M, S, T, nb, *quads, view_zeroed_host, H, st, rows);
+        if (rq == PCB_OK)
+            return launch_refine_v(H, M, S, T, nb, dy_vals, dy_first, Kgy, iy, view_zeroed_host, dst, st, rows);
         if (rq != PCB_ERR_UNSUPPORTED) return rq;
     }
     const int E = T * 3;
@@ -695,7 +726,8 @@ static int launch_refine(const float *coef, int M, int S, int T, int nb, const f
     default: return fail(PCB_ERR_UNSUPPORTED, "%s: band of %lld taps (1..12 supported)", "pcb_refocus_refi", Kx);
     }
     if (rc) return rc;
-    return launch_refine_v(H, M, S, T, nb, dy_vals, dy_first, Kgy, iy, view_zeroed_host, dst, st);
+    // (the per-slice kernel has no row restriction: it fills every row of H, the vertical pass takes what it needs)
+    return launch_refine_v(H, M, S, T, nb, dy_vals, dy_first, Kgy, iy, view_zeroed_host, dst, st, rows);
 }
 
 }  // namespace pcb

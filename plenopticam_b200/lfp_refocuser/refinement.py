@@ -295,6 +295,7 @@ class RefinementPlan(object):
         self.tx, self.ty = Bx.prefilter_toeplitz(), Ay.prefilter_toeplitz()      # interior filters (host)
         # per-slice bands
         dyv, dyf, self.Kgy = Ay.grouped()
+        self._dy_first_host = np.ascontiguousarray(dyf)
         dxv, dxf, xlo, xhi = Bx.tap_major()
         self.dy_v, self.dy_f = t(dyv), t(dyf)
         self.dx_v, self.dx_f, self.Kx = t(dxv), t(dxf), int(Bx.K)
@@ -307,6 +308,27 @@ class RefinementPlan(object):
         per_slice = M * S * T * 3 * 4                       # horizontal pass of one slice: (M, S, T, 3) float32
         self.batch = int(max(1, min(self.N, tmp_budget_bytes // per_slice, 1024 // M)))
         self.device = device
+
+    def rows(self, n_lo, n_hi, y_lo, y_hi):
+        """pcb_refi_rows_t for the output rows [y_lo, y_hi) of slices n_lo .. n_hi-1 (a rank's band of a row-sharded stack):
+        the rows of the horizontal pass the vertical windows of those outputs reach, and the rows of the prefilter's x
+        pass behind them (with slack for the whole strips / groups the y pass works in)."""
+        from .. import _native as nat
+        S = self.S
+        y_lo, y_hi = int(y_lo), min(int(y_hi), S)
+        if y_lo % GROUP or (y_hi % GROUP and y_hi != S) or not 0 <= y_lo < y_hi:
+            raise ValueError("row band must start / end on multiples of %d inside the image" % GROUP)
+        act = [j for j in range(self.M) if not self.z_host.reshape(self.M, self.M)[j].all()]
+        sidx = np.unique(self.iy[n_lo:n_hi][:, act])
+        first = self._dy_first_host[sidx][:, y_lo // GROUP:(y_hi + GROUP - 1) // GROUP]
+        h_lo, h_hi = int(first.min()), int(first.max()) + self.Kgy
+        # coefficient rows are produced in blocks of 6 (horizontal pass) out of strips of 16 / groups of 8 (y prefilter)
+        c_lo, c_hi = (h_lo // 6) * 6, min(-(-h_hi // 6) * 6, S)
+        slack = 16 + max(self.Kpy, 32)
+        r = nat.RefiRows()
+        r.out_lo, r.out_hi, r.h_lo, r.h_hi = y_lo, y_hi, c_lo, c_hi
+        r.tmp_lo, r.tmp_hi = max(c_lo - slack, 0), min(c_hi + slack, S)
+        return r
 
     def quads(self, n0, nb):
         """pcb_refi_quads_t of slices n0 .. n0+nb-1 (device tables, cached per slice range), or None."""
@@ -355,7 +377,8 @@ def device_plan(S, T, M, a_list, view_zeroed, device):
     return plan
 
 
-def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=None, coef=None, n_range=None):
+def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=None, coef=None, n_range=None,
+                 row_range=None):
     """Device evaluation: vp (M,M,S,T,3) CUDA tensor (uint16 / uint8 / float32) -> (N,S,T,3) float32 stack.
 
     out    : optional (N,S,T,3) float32 destination (e.g. this rank's block of a larger stack)
@@ -365,7 +388,10 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=N
     coef   : optional B-spline coefficients of the light field from an earlier call (`prefilter`)
     n_range: (lo, hi) - evaluate only slices lo..hi-1 of `a_list` / `plan` (a rank's block of a sharded stack; the
              operator tables are those of the whole range, so a block equals the same rows of the unsharded stack bit
-             for bit); `out` / `fanout` then address the first slice of the block"""
+             for bit); `out` / `fanout` then address the first slice of the block
+    row_range: (y_lo, y_hi) - produce only these output rows of every slice (multiples of 8; a rank's band of a ROW-sharded
+             stack); the other rows of `out` / the fan-out destinations are not touched.  `coef` may then hold only the
+             coefficient rows the band needs (`prefilter(vp, plan, rows=plan.rows(...))`)"""
     import ctypes as C
     import torch
     from .. import _native as nat
@@ -382,8 +408,9 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=N
     L, p, st = nat.lib(), ops._ptr, ops._stream()
     if N == 0:
         return out if out is not None else torch.empty((0, S, T, Cn), dtype=torch.float32, device=dev)
+    rows = plan.rows(n_lo, n_hi, row_range[0], row_range[1]) if row_range is not None else None
     if coef is None:
-        coef = prefilter(vp, plan)
+        coef = prefilter(vp, plan, rows=rows)
     if fanout is None:
         if out is None:
             out = torch.empty((N, S, T, Cn), dtype=torch.float32, device=dev)
@@ -409,13 +436,14 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=N
                                             C.c_void_p(plan.ix_d.data_ptr() + (n_lo + n0) * M * 4),
                                             lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), z_ptr,
                                             p(plan.z_dev), p(hbuf), C.byref(dst),
-                                            C.byref(qd) if qd is not None else None, st))
+                                            C.byref(qd) if qd is not None else None,
+                                            C.byref(rows) if rows is not None else None, st))
     return out
 
 
-def prefilter(vp, plan):
+def prefilter(vp, plan, rows=None):
     """B-spline coefficients of every unmasked view, float32 (M,M,S,T,3): the shift-independent half of the refinement,
-    done once per light field."""
+    done once per light field.  `rows` (pcb_refi_rows_t from `plan.rows`): only the coefficient rows a row band needs."""
     import ctypes as C
     import torch
     from .. import _native as nat
@@ -429,5 +457,6 @@ def prefilter(vp, plan):
     nat.check(L.pcb_refi_prefilter_toeplitz(p(vp), ops._pcb_dtype(vp), M, S, T, Cn, p(plan.py_v), p(plan.py_f), plan.Kpy,
                                             p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp), p(coef),
                                             hptr(hx), 0 if hx is None else int(hx.size), cx, xlo, xhi,
-                                            hptr(hy), 0 if hy is None else int(hy.size), cy, ylo, yhi, st))
+                                            hptr(hy), 0 if hy is None else int(hy.size), cy, ylo, yhi,
+                                            C.byref(rows) if rows is not None else None, st))
     return coef

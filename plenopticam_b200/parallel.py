@@ -94,16 +94,44 @@ def gather_slices(local, n_total, group=None):
 # ----------------------------------------------------------------------------------------------------------
 # per-rank halves (no communication)
 # ----------------------------------------------------------------------------------------------------------
-def local_block(vp, a_list, rank, world, refi=False, view_zeroed=None, out=None, fanout=None, coef=None):
-    """This rank's contiguous block of the LINEAR stack of light field `vp` (M,M,S,T,3): float32 (n_local,S,T,3).
+ROW_GROUP = 8        # row bands start on multiples of the vertical pass' group size (RF_GROUP)
 
-    out    : optional destination for the block (e.g. `stack[lo:hi]` of a full-size stack buffer)
-    fanout : refinement path only - [(address of slice `lo` in a destination stack, None), ...]: the kernel stores
-             every finished slice into all of them (see PeerStack.fanout)."""
+
+def row_band(S, rank, world):
+    """[y_lo, y_hi) of this rank in a ROW-sharded stack: whole groups of ROW_GROUP rows, balanced."""
+    g_lo, g_hi = shard_bounds(-(-int(S) // ROW_GROUP), rank, world)
+    return g_lo * ROW_GROUP, min(g_hi * ROW_GROUP, int(S))
+
+
+def local_block(vp, a_list, rank, world, refi=False, view_zeroed=None, out=None, fanout=None, coef=None, shard='slices'):
+    """This rank's share of the LINEAR stack of light field `vp` (M,M,S,T,3).
+
+    shard='slices': a contiguous block of slices, float32 (n_local,S,T,3);
+        out    : optional destination for the block (e.g. `stack[lo:hi]` of a full-size stack buffer)
+        fanout : refinement path only - [(address of slice `lo` in a destination stack, None), ...]: the kernel stores
+                 every finished slice into all of them (see PeerStack.fanout).
+    shard='rows' (refinement path): the band `row_band(S, rank, world)` of EVERY slice - the prefilter and the horizontal
+        pass then shrink with the band (plus the halo the vertical windows reach) instead of being repeated by every rank,
+        and the horizontal pass keeps all its slice quads busy;
+        out    : the FULL (N,S,T,3) stack the band is written into (returned); fanout addresses slice 0 of each stack."""
     from . import ops
     a_list = list(a_list)
     lo, hi = shard_bounds(len(a_list), rank, world)
     S, T, Cn = (int(v) for v in vp.shape[2:])
+    if shard == 'rows':
+        if not refi:
+            raise NotImplementedError("row sharding exists for the refinement path (BASELINE configs[3])")
+        from .lfp_refocuser.refinement import device_plan, refocus_refi
+        mask = ops.aperture_mask(vp.shape[0]) if view_zeroed is None else view_zeroed
+        plan = device_plan(S, T, int(vp.shape[0]), a_list, mask, vp.device)
+        y_lo, y_hi = row_band(S, rank, world)
+        if out is None and fanout is None:
+            out = torch.empty((len(a_list), S, T, Cn), dtype=torch.float32, device=vp.device)
+        if y_hi > y_lo:
+            refocus_refi(vp, a_list, mask, plan=plan, out=out, fanout=fanout, coef=coef, row_range=(y_lo, y_hi))
+        return out
+    if shard != 'slices':
+        raise ValueError("shard must be 'slices' or 'rows'")
     if hi == lo:
         return torch.empty((0, S, T, Cn), dtype=torch.float32, device=vp.device)
     if refi:
@@ -203,13 +231,33 @@ class PeerStack(object):
 # ----------------------------------------------------------------------------------------------------------
 # the sharded stack
 # ----------------------------------------------------------------------------------------------------------
+def gather_rows(full, group=None):
+    """All-gather of the row bands of a ROW-sharded stack (baseline transport): every rank's band of `full` (N,S,T,C) is
+    sent to everybody and written into place."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    N, S = int(full.shape[0]), int(full.shape[1])
+    hmax = max(row_band(S, r, world)[1] - row_band(S, r, world)[0] for r in range(world))
+    y_lo, y_hi = row_band(S, rank, world)
+    send = torch.zeros((N, hmax) + tuple(full.shape[2:]), dtype=full.dtype, device=full.device)
+    send[:, :y_hi - y_lo] = full[:, y_lo:y_hi]
+    recv = torch.empty((world,) + tuple(send.shape), dtype=full.dtype, device=full.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    for r in range(world):
+        a, b = row_band(S, r, world)
+        if r != rank and b > a:
+            full[:, a:b] = recv[r, :, :b - a]
+    return full
+
+
 def sharded_refocus_stack(vp, a_list, group=None, postprocess=True, refi=False, view_zeroed=None, transport='nccl',
-                          peer_stack=None, coef=None):
+                          peer_stack=None, coef=None, shard='slices'):
     """Slice-sharded LfpRefocuser.shift_and_sum on device tensors: every rank passes the same light field `vp`
     (M,M,S,T,3) and gets the full finished stack back.
     refi=True: `a_list` are the up-sampled-pixel parameters of the refinement path (range(M*r0, M*r1)); each rank
     prefilters the light field itself (shift independent) and evaluates its own slices.
-    transport='p2p' needs a `PeerStack` of the stack's shape (reusable across light fields) and refi=True."""
+    transport='p2p' needs a `PeerStack` of the stack's shape (reusable across light fields) and refi=True.
+    shard='rows' (refi only): every rank computes a band of image rows of ALL slices instead of a block of slices."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     a_list = list(a_list)
@@ -218,12 +266,14 @@ def sharded_refocus_stack(vp, a_list, group=None, postprocess=True, refi=False, 
     if transport == 'p2p':
         if peer_stack is None:
             raise ValueError("transport='p2p' needs a PeerStack")
-        local_block(vp, a_list, rank, world, refi=refi, view_zeroed=view_zeroed, fanout=peer_stack.fanout(lo), coef=coef)
-        peer_stack.barrier()
+        peer_stack.barrier()                 # every rank has finished reading the previous contents of its stack
+        local_block(vp, a_list, rank, world, refi=refi, view_zeroed=view_zeroed, coef=coef, shard=shard,
+                    fanout=peer_stack.fanout(lo if shard == 'slices' else 0))
+        peer_stack.barrier()                 # ... and all stores of this stack have landed
         full = peer_stack.local
     elif transport == 'nccl':
-        local = local_block(vp, a_list, rank, world, refi=refi, view_zeroed=view_zeroed, coef=coef)
-        full = gather_slices(local, n_total, group)
+        local = local_block(vp, a_list, rank, world, refi=refi, view_zeroed=view_zeroed, coef=coef, shard=shard)
+        full = gather_slices(local, n_total, group) if shard == 'slices' else gather_rows(local, group)
     else:
         raise ValueError("transport must be 'p2p' or 'nccl'")
     return finish_stack(full, postprocess)

@@ -145,7 +145,7 @@ def test_prefilter_register_window_kernels_equal_table_kernels(cuda):
             nat.check(L.pcb_refi_prefilter_toeplitz(p(vp), ops._pcb_dtype(vp), M, S, T, 3, p(plan.py_v), p(plan.py_f),
                                                     plan.Kpy, p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp),
                                                     p(coef), hx.ctypes.data_as(C.c_void_p), int(hx.size), cx, xlo, xhi,
-                                                    hy.ctypes.data_as(C.c_void_p), int(hy.size), cy, ylo, yhi, st))
+                                                    hy.ctypes.data_as(C.c_void_p), int(hy.size), cy, ylo, yhi, None, st))
         else:
             nat.check(L.pcb_refi_prefilter(p(vp), ops._pcb_dtype(vp), M, S, T, 3, p(plan.py_v), p(plan.py_f), plan.Kpy,
                                            p(plan.px_v), p(plan.px_f), plan.Kpx, p(plan.z_dev), p(tmp), p(coef), st))

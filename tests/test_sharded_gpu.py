@@ -44,6 +44,58 @@ def test_blocks_of_every_rank_reassemble_the_unsharded_stack(cuda, world, refi):
     assert torch.equal(par.finish_stack(full), ops.refocuser_postprocess(ref))
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_row_bands_of_every_rank_reassemble_the_unsharded_refined_stack(cuda, world):
+    """shard='rows': every rank computes a band of image rows of ALL slices from a prefilter restricted to the rows the band
+    needs; the bands written into one stack must equal the unsharded stack bit for bit, min / max included."""
+    import torch
+    from plenopticam_b200 import ops, parallel as par
+    from plenopticam_b200.lfp_refocuser.refinement import refocus_refi
+    M, S, T = 7, 101, 47                                    # 13 row groups: ragged for 2, 3 and 8 ranks
+    vp = _lf(cuda, M, S, T, 6)
+    a_list = list(range(-2 * M, 2 * M + 1))
+    mask = ops.aperture_mask(M)
+    mm_ref = ops.new_minmax()
+    ref = refocus_refi(vp, a_list, mask, mm=mm_ref)
+    full = torch.full((len(a_list), S, T, 3), float('nan'), dtype=torch.float32, device=vp.device)
+    mm = ops.new_minmax()
+    covered = 0
+    for rank in range(world):
+        y_lo, y_hi = par.row_band(S, rank, world)
+        assert y_lo % par.ROW_GROUP == 0 and (y_hi % par.ROW_GROUP == 0 or y_hi == S)
+        covered += y_hi - y_lo
+        out = par.local_block(vp, a_list, rank, world, refi=True, shard='rows',
+                              fanout=[(full.data_ptr(), mm.data_ptr())])
+        assert out is None
+    assert covered == S
+    assert torch.equal(full, ref)
+    assert ops.minmax_values(mm) == ops.minmax_values(mm_ref)
+    # a band through `out=` touches its own rows only
+    canvas = torch.full_like(full, -7.0)
+    y_lo, y_hi = par.row_band(S, 1, world)
+    par.local_block(vp, a_list, 1, world, refi=True, shard='rows', out=canvas)
+    assert torch.equal(canvas[:, y_lo:y_hi], ref[:, y_lo:y_hi])
+    assert bool((canvas[:, :y_lo] == -7.0).all()) and bool((canvas[:, y_hi:] == -7.0).all())
+    with pytest.raises(NotImplementedError):
+        par.local_block(vp, a_list, 0, world, refi=False, shard='rows')
+
+
+def test_row_band_at_illum_angular_size(cuda):
+    """M = 15 with shifts up to +-30: the vertical windows reach 14 rows beyond a band; the band plan must cover them."""
+    import torch
+    from plenopticam_b200 import ops, parallel as par
+    from plenopticam_b200.lfp_refocuser.refinement import refocus_refi
+    M, S, T = 15, 90, 33
+    vp = _lf(cuda, M, S, T, 7)
+    a_list = list(range(-2 * M, 2 * M))
+    mask = ops.aperture_mask(M)
+    ref = refocus_refi(vp, a_list, mask)
+    full = torch.zeros_like(ref)
+    for rank in range(4):
+        par.local_block(vp, a_list, rank, 4, refi=True, shard='rows', out=full)
+    assert torch.equal(full, ref)
+
+
 def test_refinement_fanout_writes_every_destination(cuda):
     """pcb_refocus_refi_fanout: the kernel stores each finished slice (and folds the min / max) into all destinations -
     here three buffers on the same GPU stand in for the peer-mapped stacks of other GPUs."""
