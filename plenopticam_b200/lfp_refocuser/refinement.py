@@ -324,11 +324,19 @@ class RefinementPlan(object):
         h_lo, h_hi = int(first.min()), int(first.max()) + self.Kgy
         # coefficient rows are produced in blocks of 6 (horizontal pass) out of strips of 16 / groups of 8 (y prefilter)
         c_lo, c_hi = (h_lo // 6) * 6, min(-(-h_hi // 6) * 6, S)
-        slack = 16 + max(self.Kpy, 32)
+        slack = 16 + self.Kpy                    # whole strips of 16 rows + the longest (grouped) prefilter window
         r = nat.RefiRows()
         r.out_lo, r.out_hi, r.h_lo, r.h_hi = y_lo, y_hi, c_lo, c_hi
         r.tmp_lo, r.tmp_hi = max(c_lo - slack, 0), min(c_hi + slack, S)
         return r
+
+    def halo_rows(self):
+        """Rows of the horizontal pass a band needs beyond each inner edge (largest reach of a vertical window)."""
+        G = self._dy_first_host.shape[1]
+        rel = self._dy_first_host - np.arange(G)[None, :] * GROUP            # window start relative to the group's first row
+        up = int(max(-rel.min(), 0))
+        down = int(max((rel + self.Kgy).max() - GROUP, 0))
+        return max(up, down)
 
     def quads(self, n0, nb):
         """pcb_refi_quads_t of slices n0 .. n0+nb-1 (device tables, cached per slice range), or None."""

@@ -97,10 +97,26 @@ def gather_slices(local, n_total, group=None):
 ROW_GROUP = 8        # row bands start on multiples of the vertical pass' group size (RF_GROUP)
 
 
-def row_band(S, rank, world):
-    """[y_lo, y_hi) of this rank in a ROW-sharded stack: whole groups of ROW_GROUP rows, balanced."""
-    g_lo, g_hi = shard_bounds(-(-int(S) // ROW_GROUP), rank, world)
-    return g_lo * ROW_GROUP, min(g_hi * ROW_GROUP, int(S))
+def row_band(S, rank, world, halo=0):
+    """[y_lo, y_hi) of this rank in a ROW-sharded stack: whole groups of ROW_GROUP rows.  `halo` (rows a band needs beyond
+    each of its inner edges: the reach of the vertical windows) balances band + halo instead of the band alone: the first
+    and the last rank have one inner edge only and get correspondingly taller bands."""
+    S, world = int(S), int(world)
+    G = -(-S // ROW_GROUP)
+    if world == 1:
+        return 0, S
+    hg = float(halo) / ROW_GROUP
+    cost = (G + hg * (2 * world - 2)) / world
+    sizes = [max(cost - hg * (1 if r in (0, world - 1) else 2), 0.0) for r in range(world)]
+    scale = G / sum(sizes) if sum(sizes) > 0 else 0.0
+    edges = [0.0]
+    for v in sizes:
+        edges.append(edges[-1] + v * scale)
+    b = [int(round(e)) for e in edges]
+    b[0], b[-1] = 0, G
+    for r in range(1, world + 1):                      # monotone
+        b[r] = max(b[r], b[r - 1])
+    return b[rank] * ROW_GROUP, min(b[rank + 1] * ROW_GROUP, S)
 
 
 def local_block(vp, a_list, rank, world, refi=False, view_zeroed=None, out=None, fanout=None, coef=None, shard='slices'):
@@ -124,7 +140,7 @@ def local_block(vp, a_list, rank, world, refi=False, view_zeroed=None, out=None,
         from .lfp_refocuser.refinement import device_plan, refocus_refi
         mask = ops.aperture_mask(vp.shape[0]) if view_zeroed is None else view_zeroed
         plan = device_plan(S, T, int(vp.shape[0]), a_list, mask, vp.device)
-        y_lo, y_hi = row_band(S, rank, world)
+        y_lo, y_hi = row_band(S, rank, world, halo=plan.halo_rows())
         if out is None and fanout is None:
             out = torch.empty((len(a_list), S, T, Cn), dtype=torch.float32, device=vp.device)
         if y_hi > y_lo:
@@ -231,20 +247,20 @@ class PeerStack(object):
 # ----------------------------------------------------------------------------------------------------------
 # the sharded stack
 # ----------------------------------------------------------------------------------------------------------
-def gather_rows(full, group=None):
+def gather_rows(full, group=None, halo=0):
     """All-gather of the row bands of a ROW-sharded stack (baseline transport): every rank's band of `full` (N,S,T,C) is
     sent to everybody and written into place."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     N, S = int(full.shape[0]), int(full.shape[1])
-    hmax = max(row_band(S, r, world)[1] - row_band(S, r, world)[0] for r in range(world))
-    y_lo, y_hi = row_band(S, rank, world)
+    bands = [row_band(S, r, world, halo) for r in range(world)]
+    hmax = max(b - a for a, b in bands)
+    y_lo, y_hi = bands[rank]
     send = torch.zeros((N, hmax) + tuple(full.shape[2:]), dtype=full.dtype, device=full.device)
     send[:, :y_hi - y_lo] = full[:, y_lo:y_hi]
     recv = torch.empty((world,) + tuple(send.shape), dtype=full.dtype, device=full.device)
     dist.all_gather_into_tensor(recv, send, group=group)
-    for r in range(world):
-        a, b = row_band(S, r, world)
+    for r, (a, b) in enumerate(bands):
         if r != rank and b > a:
             full[:, a:b] = recv[r, :, :b - a]
     return full
@@ -273,7 +289,14 @@ def sharded_refocus_stack(vp, a_list, group=None, postprocess=True, refi=False, 
         full = peer_stack.local
     elif transport == 'nccl':
         local = local_block(vp, a_list, rank, world, refi=refi, view_zeroed=view_zeroed, coef=coef, shard=shard)
-        full = gather_slices(local, n_total, group) if shard == 'slices' else gather_rows(local, group)
+        if shard == 'slices':
+            full = gather_slices(local, n_total, group)
+        else:
+            from . import ops
+            from .lfp_refocuser.refinement import device_plan
+            mask = ops.aperture_mask(vp.shape[0]) if view_zeroed is None else view_zeroed
+            plan = device_plan(int(vp.shape[2]), int(vp.shape[3]), int(vp.shape[0]), a_list, mask, vp.device)
+            full = gather_rows(local, group, halo=plan.halo_rows())
     else:
         raise ValueError("transport must be 'p2p' or 'nccl'")
     return finish_stack(full, postprocess)

@@ -50,18 +50,20 @@ def test_row_bands_of_every_rank_reassemble_the_unsharded_refined_stack(cuda, wo
     needs; the bands written into one stack must equal the unsharded stack bit for bit, min / max included."""
     import torch
     from plenopticam_b200 import ops, parallel as par
-    from plenopticam_b200.lfp_refocuser.refinement import refocus_refi
+    from plenopticam_b200.lfp_refocuser.refinement import device_plan, refocus_refi
     M, S, T = 7, 101, 47                                    # 13 row groups: ragged for 2, 3 and 8 ranks
     vp = _lf(cuda, M, S, T, 6)
     a_list = list(range(-2 * M, 2 * M + 1))
     mask = ops.aperture_mask(M)
+    halo = device_plan(S, T, M, a_list, mask, vp.device).halo_rows()
+    assert 0 < halo < 40
     mm_ref = ops.new_minmax()
     ref = refocus_refi(vp, a_list, mask, mm=mm_ref)
     full = torch.full((len(a_list), S, T, 3), float('nan'), dtype=torch.float32, device=vp.device)
     mm = ops.new_minmax()
     covered = 0
     for rank in range(world):
-        y_lo, y_hi = par.row_band(S, rank, world)
+        y_lo, y_hi = par.row_band(S, rank, world, halo)
         assert y_lo % par.ROW_GROUP == 0 and (y_hi % par.ROW_GROUP == 0 or y_hi == S)
         covered += y_hi - y_lo
         out = par.local_block(vp, a_list, rank, world, refi=True, shard='rows',
@@ -72,7 +74,7 @@ def test_row_bands_of_every_rank_reassemble_the_unsharded_refined_stack(cuda, wo
     assert ops.minmax_values(mm) == ops.minmax_values(mm_ref)
     # a band through `out=` touches its own rows only
     canvas = torch.full_like(full, -7.0)
-    y_lo, y_hi = par.row_band(S, 1, world)
+    y_lo, y_hi = par.row_band(S, 1, world, halo)
     par.local_block(vp, a_list, 1, world, refi=True, shard='rows', out=canvas)
     assert torch.equal(canvas[:, y_lo:y_hi], ref[:, y_lo:y_hi])
     assert bool((canvas[:, :y_lo] == -7.0).all()) and bool((canvas[:, y_hi:] == -7.0).all())

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--shard", default="rows", choices=["rows", "slices"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -49,11 +50,19 @@ def main():
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record(stream)
-        coef = prefilter(vp, plan)
+        if args.shard == "rows":
+            y_lo, y_hi = par.row_band(S, rank, world, plan.halo_rows())
+            rows = plan.rows(0, len(a_list), y_lo, y_hi)
+            coef = prefilter(vp, plan, rows=rows)
+        else:
+            coef = prefilter(vp, plan)
         ev[1].record(stream)
         peer.barrier()
         ev[2].record(stream)
-        refocus_refi(vp, a_list, mask, plan=plan, fanout=peer.fanout(lo), coef=coef, n_range=(lo, hi))
+        if args.shard == "rows":
+            refocus_refi(vp, a_list, mask, plan=plan, fanout=peer.fanout(0), coef=coef, row_range=(y_lo, y_hi))
+        else:
+            refocus_refi(vp, a_list, mask, plan=plan, fanout=peer.fanout(lo), coef=coef, n_range=(lo, hi))
         ev[3].record(stream)
         peer.barrier()
         ev[4].record(stream)
@@ -67,7 +76,9 @@ def main():
             acc.append(t.cpu().numpy())
     if rank == 0:
         med = np.median(np.asarray(acc), axis=0)
-        print(json.dumps({"n_gpus": world, "slices": len(a_list), "ms_max_over_ranks": dict(zip(names + ["total"], med.tolist()))}))
+        if args.shard == "rows":
+            print("rank 0 rows:", {k: getattr(rows, k) for k in ("out_lo", "out_hi", "h_lo", "h_hi", "tmp_lo", "tmp_hi")})
+        print(json.dumps({"n_gpus": world, "shard": args.shard, "slices": len(a_list), "ms_max_over_ranks": dict(zip(names + ["total"], med.tolist()))}))
     peer.close()
     dist.destroy_process_group()
 
