@@ -14,8 +14,10 @@ The reference is single-threaded Python.  To use all host cores the runner start
 the reference on its own exposure (independent exposures are how the reference would be scaled out), and reports
 the aggregate.  The data generators are the same seeded ones the GPU arm uses (plenopticam_b200/misc/synth.py).
 """
+import atexit
 import multiprocessing as mp
 import os
+import shutil
 import sys
 import tempfile
 import time
@@ -36,6 +38,26 @@ def available():
     return ref_shim.reference_available()
 
 
+def _private_reference():
+    """Give THIS process its own byte-identical copy of the reference package before importing it.  The reference rewrites
+    `plenopticam/cfg/cfg.json` inside its package directory whenever a config object is created or saved
+    (cfg/cfg.py:62-120); N worker processes doing that to one file race (one of them reads an empty file)."""
+    if ref_shim._LOADED is not None or "plenopticam" in sys.modules:
+        return
+    src = os.path.join(ref_shim.REFERENCE_ROOT, "plenopticam")
+    if _RUN_DIR is not None:                               # pool worker: the parent removes the run directory
+        dst = os.path.join(_RUN_DIR, "p%d" % os.getpid())
+        os.makedirs(dst)
+    else:
+        dst = tempfile.mkdtemp(prefix="pcb_ref_%d_" % os.getpid())
+        atexit.register(shutil.rmtree, dst, True)
+    shutil.copytree(src, os.path.join(dst, "plenopticam"), ignore=shutil.ignore_patterns("__pycache__"))
+    ref_shim.REFERENCE_ROOT = dst
+
+
+_RUN_DIR = None
+
+
 def _quiet_cfg(tmp, cent, pat, M, ran_refo):
     cfg, sta = ref_shim.make_cfg_sta(tmp, cent, pat, M, ran_refo=ran_refo)
     cfg.lfpimg = {}
@@ -48,6 +70,7 @@ def _quiet_cfg(tmp, cent, pat, M, ran_refo):
 
 def hot_path_once(raw, cent, pat, M, ran_refo):
     """One exposure through the reference's own hot-path classes; returns (stage seconds, sRGB stack)."""
+    _private_reference()
     ref_shim.load_reference()
     from plenopticam.lfp_aligner.lfp_resampler import LfpResampler
     from plenopticam.lfp_extractor.lfp_rearranger import LfpRearranger
@@ -101,10 +124,16 @@ def illum_sample(LY_full, LX_full, pitch, M, n_slices_full, area_div=16, n_slice
     LY, LX = max(8, int(round(LY_full / f))), max(8, int(round(LX_full / f)))
     ran = (-(n_slices // 2), n_slices - n_slices // 2)
     jobs = [(seed0 + k, LY, LX, pitch, M, ran) for k in range(procs)]
+    global _RUN_DIR
     t0 = time.perf_counter()
     if procs > 1:
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_illum_job, jobs)
+        _RUN_DIR = tempfile.mkdtemp(prefix="pcb_ref_run_")     # inherited by the forked workers
+        try:
+            with mp.get_context("fork").Pool(procs) as pool:
+                res = pool.map(_illum_job, jobs)
+        finally:
+            shutil.rmtree(_RUN_DIR, True)
+            _RUN_DIR = None
     else:
         res = [_illum_job(jobs[0])]
     wall = time.perf_counter() - t0
@@ -126,6 +155,7 @@ def config1_full(with_white=True):
     """BASELINE.json configs[0] in full through the reference's stage classes: rec grid 186 x 279 lenslets, pitch 11 px,
     M = 9, white image, LfpAligner (de-vignetting + local resampling) -> LfpExtractor -> LfpRefocuser, ran_refo [-1, 1].
     One process (the reference is single-threaded).  Returns stage seconds + output checksums."""
+    _private_reference()
     ref_shim.load_reference()
     from plenopticam.lfp_aligner import LfpAligner
     from plenopticam.lfp_extractor import LfpExtractor
