@@ -205,6 +205,17 @@ int pcb_refocus_int_srgb(const void *vp, int dtype, int M, int S, int T, int C, 
  *       view_zeroed_host / view_zeroed: the M*M mask on the host and on the device
  *       tmp: float32 scratch (N,M,S,T,3); out: float32 (N,S,T,3); mm: nullable fused min/max of the stack.
  * ------------------------------------------------------------------------------------------------ */
+/* The summed UP-SAMPLED image of ONE refined slice, i.e. `final_img` of lfp_shiftandsum.py:123-124 before the down-sampling
+ * of :135 - what the reference histogram-aligns, sRGB-encodes and writes as upscale_<a/M>.png (:126-132).
+ *   coef: B-spline coefficients from pcb_refi_prefilter;  a: shift in up-sampled pixels;
+ *   fx[T*M], wx[T*M][4] / fy[S*M], wy[S*M][4]: first coefficient and the four cubic B-spline weights of every up-sampled
+ *   sample (img_resize(view, M), misc/data_proc.py:57-92; device);  tmp: float32 (M, S, T*M, 3);  out: float32 (S*M, T*M, 3).
+ * A slow path (732 MB per slice at Illum size) for callers that want the file; contrast / sRGB: pcb_contrast_bounds +
+ * pcb_contrast_srgb on `out`. */
+int pcb_refi_upscaled_slice(const float *coef, int M, int S, int T, int C, int a,
+                            const int32_t *fx, const float *wx, const int32_t *fy, const float *wy,
+                            const uint8_t *view_zeroed_host, float *tmp, float *out, void *stream);
+
 /* Row restriction of the refinement passes (host struct, nullable everywhere: NULL = the whole image).  For a ROW-sharded
  * stack a rank produces the output rows [out_lo, out_hi) of every slice (out_lo a multiple of 8; out_hi too unless it is S);
  * for that it needs the rows [h_lo, h_hi) of the horizontal pass = of the B-spline coefficients, and the prefilter's x pass

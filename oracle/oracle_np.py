@@ -441,7 +441,21 @@ def img_resize(img, scale):
     return np.einsum('yn,nmc,xm->yxc', Wy, img, Wx, optimize=True)
 
 
-def refocus_refi(vp, ran_refo, M, a_list=None):
+def refocus_refi_upscaled(vp, ran_refo, M, a_list=None):
+    """The summed UP-SAMPLED image of every refined slice BEFORE the down-sampling (`final_img` at
+    lfp_shiftandsum.py:123-124): what the reference histogram-aligns, sRGB-encodes and writes as upscale_*.png (:126-132).
+    float64 (N, S*M, T*M, C)."""
+    return refocus_refi(vp, ran_refo, M, a_list=a_list, _upscaled=True)
+
+
+def uint8_norm(img):
+    """misc/normalizer.py:48-51 — global min / max of the float32 cast, round-half-even."""
+    d = np.asarray(img, dtype='float32')
+    mn, mx = d.min(), d.max()
+    return np.asarray(np.round(norm_fun(d, mn, mx) * (2 ** 8 - 1)), dtype=np.uint8)
+
+
+def refocus_refi(vp, ran_refo, M, a_list=None, _upscaled=False):
     """lfp_shiftandsum.py:77-139 with opt_refi: every view upsampled xM (:102), shifts in upsampled
     pixels a in range(M*r0, M*r1) (:93-94), summed, cropped (:123-124), downsampled x1/M (:135).
     Materialises the upsampled views; use only at small sizes.  `a_list`: evaluate only these members of the
@@ -471,7 +485,7 @@ def refocus_refi(vp, ran_refo, M, a_list=None):
                     continue
                 xi = np.clip(xs + a * (c - i), 0, T * M - 1)
                 acc += ups[(j, i)][yi][:, xi]
-        stack.append(img_resize(acc, 1. / M))
+        stack.append(acc if _upscaled else img_resize(acc, 1. / M))
     return np.asarray(stack)
 
 

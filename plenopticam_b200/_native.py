@@ -156,6 +156,7 @@ _SIGNATURES = {
                               _vp, _vp, _vp]),
     "pcb_refocus_refi_fanout": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _vp, _vp, _vp]),
+    "pcb_refi_upscaled_slice": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcb_peer_alloc": (_i, [_i64, C.POINTER(C.c_void_p)]),
     "pcb_peer_free": (_i, [_vp]),
     "pcb_peer_export": (_i, [_vp, C.c_char_p]),

@@ -473,6 +473,16 @@ int pcb_refocus_refi_fanout(const float *coef, int M, int S, int T, int C, int N
                          view_zeroed_host, tmp, dst, as_stream(stream), quads_host, rows_host);
 }
 
+int pcb_refi_upscaled_slice(const float *coef, int M, int S, int T, int C, int a, const int32_t *fx, const float *wx,
+                            const int32_t *fy, const float *wy, const uint8_t *view_zeroed_host, float *tmp, float *out,
+                            void *stream) {
+    PCB_REQUIRE(coef && fx && wx && fy && wy && view_zeroed_host && tmp && out, "pointers");
+    PCB_REQUIRE(M > 0 && M <= RF_MAXM && M % 2 == 1 && S >= 4 && T >= 4 && S <= 65535, "sizes, odd M <= 32");
+    PCB_REQUIRE((int64_t)S * M <= 65535, "S * M <= 65535");
+    PCB_REQUIRE(C == 3, "3 colour channels (lfp_shiftandsum.py:97)");
+    return launch_refi_upscaled(coef, M, S, T, a, fx, wx, fy, wy, view_zeroed_host, tmp, out, as_stream(stream));
+}
+
 // ---- peer-mapped buffers (slice-sharded stacks) --------------------------------------------------------------------
 int pcb_peer_alloc(int64_t bytes, void **dptr_host) {
     PCB_REQUIRE(bytes > 0 && dptr_host != nullptr, "bytes > 0, dptr");

@@ -538,6 +538,77 @@ refine_v_kernel(const float *__restrict__ H, int M, int S, int E, const float *_
     if (dst.mm[0] != nullptr) block_minmax_commit_fanout(mn, mx, dst);
 }
 
+// ---- the summed UP-SAMPLED image of one slice (slow path) -----------------------------------------------------------
+// The reference writes, per refined slice, the up-sampled sum itself as upscale_*.png (lfp_shiftandsum.py:126-132).  With
+// coef = B-spline coefficients of the views, Up_ji = Ey . coef_ji . Ex^T (4 taps per fine sample and axis) and
+//     U_a[Y, X] = (1/M) sum_{(j,i) active} Up_ji[clamp(Y + a (c0 - j)), clamp(X + a (c0 - i))]
+// separates into a horizontal pass per view row (G_j, S x T M) and a vertical pass over the view rows.  732 MB per slice
+// at Illum size: offered for exporters that want the file, not part of the timed path.
+__global__ void __launch_bounds__(256)
+refi_up_h_kernel(const float *__restrict__ coef, int M, int S, int T, int TM, int a, const int32_t *__restrict__ fx,
+                 const float4 *__restrict__ wx, RefineHCtl ctl, float *__restrict__ G) {
+    const int X = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, j = blockIdx.z;
+    const uint32_t act = ctl.active[j];
+    if (act == 0u || X >= TM) return;
+    const int c0 = M / 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int i = 0; i < M; ++i) {
+        if (!((act >> i) & 1u)) continue;
+        const int Xs = min(max(X + a * (c0 - i), 0), TM - 1);
+        const int f = __ldg(fx + Xs);
+        const float4 w = __ldg(wx + Xs);
+        const float *row = coef + (((size_t)(j * M + i) * S + r) * T + f) * 3;
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int o = min(f + q, T - 1) - f;                 // a padded tap (weight 0) never leaves the row
+            a0 = fmaf(wv[q], __ldg(row + o * 3 + 0), a0);
+            a1 = fmaf(wv[q], __ldg(row + o * 3 + 1), a1);
+            a2 = fmaf(wv[q], __ldg(row + o * 3 + 2), a2);
+        }
+    }
+    float *o = G + (((size_t)j * S + r) * TM + X) * 3;
+    o[0] = a0; o[1] = a1; o[2] = a2;
+}
+
+__global__ void __launch_bounds__(256)
+refi_up_v_kernel(const float *__restrict__ G, int M, int S, int SM, int E, int a, const int32_t *__restrict__ fy,
+                 const float4 *__restrict__ wy, RefineHCtl ctl, float *__restrict__ U) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+    if (e >= E) return;
+    const int c0 = M / 2;
+    float acc = 0.f;
+    for (int j = 0; j < M; ++j) {
+        if (ctl.active[j] == 0u) continue;
+        const int Ys = min(max(Y + a * (c0 - j), 0), SM - 1);
+        const int f = __ldg(fy + Ys);
+        const float4 w = __ldg(wy + Ys);
+        const float *col = G + ((size_t)j * S + f) * E + e;
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc = fmaf(wv[p], __ldg(col + (size_t)(min(f + p, S - 1) - f) * E), acc);
+    }
+    U[(size_t)Y * E + e] = acc * (1.0f / (float)M);
+}
+
+static int launch_refi_upscaled(const float *coef, int M, int S, int T, int a, const int32_t *fx, const float *wx,
+                                const int32_t *fy, const float *wy, const uint8_t *view_zeroed_host, float *G, float *U,
+                                cudaStream_t st) {
+    RefineHCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    for (int j = 0; j < M; ++j)
+        for (int i = 0; i < M; ++i)
+            if (!view_zeroed_host[j * M + i]) ctl.active[j] |= 1u << i;
+    const int TM = T * M, SM = S * M, E = TM * 3;
+    refi_up_h_kernel<<<dim3((TM + 255) / 256, S, M), 256, 0, st>>>(coef, M, S, T, TM, a, fx,
+                                                                   reinterpret_cast<const float4 *>(wx), ctl, G);
+    PCB_LAUNCH_OK();
+    refi_up_v_kernel<<<dim3((E + 255) / 256, SM), 256, 0, st>>>(G, M, S, SM, E, a, fy, reinterpret_cast<const float4 *>(wy),
+                                                               ctl, U);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------------------
 // tx / ty: interior Toeplitz description of the two axes (lo > hi: none)
 // rows: optional restriction (row-sharded stacks): the x pass runs for rows [tmp_lo, tmp_hi) only and the y pass produces

@@ -13,6 +13,13 @@ from ..lfp_extractor.lfp_viewpoints import LfpViewpoints
 
 class LfpShiftAndSum(LfpViewpoints):
 
+    #: The reference writes, for every refined slice, the summed UP-SAMPLED image as `upscale_<a/M>.png` through
+    #: LfpExporter.save_refo_slice (lfp_shiftandsum.py:126-132; 6510 x 9375 px per slice at Illum size).  File export is
+    #: outside this package, so the side effect is opt-in: set `upscale_sink` to a callable `(fname, img)` - e.g.
+    #: `lambda a, img: LfpExporter(cfg=cfg, sta=sta).save_refo_slice(a, img, string='upscale_')` with the reference's
+    #: exporter - and it receives the same float32 sRGB image under the same name, slice by slice (slow path).
+    upscale_sink = None
+
     def __init__(self, lfp_img_align=None, *args, **kwargs):
         super(LfpShiftAndSum, self).__init__(*args, **kwargs)
         self.lfp_img_align = lfp_img_align
@@ -64,6 +71,14 @@ class LfpShiftAndSum(LfpViewpoints):
             from .refinement import refocus_refi
             a_list = range(M * ran[0], M * ran[1])
             self._dev_stack = refocus_refi(vp, a_list, self.circular_view_aperture_mask())
+            if self.upscale_sink is not None:
+                from .refinement import device_plan, upscaled_slices
+                mask = self.circular_view_aperture_mask()
+                plan = device_plan(int(vp.shape[2]), int(vp.shape[3]), M, list(a_list), mask, vp.device)
+                for a, img in upscaled_slices(vp, list(a_list), mask, plan):
+                    if self.sta.interrupt:
+                        return False
+                    self.upscale_sink(np.round(a / M, 2), np.asarray(ops.to_host(img)))        # fname as in :130
         else:
             a_list = range(*ran)
             self._dev_stack = ops.refocus_int(vp, a_list, self.circular_view_aperture_mask())

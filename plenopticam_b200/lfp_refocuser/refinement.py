@@ -108,6 +108,20 @@ class AxisOperators(object):
         if nd != n:
             raise ValueError("down-sampled size %d != %d" % (nd, n))
         dn = spline_matrix(nf, nd)                      # img_resize(sum, 1/M):  n*M -> n
+        # the four cubic B-spline taps of every up-sampled sample (rows of ev_up): first coefficient + weights, padded with
+        # zeros where a row has fewer (the up-sampled image itself is only needed by `upscaled_slices`)
+        ev = ev_up.tocsr()
+        self.up_first = np.zeros(nf, dtype=np.int32)
+        self.up_w = np.zeros((nf, 4), dtype=np.float32)
+        for X in range(nf):
+            cols = ev.indices[ev.indptr[X]:ev.indptr[X + 1]]
+            vals = ev.data[ev.indptr[X]:ev.indptr[X + 1]]
+            keep = vals != 0
+            cols, vals = cols[keep], vals[keep]
+            f0 = int(cols.min())
+            assert cols.max() - f0 < 4
+            self.up_first[X] = f0
+            self.up_w[X, cols - f0] = vals
         P = np.linalg.inv(colloc.toarray())
         self.p_first, pv = _band(P, BAND_EPS)
         self.p_vals = pv.astype(np.float32)
@@ -447,6 +461,37 @@ def refocus_refi(vp, a_list, view_zeroed, mm=None, plan=None, out=None, fanout=N
                                             C.byref(qd) if qd is not None else None,
                                             C.byref(rows) if rows is not None else None, st))
     return out
+
+
+def upscaled_slices(vp, a_values, view_zeroed, plan, coef=None, srgb=True):
+    """Generator over the summed UP-SAMPLED images of the refined slices `a_values` (shifts in up-sampled pixels, members
+    of the plan's range): float32 CUDA tensors (S*M, T*M, 3) - `final_img` of lfp_shiftandsum.py:123-124 and, with
+    srgb=True, the `upscale_img` the reference hands to LfpExporter.save_refo_slice (:127-131: histogram-aligned against
+    itself, sRGB-encoded).  One buffer is reused: consume (or clone) a slice before asking for the next."""
+    import ctypes as C
+    import torch
+    from .. import _native as nat
+    from .. import ops
+    M, M2, S, T, Cn = (int(v) for v in vp.shape)
+    Ay, Bx = build_operators(S, T, M, plan.a_list)
+    dev = vp.device
+    if coef is None:
+        coef = prefilter(vp, plan)
+    t = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+    fx, wx, fy, wy = t(Bx.up_first), t(Bx.up_w), t(Ay.up_first), t(Ay.up_w)
+    G = torch.empty((M, S, T * M, Cn), dtype=torch.float32, device=dev)
+    U = torch.empty((S * M, T * M, Cn), dtype=torch.float32, device=dev)
+    out = torch.empty_like(U) if srgb else None
+    L, p = nat.lib(), ops._ptr
+    z_ptr = plan.z_host.ctypes.data_as(C.c_void_p)
+    for a in a_values:
+        nat.check(L.pcb_refi_upscaled_slice(p(coef), M, S, T, Cn, int(a), p(fx), p(wx), p(fy), p(wy), z_ptr, p(G), p(U),
+                                            ops._stream()))
+        if not srgb:
+            yield int(a), U
+            continue
+        lohi = ops.contrast_bounds(U)                       # auto_hist_align(final_img.copy(), ref_img=final_img, opt=True)
+        yield int(a), ops.contrast_srgb(U, lohi, mm=ops.minmax_f32(U), out=out)
 
 
 def prefilter(vp, plan, rows=None):

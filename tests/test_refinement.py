@@ -201,3 +201,55 @@ def test_quad_kernel_equals_tap_kernel_bit_for_bit(cuda):
         finally:
             os.environ.pop("PCB_REFINE_KERNEL", None)
         assert torch.equal(got, ref)
+
+
+def test_upscaled_oracle_matches_the_reference_png_bytes():
+    """The oracle's up-sampled sum -> auto_hist_align(ref = itself) -> sRGB -> uint8_norm equals, byte for byte, what the
+    unmodified reference handed to imageio for its upscale_*.png files (oracle/gen_golden_upscale.py)."""
+    g = golden("refocus_upscale_u16")
+    ups = onp.refocus_refi_upscaled(g["vp"], tuple(int(v) for v in g["ran_refo"]), int(g["M"]))
+    o8 = np.stack([onp.uint8_norm(onp.srgb_conv(onp.auto_hist_align(u, u))) for u in ups])
+    assert np.array_equal(o8, g["upscaled_u8"])
+    assert [str(n) for n in g["names"]] == ["%s.png" % np.round(a / 5, 2) for a in range(-5, 5)]
+
+
+@pytest.mark.gpu
+def test_upscale_sink_receives_the_reference_png_content(cuda):
+    """LfpShiftAndSum.upscale_sink: the opt-in form of the reference's upscale_*.png side effect (lfp_shiftandsum.py:126-132).
+    Quantised like misc.save_img_file would (Normalizer.uint8_norm) the images equal the reference's bytes up to 1 LSB, and
+    the names are the reference's."""
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_refocuser import LfpShiftAndSum
+    g = golden("refocus_upscale_u16")
+    M = int(g["M"])
+    cfg, sta = make_cfg(M=M, ran_refo=[int(v) for v in g["ran_refo"]], refi=True)
+    got = []
+    obj = LfpShiftAndSum(vp_img_arr=g["vp"], cfg=cfg, sta=sta)
+    obj.upscale_sink = lambda fname, img: got.append((fname, np.array(img)))
+    assert obj.main() is True
+    assert np.abs(obj.refo_stack - g["stack"]).max() <= 5e-6 * np.abs(g["stack"]).max()
+    assert ["%s.png" % f for f, _ in got] == [str(n) for n in g["names"]]
+    for (_, img), want in zip(got, g["upscaled_u8"]):
+        assert img.dtype == np.float32 and img.shape == want.shape
+        q = ops.to_host(ops.uint8_norm(ops.to_device(img)))
+        assert np.abs(q.astype(int) - want.astype(int)).max() <= 1
+
+
+@pytest.mark.gpu
+def test_upscaled_slices_vs_oracle(cuda):
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_refocuser.refinement import device_plan, upscaled_slices
+    rng = np.random.default_rng(33)
+    M, S, T = 7, 9, 12
+    vp = (rng.random((M, M, S, T, 3)) * 65535).astype(np.uint16)
+    ran = (-1, 1)
+    a_all = list(range(M * ran[0], M * ran[1]))
+    probe = [-7, -3, 0, 6]
+    ref = onp.refocus_refi_upscaled(vp, ran, M, a_list=probe)
+    dev = ops.to_device(vp)
+    mask = ops.aperture_mask(M)
+    plan = device_plan(S, T, M, a_all, mask, dev.device)
+    for (a, U), want in zip(upscaled_slices(dev, probe, mask, plan, srgb=False), ref):
+        got = ops.to_host(U)
+        assert got.shape == (S * M, T * M, 3)
+        assert np.abs(got - want).max() <= 5e-6 * np.abs(want).max(), a
