@@ -13,7 +13,8 @@ The JSON line also carries:
   stage_ms / stage_gbs   per-stage CUDA-event times inside the timed region and achieved algorithmic GB/s
   roofline               dominant stage against the measured HBM peak (MEASURED_PEAKS.json), DRAM traffic from ncu
   roofline_smem          the persistent shift-and-sum kernel against the shared-memory roofline that actually bounds it
-  aligned_lfs_per_s      BASELINE configs[1]: align + explicit sub-aperture gather only
+  aligned_lfs_per_s      BASELINE configs[1]: align + explicit sub-aperture gather only (rotate_ms: LfpRotator on one exposure,
+                         an optional stage of the aligner that is off by default and therefore outside the step)
   refined_stack          BASELINE configs[3] on one GPU: 60 sub-pixel-refined slices of one light field
   sharded_stack          (N > 1) the same 60 slices sharded over the ranks, exchange fused into the finishing kernel
                          (peer stores over NVLink) and, beside it, the NCCL all-gather form; equality with the unsharded stack
@@ -433,6 +434,11 @@ def main():
         ms_av, _ = timed(align_vp, 1, Kx, 2)
         extras["aligned_lfs_per_s"] = world * Kx / (ms_av * 1e-3)
         extras["align_viewpoints_ms"] = ms_av / Kx
+        # ---- LfpRotator (opt_rota, off by default in the reference: cfg/constants.py): cubic B-spline rotation of one exposure
+        def rot(raw, ev=None):
+            ops.rotate(raw, 0.004)
+        ms_rot, _ = timed(rot, 1, 5, 2)
+        extras["rotate_ms"] = ms_rot / 5
 
     # ---- BASELINE configs[3]: 60 refined slices of ONE light field (same on every rank), unsharded and sharded
     refined = None
@@ -646,7 +652,7 @@ def main():
         "roofline": roofline, "roofline_smem": roofline_smem, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "e2e_classes": e2e_classes, "unfused": {k: extras[k] for k in ("explicit_gather", "explicit_gather_and_post")
                                                 if k in extras},
-        "align_viewpoints_ms": extras.get("align_viewpoints_ms"),
+        "align_viewpoints_ms": extras.get("align_viewpoints_ms"), "rotate_ms": extras.get("rotate_ms"),
         "refined_stack": refined, "sharded_stack": sharded, "batch256": batch,
         "gpu_launches": launches_per_step * K, "clocks": clocks,
     }
