@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--slices", type=int, default=64)
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-fuse-post", action="store_true")
+    ap.add_argument("--explicit-gather", action="store_true",
+                    help="separate viewpoints kernel + refocus from the 4-D array (default: refocus reads the aligned image)")
     args = ap.parse_args()
 
     import torch
@@ -41,14 +43,20 @@ def main():
         ev[0].record()
         pipe.align(raw)
         ev[1].record()
-        pipe.viewpoints()
-        ev[2].record()
-        if args.no_fuse_post or pipe.refocus_post() is False:
-            pipe.refocus()
-            ev[3].record()
-            pipe.post_process()
+        if args.explicit_gather or args.no_fuse_post:
+            pipe.viewpoints()
+            ev[2].record()
+            if args.no_fuse_post or pipe.refocus_post() is False:
+                pipe.refocus()
+                ev[3].record()
+                pipe.post_process()
+            else:
+                ev[3].record()              # fused epilogue: "refocus" below is 0, "post" carries the whole stage
         else:
-            ev[3].record()                  # fused epilogue: "refocus" below is 0, "post" carries the whole stage
+            ev[2].record()                  # no separate gather: the refocus kernel reads the aligned image
+            ev[3].record()
+            if pipe._refocus_from_aligned() is False:
+                raise SystemExit("no aligned-direct refocus form for this workload")
         ev[4].record()
         torch.cuda.synchronize()
         print("step %d: " % it + ", ".join("%s %.3f ms" % (n, ev[k].elapsed_time(ev[k + 1])) for k, n in enumerate(names)))
