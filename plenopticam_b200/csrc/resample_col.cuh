@@ -23,9 +23,9 @@
 
 namespace pcb {
 
-constexpr int RC_THREADS = 384;
-constexpr int RC_KT = 17;            // output lens columns per CTA: 17 * 15 * 3 = 765 columns ~ 2 per thread
-constexpr int RC_TS = 736;           // tile row stride in floats
+constexpr int RC_THREADS = 320;
+constexpr int RC_KT = 14;            // output lens columns per CTA: 14 * 15 * 3 = 630 columns ~ 2 per thread
+constexpr int RC_TS = 672;           // tile row stride in floats
 constexpr int RC_ROWS = 19;          // tile rows (M + 1 + scatter allowance for M = 15)
 constexpr int RC_MAX_SRC = 32;       // source lenses per CTA
 constexpr float RC_SKIP_EPS = 4e-6f; // >> the rounding of 8 products of 3 factors + 7 FMAs (~16 * 2^-24 = 1e-6)
@@ -104,7 +104,7 @@ __device__ __forceinline__ void rc_emit(const ResampleOut<MODE> &out, size_t o, 
 
 // MT: micro-image size known at compile time (row loop fully unrolled, immediate LDS offsets) or 0 = runtime.
 template <int MODE, int MT>
-__global__ void __launch_bounds__(RC_THREADS, 3)
+__global__ void __launch_bounds__(RC_THREADS, 4)
 resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__restrict__ out_u16,
                     pcb_minmax_t *mm_rw, const pcb_minmax_t *mm_ro) {
     extern __shared__ __align__(16) float tile[];          // [RC_ROWS][RC_TS]
