@@ -106,3 +106,27 @@ def test_fast_grid_fit_is_bit_identical_to_the_plain_form_and_plans_are_cached()
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     a[0][0, 0] += 1.0                                                          # callers get copies
     assert not np.array_equal(a[0], glob.projective_plan(cent, (420, 520, 3), 'hex', 1)[0])
+
+
+def test_warp_restatement_agrees_with_an_independent_bilinear_sampler():
+    """scikit-image is not installed (the `transform.warp` call of the global resampler is restated in
+    oracle_np.warp_projective, parity unpinned).  What CAN be pinned here: away from the image border the restatement is
+    plain bilinear sampling at the projectively mapped positions, and scipy.ndimage.map_coordinates(order=1) - an
+    independent third-party implementation of exactly that - agrees to float64 rounding."""
+    import scipy.ndimage as ndi
+    rng = np.random.default_rng(5)
+    img = rng.random((41, 53, 3))
+    m = np.array([[1.01, 0.02, -0.7], [-0.015, 0.99, 0.9], [1e-5, -2e-5, 1.0]])      # output (c, r, 1) -> input (x, y, z)
+    out = onp.warp_projective(img, m, (41, 53))
+    rr, cc = np.mgrid[0:41, 0:53].astype(np.float64)
+    z = m[2, 0] * cc + m[2, 1] * rr + m[2, 2]
+    x = (m[0, 0] * cc + m[0, 1] * rr + m[0, 2]) / z
+    y = (m[1, 0] * cc + m[1, 1] * rr + m[1, 2]) / z
+    inside = (x >= 0) & (x <= 52) & (y >= 0) & (y <= 40)
+    assert inside.mean() > 0.9
+    for ch in range(3):
+        ref = ndi.map_coordinates(img[..., ch], [y, x], order=1, mode='nearest')
+        assert np.abs(out[..., ch] - ref)[inside].max() < 1e-12
+    # outside the image the restatement returns cval = 0 (mode='constant'), never an extrapolation
+    far = (x < -1) | (x > 53) | (y < -1) | (y > 41)
+    assert np.all(out[far] == 0.0)
