@@ -13,6 +13,7 @@
 #include "refine.cuh"
 #include "resample.cuh"
 #include "resample_col.cuh"
+#include "resample_pipe.cuh"
 #include "global_resample.cuh"
 #include "rotate.cuh"
 #include "viewpoints.cuh"
@@ -35,6 +36,7 @@ static inline int grid_for(int64_t n, int per_block) {
 template <int MODE>
 static int dispatch_resample(const ResampleArgs &a, int raw_dtype, float *out_f32, uint16_t *out_u16,
                              pcb_minmax_t *mm_rw, const pcb_minmax_t *mm_ro, cudaStream_t st) {
+    if (resample_pipe_applies(a, raw_dtype)) return launch_resample_pipe<MODE>(a, out_f32, out_u16, mm_rw, mm_ro, st);
     if (resample_col_applies(a, raw_dtype)) return launch_resample_col<MODE>(a, out_f32, out_u16, mm_rw, mm_ro, st);
     return launch_resample<MODE>(a, raw_dtype, out_f32, out_u16, mm_rw, mm_ro, st);
 }

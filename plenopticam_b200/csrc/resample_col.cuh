@@ -102,6 +102,92 @@ __device__ __forceinline__ void rc_emit(const ResampleOut<MODE> &out, size_t o, 
     if (MODE != RS_U16) { mn = fminf(mn, val); mx = fmaxf(mx, val); }
 }
 
+// The output columns of one tile: thread `tid` of `nthreads` walks columns tid, tid + nthreads, ... down the patch rows.
+// Shared by the one-tile-per-CTA kernel below and the persistent pipelined kernel of resample_pipe.cuh.
+template <int MODE, int MT, int TS = RC_TS>
+__device__ __forceinline__ void rc_columns(const ResampleArgs &p, const ResampleOut<MODE> &out, const float *tile, int shift,
+                                           const pcb_lens_t *s_lens, int xa, bool lens_in_smem, bool use_tile, int ymin,
+                                           int xmin, int ly, int k0, int kn, const pcb_hexcol_t *hc, int tid, int nthreads,
+                                           float &mn, float &mx) {
+    const int M = MT ? MT : p.M;
+    const uint16_t *raw = reinterpret_cast<const uint16_t *>(p.raw);
+    const int ncols_tile = kn * M * 3;
+    for (int lc = tid; lc < ncols_tile; lc += nthreads) {
+        const int px = lc / 3;
+        const int ch = lc - px * 3;
+        const int kl = px / M;
+        const int u = px - kl * M;
+        const int k = k0 + kl;
+        const int us = p.flip ? (M - 1 - u) : u;
+        const int col = k0 * M * 3 + lc;
+
+        int x0 = k, x1 = k;
+        float w = 0.f;
+        if (hc) { const pcb_hexcol_t h = hc[k]; x0 = h.x0; x1 = h.x1; w = h.w; }
+        const bool two = (w != 0.f);
+        const pcb_lens_t L0 = lens_in_smem ? s_lens[x0 - xa] : p.lens[ly * p.LX + x0];
+        pcb_lens_t L1 = L0;
+        if (two) L1 = lens_in_smem ? s_lens[x1 - xa] : p.lens[ly * p.LX + x1];
+        const bool ok0 = L0.oy != PCB_LENS_INVALID;
+        const bool ok1 = two && (L1.oy != PCB_LENS_INVALID);
+        // eight weights: [lens][dy][dx]
+        const float h0 = ok0 ? (two ? 1.f - w : 1.f) : 0.f, h1 = ok1 ? w : 0.f;
+        const float a00 = h0 * (1.f - L0.wy), a01 = h0 * L0.wy, a10 = h1 * (1.f - L1.wy), a11 = h1 * L1.wy;
+        const float W000 = a00 * (1.f - L0.wx), W001 = a00 * L0.wx, W010 = a01 * (1.f - L0.wx), W011 = a01 * L0.wx;
+        const float W100 = a10 * (1.f - L1.wx), W101 = a10 * L1.wx, W110 = a11 * (1.f - L1.wx), W111 = a11 * L1.wx;
+
+        size_t o = ((size_t)ly * M + (p.flip ? M - 1 : 0)) * (size_t)p.ncols + col;
+        const long long ostep = p.flip ? -(long long)p.ncols : (long long)p.ncols;
+
+        if (use_tile) {
+            const float *t0 = tile + shift + (ok0 ? (L0.oy - ymin) * TS + (L0.ox - xmin + us) * 3 + ch : 0);
+            const float *t1 = ok1 ? tile + shift + (L1.oy - ymin) * TS + (L1.ox - xmin + us) * 3 + ch : t0;   // finite x 0
+            float pa0 = t0[0], pb0 = t0[3], pa1 = t1[0], pb1 = t1[3];
+            if (MT) {
+#pragma unroll
+                for (int r = 1; r <= (MT ? MT : 1); ++r) {
+                    const float a0 = t0[r * TS], b0 = t0[r * TS + 3], a1 = t1[r * TS], b1 = t1[r * TS + 3];
+                    float val = W000 * pa0;
+                    val = fmaf(W001, pb0, val); val = fmaf(W010, a0, val); val = fmaf(W011, b0, val);
+                    val = fmaf(W100, pa1, val); val = fmaf(W101, pb1, val); val = fmaf(W110, a1, val);
+                    val = fmaf(W111, b1, val);
+                    rc_emit<MODE>(out, o, val, mn, mx);
+                    o += ostep;
+                    pa0 = a0; pb0 = b0; pa1 = a1; pb1 = b1;
+                }
+            } else {
+                for (int r = 1; r <= M; ++r) {
+                    t0 += TS; t1 += TS;
+                    const float a0 = t0[0], b0 = t0[3], a1 = t1[0], b1 = t1[3];
+                    float val = W000 * pa0;
+                    val = fmaf(W001, pb0, val); val = fmaf(W010, a0, val); val = fmaf(W011, b0, val);
+                    val = fmaf(W100, pa1, val); val = fmaf(W101, pb1, val); val = fmaf(W110, a1, val);
+                    val = fmaf(W111, b1, val);
+                    rc_emit<MODE>(out, o, val, mn, mx);
+                    o += ostep;
+                    pa0 = a0; pb0 = b0; pa1 = a1; pb1 = b1;
+                }
+            }
+        } else {
+            const size_t stride = (size_t)p.W * 3;
+            const uint16_t *g0 = raw + ((size_t)(ok0 ? L0.oy : 0) * p.W + (ok0 ? L0.ox : 0) + us) * 3 + ch;
+            const uint16_t *g1 = ok1 ? raw + ((size_t)L1.oy * p.W + L1.ox + us) * 3 + ch : g0;
+            float pa0 = (float)__ldg(g0), pb0 = (float)__ldg(g0 + 3), pa1 = (float)__ldg(g1), pb1 = (float)__ldg(g1 + 3);
+            for (int r = 1; r <= M; ++r) {
+                g0 += stride; g1 += stride;
+                const float a0 = (float)__ldg(g0), b0 = (float)__ldg(g0 + 3), a1 = (float)__ldg(g1), b1 = (float)__ldg(g1 + 3);
+                float val = W000 * pa0;
+                val = fmaf(W001, pb0, val); val = fmaf(W010, a0, val); val = fmaf(W011, b0, val);
+                val = fmaf(W100, pa1, val); val = fmaf(W101, pb1, val); val = fmaf(W110, a1, val);
+                val = fmaf(W111, b1, val);
+                rc_emit<MODE>(out, o, val, mn, mx);
+                o += ostep;
+                pa0 = a0; pb0 = b0; pa1 = a1; pb1 = b1;
+            }
+        }
+    }
+}
+
 // MT: micro-image size known at compile time (row loop fully unrolled, immediate LDS offsets) or 0 = runtime.
 template <int MODE, int MT>
 __global__ void __launch_bounds__(RC_THREADS, 4)
@@ -230,81 +316,8 @@ resample_col_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__res
     }
 
     float mn = INFINITY, mx = -INFINITY;
-    const int ncols_tile = kn * M * 3;
-    for (int lc = tid; lc < ncols_tile; lc += RC_THREADS) {
-        const int px = lc / 3;
-        const int ch = lc - px * 3;
-        const int kl = px / M;
-        const int u = px - kl * M;
-        const int k = k0 + kl;
-        const int us = p.flip ? (M - 1 - u) : u;
-        const int col = k0 * M * 3 + lc;
-
-        int x0 = k, x1 = k;
-        float w = 0.f;
-        if (hc) { const pcb_hexcol_t h = hc[k]; x0 = h.x0; x1 = h.x1; w = h.w; }
-        const bool two = (w != 0.f);
-        const pcb_lens_t L0 = lens_in_smem ? s_lens[x0 - xa] : p.lens[ly * p.LX + x0];
-        pcb_lens_t L1 = L0;
-        if (two) L1 = lens_in_smem ? s_lens[x1 - xa] : p.lens[ly * p.LX + x1];
-        const bool ok0 = L0.oy != PCB_LENS_INVALID;
-        const bool ok1 = two && (L1.oy != PCB_LENS_INVALID);
-        // eight weights: [lens][dy][dx]
-        const float h0 = ok0 ? (two ? 1.f - w : 1.f) : 0.f, h1 = ok1 ? w : 0.f;
-        const float a00 = h0 * (1.f - L0.wy), a01 = h0 * L0.wy, a10 = h1 * (1.f - L1.wy), a11 = h1 * L1.wy;
-        const float W000 = a00 * (1.f - L0.wx), W001 = a00 * L0.wx, W010 = a01 * (1.f - L0.wx), W011 = a01 * L0.wx;
-        const float W100 = a10 * (1.f - L1.wx), W101 = a10 * L1.wx, W110 = a11 * (1.f - L1.wx), W111 = a11 * L1.wx;
-
-        size_t o = ((size_t)ly * M + (p.flip ? M - 1 : 0)) * (size_t)p.ncols + col;
-        const long long ostep = p.flip ? -(long long)p.ncols : (long long)p.ncols;
-
-        if (use_tile) {
-            const float *t0 = tile + shift + (ok0 ? (L0.oy - ymin) * RC_TS + (L0.ox - xmin + us) * 3 + ch : 0);
-            const float *t1 = ok1 ? tile + shift + (L1.oy - ymin) * RC_TS + (L1.ox - xmin + us) * 3 + ch : t0;   // finite x 0
-            float pa0 = t0[0], pb0 = t0[3], pa1 = t1[0], pb1 = t1[3];
-            if (MT) {
-#pragma unroll
-                for (int r = 1; r <= (MT ? MT : 1); ++r) {
-                    const float a0 = t0[r * RC_TS], b0 = t0[r * RC_TS + 3], a1 = t1[r * RC_TS], b1 = t1[r * RC_TS + 3];
-                    float val = W000 * pa0;
-                    val = fmaf(W001, pb0, val); val = fmaf(W010, a0, val); val = fmaf(W011, b0, val);
-                    val = fmaf(W100, pa1, val); val = fmaf(W101, pb1, val); val = fmaf(W110, a1, val);
-                    val = fmaf(W111, b1, val);
-                    rc_emit<MODE>(out, o, val, mn, mx);
-                    o += ostep;
-                    pa0 = a0; pb0 = b0; pa1 = a1; pb1 = b1;
-                }
-            } else {
-                for (int r = 1; r <= M; ++r) {
-                    t0 += RC_TS; t1 += RC_TS;
-                    const float a0 = t0[0], b0 = t0[3], a1 = t1[0], b1 = t1[3];
-                    float val = W000 * pa0;
-                    val = fmaf(W001, pb0, val); val = fmaf(W010, a0, val); val = fmaf(W011, b0, val);
-                    val = fmaf(W100, pa1, val); val = fmaf(W101, pb1, val); val = fmaf(W110, a1, val);
-                    val = fmaf(W111, b1, val);
-                    rc_emit<MODE>(out, o, val, mn, mx);
-                    o += ostep;
-                    pa0 = a0; pb0 = b0; pa1 = a1; pb1 = b1;
-                }
-            }
-        } else {
-            const size_t stride = (size_t)p.W * 3;
-            const uint16_t *g0 = raw + ((size_t)(ok0 ? L0.oy : 0) * p.W + (ok0 ? L0.ox : 0) + us) * 3 + ch;
-            const uint16_t *g1 = ok1 ? raw + ((size_t)L1.oy * p.W + L1.ox + us) * 3 + ch : g0;
-            float pa0 = (float)__ldg(g0), pb0 = (float)__ldg(g0 + 3), pa1 = (float)__ldg(g1), pb1 = (float)__ldg(g1 + 3);
-            for (int r = 1; r <= M; ++r) {
-                g0 += stride; g1 += stride;
-                const float a0 = (float)__ldg(g0), b0 = (float)__ldg(g0 + 3), a1 = (float)__ldg(g1), b1 = (float)__ldg(g1 + 3);
-                float val = W000 * pa0;
-                val = fmaf(W001, pb0, val); val = fmaf(W010, a0, val); val = fmaf(W011, b0, val);
-                val = fmaf(W100, pa1, val); val = fmaf(W101, pb1, val); val = fmaf(W110, a1, val);
-                val = fmaf(W111, b1, val);
-                rc_emit<MODE>(out, o, val, mn, mx);
-                o += ostep;
-                pa0 = a0; pb0 = b0; pa1 = a1; pb1 = b1;
-            }
-        }
-    }
+    rc_columns<MODE, MT>(p, out, tile, shift, s_lens, xa, lens_in_smem, use_tile, ymin, xmin, ly, k0, kn, hc, tid, RC_THREADS,
+                         mn, mx);
     if (MODE != RS_U16 && mm_rw != nullptr) block_minmax_commit(mn, mx, mm_rw);
 }
 

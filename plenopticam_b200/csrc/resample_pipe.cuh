@@ -1,0 +1,276 @@
+// (a) Micro-image resampling, PERSISTENT warp-specialised form of resample_col.cuh for uint16 RGB exposures.
+//
+// resample_col_kernel is one tile per CTA: tables -> raw rows -> barrier -> columns, and what bounds it is that chain
+// (ncu: barrier 27-31 %, long scoreboard 15-38 % of the stall samples at 65 % issue utilisation), not bytes or flops.
+// Here a CTA walks many tiles and a dedicated PRODUCER warp runs one tile ahead of the CONSUMER warps:
+//
+//   producer : tile tables (hex-column entries + lens window, one global-memory latency), the tile's bounding box, then
+//              one cp.async.bulk per raw row of the box (TMA unit, no registers, completion on an mbarrier) into a
+//              uint16 ring of two slots; it also snapshots the running global bounds for the min/max pass' skip test;
+//   consumers: wait for the slot, convert it to the float32 tile (shared -> shared, the same magic-number conversion as
+//              before), and run the column loop of resample_col.cuh (rc_columns, unchanged arithmetic: identical bits).
+//
+// So the global-memory latency of tile t+1 is spent while tile t is interpolated, a dropped tile of the min/max pass costs
+// its conversion only (no CTA launch, no table / raw latency on the critical path), and there is no per-tile CTA
+// prologue.  Tiles whose aligned bulk copies would leave the caller's buffer, whose box does not fit the tile, or rows
+// that are not 4-byte phase-aligned take the direct global path inside rc_columns, exactly like the one-tile kernel.
+#pragma once
+#include "common.cuh"
+#include "resample_col.cuh"
+#include "refocus_pxp.cuh"        // mbarrier / bulk-copy helpers
+
+namespace pcb {
+
+#ifndef PCB_RPK_KT
+#define PCB_RPK_KT 16
+#define PCB_RPK_TS 704
+#define PCB_RPK_CONS 384
+#endif
+constexpr int RPK_KT = PCB_RPK_KT;                   // output lens columns per tile
+constexpr int RPK_TS = PCB_RPK_TS;                   // float tile row stride (a multiple of 32)
+constexpr int RPK_CONS = PCB_RPK_CONS;               // consumer threads
+constexpr int RPK_THREADS = RPK_CONS + 32;           // + one producer warp
+constexpr int RPK_RSTR = ((RPK_TS * 2 + 32 + 15) / 16) * 16;      // bytes per raw row in a ring slot
+constexpr int RPK_SLOT = RC_ROWS * RPK_RSTR;         // bytes per ring slot
+
+struct RpkDesc {                  // what the producer hands over per tile
+    int ly, k0, kn, xa, nsrc;
+    int ymin, xmin, R, Wt;
+    int use_tile;                 // 1: raw rows are in the ring slot; 0: rc_columns reads global memory directly
+    int ninv;
+    int rowoff[RC_ROWS];          // byte offset of sample (xmin * 3) of row rr inside its slot row
+    float g_mn, g_mx;             // running global bounds when the tile was prepared (min/max pass)
+    pcb_lens_t lens[RC_MAX_SRC];
+};
+
+__device__ __forceinline__ void rpk_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RPK_CONS) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int MODE, int MT>
+__global__ void __launch_bounds__(RPK_THREADS, 2)
+resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__restrict__ out_u16, pcb_minmax_t *mm_rw,
+                     const pcb_minmax_t *mm_ro, int ntx, int ntiles) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    float *tile = reinterpret_cast<float *>(dsm);                                  // [RC_ROWS][RPK_TS]
+    unsigned char *ring = dsm + (size_t)RC_ROWS * RPK_TS * sizeof(float);           // 2 slots of RPK_SLOT bytes
+    __shared__ RpkDesc s_desc[2];
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    __shared__ int s_smm[2];
+    const int M = MT ? MT : p.M;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint16_t *raw = reinterpret_cast<const uint16_t *>(p.raw);
+    const size_t raw_lo = reinterpret_cast<size_t>(raw), raw_hi = raw_lo + (size_t)p.H * p.W * 6;
+    const bool may_skip = MODE == RS_MINMAX && mm_rw != nullptr && p.skip;
+
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], RPK_CONS / 32); mbar_init(&s_empty[1], RPK_CONS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == RPK_CONS / 32) {
+        // ================================================= producer =================================================
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int slot = it & 1;
+            const int ly = t / ntx, k0 = (t - ly * ntx) * RPK_KT;
+            const int kn = min(RPK_KT, p.Xs - k0);
+            const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((ly + p.hex_odd) & 1) * p.Xs : nullptr;
+            // ---- tables (as in resample_col_kernel: one latency)
+            float g_mn = 0.f, g_mx = 0.f;
+            uint32_t kmn = 0u, kmx = 0u;
+            if (may_skip && lane == 0) {
+                kmn = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmin);
+                kmx = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax);
+            }
+            int xa = k0, xb = k0 + kn - 1, xa_est = k0;
+            pcb_hexcol_t h;
+            h.x0 = h.x1 = 0; h.w = 0.f; h.reserved = 0;
+            if (hc) {
+                xa_est = max((int)floorf((float)k0 * (float)p.LX / (float)max(p.Xs - 1, 1)) - 1, 0);
+                if (lane < 2) h = hc[lane == 0 ? k0 : k0 + kn - 1];
+            }
+            const int xs = min(xa_est + lane, p.LX - 1);
+            pcb_lens_t Ls = p.lens[ly * p.LX + xs];
+            if (may_skip) {
+                g_mn = key_to_float(__shfl_sync(0xffffffffu, kmn, 0));
+                g_mx = key_to_float(__shfl_sync(0xffffffffu, kmx, 0));
+            }
+            if (hc) {
+                xa = __shfl_sync(0xffffffffu, h.x0, 0);
+                const int bx0 = __shfl_sync(0xffffffffu, h.x0, 1), bx1 = __shfl_sync(0xffffffffu, h.x1, 1);
+                const float bw = __shfl_sync(0xffffffffu, h.w, 1);
+                xb = bw == 0.f ? bx0 : bx1;
+            }
+            const int nsrc = xb - xa + 1;
+            const int from = xa + lane - xa_est;
+            pcb_lens_t L;
+            L.oy = __shfl_sync(0xffffffffu, Ls.oy, from & 31);
+            L.ox = __shfl_sync(0xffffffffu, Ls.ox, from & 31);
+            L.wy = __shfl_sync(0xffffffffu, Ls.wy, from & 31);
+            L.wx = __shfl_sync(0xffffffffu, Ls.wx, from & 31);
+            const bool mine = lane < nsrc && nsrc <= RC_MAX_SRC;
+            if (mine && (from < 0 || from > 31 || xa_est + from > p.LX - 1)) L = p.lens[ly * p.LX + xa + lane];
+            const bool valid = mine && L.oy != PCB_LENS_INVALID;
+            int b0 = valid ? L.oy : INT32_MAX, b1 = valid ? L.oy : INT32_MIN;
+            int b2 = valid ? L.ox : INT32_MAX, b3 = valid ? L.ox : INT32_MIN;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                b0 = min(b0, __shfl_xor_sync(0xffffffffu, b0, o)); b1 = max(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+                b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o)); b3 = max(b3, __shfl_xor_sync(0xffffffffu, b3, o));
+            }
+            const unsigned inv = __ballot_sync(0xffffffffu, mine && !valid);
+            const int ymin = b0, xmin = b2;
+            const int R = b1 - ymin + M + 1, Wt = (b3 - xmin + M + 1) * 3;
+            const bool any_valid = b1 != INT32_MIN;
+            bool use_tile = nsrc <= RC_MAX_SRC && any_valid && R <= RC_ROWS && Wt + 2 <= RPK_TS &&
+                            (raw_lo & 3) == 0 && ((p.W * 3) & 1) == 0;
+            // ---- bulk copies: the 16-byte aligned superset of every row of the box; all of it must lie inside the image
+            size_t a0 = 0;
+            uint32_t nbytes = 0;
+            if (use_tile && lane < R) {
+                const size_t A = raw_lo + (((size_t)(ymin + lane)) * p.W + xmin) * 6;
+                a0 = A & ~(size_t)15;
+                nbytes = (uint32_t)(((A + (size_t)Wt * 2 + 2 + 15) & ~(size_t)15) - a0);      // + one sample of slack
+            }
+            const bool row_ok = !(use_tile && lane < R) || (a0 >= raw_lo && a0 + nbytes <= raw_hi && nbytes <= (uint32_t)RPK_RSTR);
+            use_tile = use_tile && __all_sync(0xffffffffu, row_ok);
+            uint32_t total = use_tile && lane < R ? nbytes : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            // ---- the slot (ring rows AND descriptor) is free once the consumers are through with the tile before last
+            if (it >= 2) mbar_wait(&s_empty[slot], ((it >> 1) - 1) & 1);
+            RpkDesc &d = s_desc[slot];
+            if (mine) d.lens[lane] = L;
+            if (use_tile && lane < R) {
+                const size_t A = raw_lo + (((size_t)(ymin + lane)) * p.W + xmin) * 6;
+                d.rowoff[lane] = (int)(A - a0);
+            }
+            if (lane == 0) {
+                d.ly = ly; d.k0 = k0; d.kn = kn; d.xa = xa; d.nsrc = nsrc;
+                d.ymin = ymin; d.xmin = xmin; d.R = R; d.Wt = Wt;
+                d.use_tile = use_tile ? 1 : 0;
+                d.ninv = __popc(inv);
+                d.g_mn = g_mn; d.g_mx = g_mx;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the slot before async writes
+                mbar_expect_tx(&s_full[slot], total);                           // (arrive: the descriptor stores precede it)
+            }
+            __syncwarp();
+            if (use_tile && lane < R)
+                tma_bulk_g2s(ring + (size_t)slot * RPK_SLOT + (size_t)lane * RPK_RSTR, reinterpret_cast<const void *>(a0),
+                             nbytes, &s_full[slot]);
+        }
+        return;
+    }
+
+    // ===================================================== consumers =====================================================
+    ResampleOut<MODE> out;
+    out.f32 = out_f32; out.u16 = out_u16;
+    out.qz.init(0.f, 0.f);
+    if (MODE == RS_U16) out.qz.init(key_to_float(mm_ro->kmin), key_to_float(mm_ro->kmax));
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int slot = it & 1;
+        mbar_wait(&s_full[slot], (it >> 1) & 1);
+        const RpkDesc &d = s_desc[slot];
+        const bool use_tile = d.use_tile != 0;
+        const int R = d.R, Wt = d.Wt;
+        int shift = 0;
+        float smn = INFINITY, smx = 0.f;
+        if (tid == 0) { s_smm[0] = 0x7f800000; s_smm[1] = 0; }
+        if (use_tile) {
+            // ring slot (uint16, any 2-byte phase) -> float tile: whole 32-bit words from the word that holds the first sample
+            const unsigned char *srow0 = ring + (size_t)slot * RPK_SLOT;
+            shift = (d.rowoff[0] >> 1) & 1;                                     // same phase for every row (W * 3 even)
+            const int nw = (Wt + shift + 1) >> 1;
+            for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
+                const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RPK_RSTR + (d.rowoff[rr] & ~3));
+                float2 *dst = reinterpret_cast<float2 *>(tile + rr * RPK_TS);
+                for (int m = lane; m < nw; m += 32) {
+                    const uint32_t v = wsrc[m];
+                    const float2 f2 = make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7610)) - 8388608.0f,
+                                                  __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7632)) - 8388608.0f);
+                    dst[m] = f2;
+                    if (may_skip) {
+                        // the word may hold one sample before / after the box: neighbours of the row, a superset is fine
+                        smn = fminf(smn, fminf(f2.x, f2.y));
+                        smx = fmaxf(smx, fmaxf(f2.x, f2.y));
+                    }
+                }
+            }
+        }
+        rpk_consumer_sync();                 // s_smm reset visible; (tile complete comes with the next barrier)
+        bool skip = false;
+        if (may_skip && use_tile) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                smn = fminf(smn, __shfl_xor_sync(0xffffffffu, smn, o));
+                smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
+            }
+            if (lane == 0) {
+                atomicMin(&s_smm[0], __float_as_int(smn));
+                atomicMax(&s_smm[1], __float_as_int(smx));
+            }
+        }
+        rpk_consumer_sync();                 // tile complete, s_smm complete
+        if (may_skip && use_tile && d.ninv == 0) {
+            const float tmn = __int_as_float(s_smm[0]), tmx = __int_as_float(s_smm[1]);
+            skip = tmn * (1.f - RC_SKIP_EPS) > d.g_mn && tmx * (1.f + RC_SKIP_EPS) < d.g_mx;      // uniform over the CTA
+        }
+        if (!skip) {
+            const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((d.ly + p.hex_odd) & 1) * p.Xs : nullptr;
+            float mn = INFINITY, mx = -INFINITY;
+            rc_columns<MODE, MT, RPK_TS>(p, out, tile, shift, d.lens, d.xa, d.nsrc <= RC_MAX_SRC, use_tile, d.ymin, d.xmin, d.ly,
+                                 d.k0, d.kn, hc, tid, RPK_CONS, mn, mx);
+            if (MODE != RS_U16 && mm_rw != nullptr) {
+                // commit per tile so that the bounds the next tiles are tested against keep moving
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                if (lane == 0) {
+                    if (mn != INFINITY) atomicMin(&mm_rw->kmin, float_to_key(mn));
+                    if (mx != -INFINITY) atomicMax(&mm_rw->kmax, float_to_key(mx));
+                }
+            }
+        }
+        rpk_consumer_sync();                 // everybody is done with the tile and the descriptor
+        if (lane == 0) mbar_arrive(&s_empty[slot]);
+    }
+}
+
+static bool resample_pipe_applies(const ResampleArgs &a, int raw_dtype) {
+    const char *e = getenv("PCB_RESAMPLE_KERNEL");
+    if (e && (!strcmp(e, "tile") || !strcmp(e, "col"))) return false;
+    return raw_dtype == PCB_U16 && a.C == 3 && a.M + 2 <= RC_ROWS && a.M >= 1;
+}
+
+template <int MODE>
+static int launch_resample_pipe(const ResampleArgs &a_in, float *out_f32, uint16_t *out_u16, pcb_minmax_t *mm_rw,
+                                const pcb_minmax_t *mm_ro, cudaStream_t st) {
+    ResampleArgs a = a_in;
+    a.skip = (getenv("PCB_RESAMPLE_NOSKIP") && atoi(getenv("PCB_RESAMPLE_NOSKIP"))) ? 0 : 1;
+    const size_t smem = (size_t)RC_ROWS * RPK_TS * sizeof(float) + 2 * (size_t)RPK_SLOT;
+    const int ntx = (a.Xs + RPK_KT - 1) / RPK_KT;
+    const int ntiles = ntx * a.LY;
+    const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
+    if (a.M == 15) {
+        PCB_CUDA(cudaFuncSetAttribute(resample_pipe_kernel<MODE, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resample_pipe_kernel<MODE, 15><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles);
+    } else {
+        PCB_CUDA(cudaFuncSetAttribute(resample_pipe_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resample_pipe_kernel<MODE, 0><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles);
+    }
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
+}  // namespace pcb
