@@ -58,6 +58,7 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
     __shared__ RpkDesc s_desc[2];
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
     __shared__ int s_smm[2];
+    __shared__ uint32_t s_tmm[2];          // ordered keys of the min / max of the tile being interpolated
     const int M = MT ? MT : p.M;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -66,6 +67,7 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
     const bool may_skip = MODE == RS_MINMAX && mm_rw != nullptr && p.skip;
 
     if (tid == 0) {
+        s_tmm[0] = 0xffffffffu; s_tmm[1] = 0u;
         mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
         mbar_init(&s_empty[0], RPK_CONS / 32); mbar_init(&s_empty[1], RPK_CONS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -74,31 +76,46 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
 
     if (warp == RPK_CONS / 32) {
         // ================================================= producer =================================================
+        // The table loads of tile t + stride are issued before tile t is processed (register-carried), so their latency
+        // runs under the wait for a free slot instead of in front of every tile's bulk copies.
+        struct Pending { pcb_hexcol_t h; pcb_lens_t Ls; uint32_t kmn, kmx; int xa_est; };
+        auto request = [&](int t) {
+            Pending q;
+            q.h.x0 = q.h.x1 = 0; q.h.w = 0.f; q.h.reserved = 0;
+            q.kmn = q.kmx = 0u;
+            const int ly = t / ntx, k0 = (t - ly * ntx) * RPK_KT;
+            const int kn = min(RPK_KT, p.Xs - k0);
+            const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((ly + p.hex_odd) & 1) * p.Xs : nullptr;
+            q.xa_est = k0;
+            if (hc) {
+                q.xa_est = max((int)floorf((float)k0 * (float)p.LX / (float)max(p.Xs - 1, 1)) - 1, 0);
+                if (lane < 2) q.h = hc[lane == 0 ? k0 : k0 + kn - 1];
+            }
+            q.Ls = p.lens[ly * p.LX + min(q.xa_est + lane, p.LX - 1)];
+            if (may_skip && lane == 0) {
+                q.kmn = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmin);
+                q.kmx = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax);
+            }
+            return q;
+        };
         int it = 0;
+        Pending nxt = request(blockIdx.x);
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int slot = it & 1;
             const int ly = t / ntx, k0 = (t - ly * ntx) * RPK_KT;
             const int kn = min(RPK_KT, p.Xs - k0);
             const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((ly + p.hex_odd) & 1) * p.Xs : nullptr;
-            // ---- tables (as in resample_col_kernel: one latency)
-            float g_mn = 0.f, g_mx = 0.f;
-            uint32_t kmn = 0u, kmx = 0u;
-            if (may_skip && lane == 0) {
-                kmn = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmin);
-                kmx = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax);
-            }
-            int xa = k0, xb = k0 + kn - 1, xa_est = k0;
-            pcb_hexcol_t h;
-            h.x0 = h.x1 = 0; h.w = 0.f; h.reserved = 0;
-            if (hc) {
-                xa_est = max((int)floorf((float)k0 * (float)p.LX / (float)max(p.Xs - 1, 1)) - 1, 0);
-                if (lane < 2) h = hc[lane == 0 ? k0 : k0 + kn - 1];
-            }
-            const int xs = min(xa_est + lane, p.LX - 1);
-            pcb_lens_t Ls = p.lens[ly * p.LX + xs];
+            const Pending cur = nxt;
+            if (t + (int)gridDim.x < ntiles) nxt = request(t + gridDim.x);
+            // ---- tables (as in resample_col_kernel)
+            float g_mn = __int_as_float(0x7fffffff), g_mx = __int_as_float(0x7fffffff);   // NaN: "unknown" (always commit)
+            int xa = k0, xb = k0 + kn - 1;
+            const int xa_est = cur.xa_est;
+            const pcb_hexcol_t h = cur.h;
+            const pcb_lens_t Ls = cur.Ls;
             if (may_skip) {
-                g_mn = key_to_float(__shfl_sync(0xffffffffu, kmn, 0));
-                g_mx = key_to_float(__shfl_sync(0xffffffffu, kmx, 0));
+                g_mn = key_to_float(__shfl_sync(0xffffffffu, cur.kmn, 0));
+                g_mx = key_to_float(__shfl_sync(0xffffffffu, cur.kmx, 0));
             }
             if (hc) {
                 xa = __shfl_sync(0xffffffffu, h.x0, 0);
@@ -183,66 +200,85 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
         const bool use_tile = d.use_tile != 0;
         const int R = d.R, Wt = d.Wt;
         int shift = 0;
-        float smn = INFINITY, smx = 0.f;
-        if (tid == 0) { s_smm[0] = 0x7f800000; s_smm[1] = 0; }
+        const unsigned char *srow0 = ring + (size_t)slot * RPK_SLOT;
+        int nw = 0;
         if (use_tile) {
-            // ring slot (uint16, any 2-byte phase) -> float tile: whole 32-bit words from the word that holds the first sample
-            const unsigned char *srow0 = ring + (size_t)slot * RPK_SLOT;
             shift = (d.rowoff[0] >> 1) & 1;                                     // same phase for every row (W * 3 even)
-            const int nw = (Wt + shift + 1) >> 1;
+            nw = (Wt + shift + 1) >> 1;             // words per row from the word that holds the first sample
+        }
+        bool skip = false;
+        if (may_skip) {
+            // min / max of the raw samples of the tile on the packed uint16 pairs (a word may hold one sample before /
+            // after the box: neighbours of the row, a superset is fine); most tiles end here
+            if (tid == 0) { s_smm[0] = 0xffff; s_smm[1] = 0; }
+            uint32_t pmn = 0xffffffffu, pmx = 0u;
+            if (use_tile) {
+                for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
+                    const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RPK_RSTR + (d.rowoff[rr] & ~3));
+                    for (int m = lane; m < nw; m += 32) {
+                        const uint32_t v = wsrc[m];
+                        pmn = __vminu2(pmn, v);
+                        pmx = __vmaxu2(pmx, v);
+                    }
+                }
+            }
+            uint32_t lo = min(pmn & 0xffffu, pmn >> 16), hi = max(pmx & 0xffffu, pmx >> 16);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            rpk_consumer_sync();             // s_smm reset visible
+            if (lane == 0 && use_tile) {
+                atomicMin(&s_smm[0], (int)lo);
+                atomicMax(&s_smm[1], (int)hi);
+            }
+            rpk_consumer_sync();             // s_smm complete
+            if (use_tile && d.ninv == 0) {
+                const float tmn = (float)s_smm[0], tmx = (float)s_smm[1];
+                skip = tmn * (1.f - RC_SKIP_EPS) > d.g_mn && tmx * (1.f + RC_SKIP_EPS) < d.g_mx;      // uniform over the CTA
+            }
+        }
+        if (use_tile && !skip) {
+            // ring slot (uint16, any 2-byte phase) -> float tile: whole 32-bit words
             for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
                 const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RPK_RSTR + (d.rowoff[rr] & ~3));
                 float2 *dst = reinterpret_cast<float2 *>(tile + rr * RPK_TS);
                 for (int m = lane; m < nw; m += 32) {
                     const uint32_t v = wsrc[m];
-                    const float2 f2 = make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7610)) - 8388608.0f,
-                                                  __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7632)) - 8388608.0f);
-                    dst[m] = f2;
-                    if (may_skip) {
-                        // the word may hold one sample before / after the box: neighbours of the row, a superset is fine
-                        smn = fminf(smn, fminf(f2.x, f2.y));
-                        smx = fmaxf(smx, fmaxf(f2.x, f2.y));
-                    }
+                    dst[m] = make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7610)) - 8388608.0f,
+                                         __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7632)) - 8388608.0f);
                 }
             }
         }
-        rpk_consumer_sync();                 // s_smm reset visible; (tile complete comes with the next barrier)
-        bool skip = false;
-        if (may_skip && use_tile) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                smn = fminf(smn, __shfl_xor_sync(0xffffffffu, smn, o));
-                smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
-            }
-            if (lane == 0) {
-                atomicMin(&s_smm[0], __float_as_int(smn));
-                atomicMax(&s_smm[1], __float_as_int(smx));
-            }
-        }
-        rpk_consumer_sync();                 // tile complete, s_smm complete
-        if (may_skip && use_tile && d.ninv == 0) {
-            const float tmn = __int_as_float(s_smm[0]), tmx = __int_as_float(s_smm[1]);
-            skip = tmn * (1.f - RC_SKIP_EPS) > d.g_mn && tmx * (1.f + RC_SKIP_EPS) < d.g_mx;      // uniform over the CTA
-        }
+        if (!skip) rpk_consumer_sync();      // tile complete (uniform: every consumer took the same decision)
         if (!skip) {
             const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((d.ly + p.hex_odd) & 1) * p.Xs : nullptr;
             float mn = INFINITY, mx = -INFINITY;
             rc_columns<MODE, MT, RPK_TS>(p, out, tile, shift, d.lens, d.xa, d.nsrc <= RC_MAX_SRC, use_tile, d.ymin, d.xmin, d.ly,
                                  d.k0, d.kn, hc, tid, RPK_CONS, mn, mx);
             if (MODE != RS_U16 && mm_rw != nullptr) {
-                // commit per tile so that the bounds the next tiles are tested against keep moving
+                // fold the tile's bounds in shared memory first: ONE pair of global atomics per tile (and only when the tile
+                // moves the bounds the producer saw) - every warp hitting the same two global words serialises in L2
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 }
                 if (lane == 0) {
-                    if (mn != INFINITY) atomicMin(&mm_rw->kmin, float_to_key(mn));
-                    if (mx != -INFINITY) atomicMax(&mm_rw->kmax, float_to_key(mx));
+                    if (mn != INFINITY) atomicMin(&s_tmm[0], float_to_key(mn));
+                    if (mx != -INFINITY) atomicMax(&s_tmm[1], float_to_key(mx));
                 }
             }
         }
         rpk_consumer_sync();                 // everybody is done with the tile and the descriptor
+        if (MODE != RS_U16 && mm_rw != nullptr && tid == 0 && !skip) {
+            const uint32_t kmn = s_tmm[0], kmx = s_tmm[1];
+            s_tmm[0] = 0xffffffffu; s_tmm[1] = 0u;              // for the next tile (nobody touches it before the next fold)
+            // d.g_* are NaN until the first commits have landed: the comparisons are then false -> commit
+            if (kmn != 0xffffffffu && !(key_to_float(kmn) >= d.g_mn)) atomicMin(&mm_rw->kmin, kmn);
+            if (kmx != 0u && !(key_to_float(kmx) <= d.g_mx)) atomicMax(&mm_rw->kmax, kmx);
+        }
         if (lane == 0) mbar_arrive(&s_empty[slot]);
     }
 }
