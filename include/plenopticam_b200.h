@@ -25,7 +25,7 @@ extern "C" {
 
 /* ABI revision: bumped whenever an entry point is added or its arguments change.  pcb_version() returns the value the
  * library was built with; a binding refuses a library of another revision (plenopticam_b200/_native.py). */
-#define PCB_ABI_VERSION 200
+#define PCB_ABI_VERSION 201
 
 #define PCB_OK               0
 #define PCB_ERR_INVALID      1   /* bad argument (null pointer, non-positive size, unsupported dtype)  */
@@ -151,15 +151,25 @@ int pcb_refocus_int(const void *vp, int dtype, int M, int S, int T, int C,
  * LfpCropper.crop_micro_image (lfp_extractor/lfp_cropper.py:58-62) and LfpRearranger.compose_viewpoints
  * (lfp_extractor/lfp_rearranger.py:93-101) are folded into the staging of the refocus tiles (one bulk copy per aligned
  * row).  Same results bit for bit.  PCB_ERR_UNSUPPORTED when the persistent packed-pixel kernel does not apply
- * (then: pcb_viewpoints + pcb_refocus_int). */
+ * (then: pcb_viewpoints + pcb_refocus_int).
+ * scratch_flags (0 = the call zeroes the accumulators itself and leaves them dirty, like pcb_refocus_int):
+ *   PCB_REFOCUS_LEAVE_ZEROED    the pass that reads an accumulator word last stores zero behind it, so the scratch comes
+ *                               back with clean accumulators;
+ *   PCB_REFOCUS_SCRATCH_ZEROED  the caller vouches that the accumulators ARE zero - the previous call on this scratch was
+ *                               one of these two with PCB_REFOCUS_LEAVE_ZEROED, ordered before this one, and nothing wrote
+ *                               to the scratch since - and the call skips its memset (209 MB per Illum exposure).
+ * A sequence of exposures passes LEAVE_ZEROED on the first call and both flags from then on. */
+#define PCB_REFOCUS_SCRATCH_ZEROED 1
+#define PCB_REFOCUS_LEAVE_ZEROED 2
 int pcb_refocus_int_aligned(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
                             const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host,
-                            void *scratch, int64_t scratch_bytes, float *out, pcb_minmax_t *mm, void *stream);
+                            void *scratch, int64_t scratch_bytes, float *out, pcb_minmax_t *mm, int scratch_flags,
+                            void *stream);
 int pcb_refocus_int_srgb_aligned(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
                                  const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host,
                                  void *scratch, int64_t scratch_bytes, double q_lo, double q_hi,
                                  float *ref_slice, double *lohi, void *pscratch, float *out, pcb_minmax_t *mm,
-                                 void *stream);
+                                 int scratch_flags, void *stream);
 int pcb_refocus_int_direct(const void *vp, int dtype, int M, int S, int T, int C,
                            const int32_t *a_list_dev, int N, const uint8_t *view_zeroed_dev,
                            float *out, pcb_minmax_t *mm, void *stream);

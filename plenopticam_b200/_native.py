@@ -64,7 +64,7 @@ def _sources():
 
 #: ABI the binding below was written against; `pcb_version()` of the loaded library must return it.  Bump together
 #: with PCB_ABI_VERSION in include/plenopticam_b200.h whenever an entry point is added or its arguments change.
-ABI_VERSION = 200
+ABI_VERSION = 201
 
 STAMP_PATH = LIB_PATH + ".srchash"
 
@@ -144,9 +144,9 @@ _SIGNATURES = {
     "pcb_refocus_int_scratch_bytes": (_i64, [_i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pcb_refocus_int": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "pcb_refocus_int_srgb": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "pcb_refocus_int_aligned": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "pcb_refocus_int_aligned": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _i, _vp]),
     "pcb_refocus_int_srgb_aligned": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, C.c_double, C.c_double, _vp,
-                                          _vp, _vp, _vp, _vp, _vp]),
+                                          _vp, _vp, _vp, _vp, _i, _vp]),
     "pcb_refocus_int_direct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refocus_int_zero": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "pcb_refi_prefilter": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),

@@ -315,12 +315,13 @@ int pcb_refocus_int_srgb(const void *vp, int dtype, int M, int S, int T, int C, 
 static int refocus_aligned_common(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
                                   const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host, void *scratch,
                                   int64_t scratch_bytes, float *out, pcb_minmax_t *mm, const PxpFusedPost *post,
-                                  cudaStream_t st, const char *who) {
+                                  int scratch_flags, cudaStream_t st, const char *who) {
     PCB_REQUIRE(aligned != nullptr && a_list_host != nullptr && view_zeroed_host != nullptr && out != nullptr &&
                 scratch != nullptr, "pointers");
     PCB_REQUIRE(M > 0 && S > 0 && T > 0 && C > 0 && N > 0 && N <= 65535, "sizes");
     PCB_REQUIRE(M % 2 == 1, "odd M (even M changes the slice shape, lfp_shiftandsum.py:123-124)");
     PCB_REQUIRE(Ma >= M && (Ma - M) % 2 == 0, "aligned pitch >= M with an even crop margin (lfp_cropper.py:34)");
+    PCB_REQUIRE((scratch_flags & ~(PCB_REFOCUS_SCRATCH_ZEROED | PCB_REFOCUS_LEAVE_ZEROED)) == 0, "scratch_flags");
     PCB_REQUIRE(scratch_bytes >= pcb_refocus_int_scratch_bytes(dtype, M, S, T, C, a_list_host, N, view_zeroed_host),
                 "scratch_bytes >= pcb_refocus_int_scratch_bytes(...)");
     const RefocusPlan pl = refocus_plan(dtype, M, S, T, C, a_list_host, N, view_zeroed_host, aligned, Ma);
@@ -328,25 +329,25 @@ static int refocus_aligned_common(const void *aligned, int dtype, int Ma, int M,
         return fail(PCB_ERR_UNSUPPORTED, "%s: reading the aligned image directly exists for the packed-pixel kernel only "
                     "(uint16 RGB, M <= 16, row <= 2048 px, tiles that fit one SM); run pcb_viewpoints first", who);
     return launch_refocus_pxp(pl.px, pl.pxp, (const uint16_t *)aligned, a_list_host, view_zeroed_host, scratch, out, mm,
-                              st, post);
+                              st, post, scratch_flags);
 }
 
 int pcb_refocus_int_aligned(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
                             const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host, void *scratch,
-                            int64_t scratch_bytes, float *out, pcb_minmax_t *mm, void *stream) {
+                            int64_t scratch_bytes, float *out, pcb_minmax_t *mm, int scratch_flags, void *stream) {
     return refocus_aligned_common(aligned, dtype, Ma, M, S, T, C, a_list_host, N, view_zeroed_host, scratch,
-                                  scratch_bytes, out, mm, nullptr, as_stream(stream), __func__);
+                                  scratch_bytes, out, mm, nullptr, scratch_flags, as_stream(stream), __func__);
 }
 
 int pcb_refocus_int_srgb_aligned(const void *aligned, int dtype, int Ma, int M, int S, int T, int C,
                                  const int32_t *a_list_host, int N, const uint8_t *view_zeroed_host, void *scratch,
                                  int64_t scratch_bytes, double q_lo, double q_hi, float *ref_slice, double *lohi,
-                                 void *pscratch, float *out, pcb_minmax_t *mm, void *stream) {
+                                 void *pscratch, float *out, pcb_minmax_t *mm, int scratch_flags, void *stream) {
     PCB_REQUIRE(ref_slice != nullptr && lohi != nullptr && pscratch != nullptr && mm != nullptr, "pointers");
     PxpFusedPost post;
     post.q_lo = q_lo; post.q_hi = q_hi; post.ref_slice = ref_slice; post.lohi = lohi; post.pscratch = pscratch;
     return refocus_aligned_common(aligned, dtype, Ma, M, S, T, C, a_list_host, N, view_zeroed_host, scratch,
-                                  scratch_bytes, out, mm, &post, as_stream(stream), __func__);
+                                  scratch_bytes, out, mm, &post, scratch_flags, as_stream(stream), __func__);
 }
 
 // The direct (slice-stationary) form only; kept addressable for A/B measurements and as the general path.

@@ -58,14 +58,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float contrast_srgb_one(float x, double lo, double inv, bool scale) {
     // the clip runs after the (monotone) cast to float32: same result, two float64 instructions fewer — the float64
     // pipe is what the fused refocus epilogue waits for
     // x*inv - lo*inv in one FMA (lo*inv is loop-invariant): within 2 ulp(double) of the reference's float64 quotient
     const float y = fminf(fmaxf(scale ? (float)fma((double)x, inv, -(lo * inv)) : x, 0.f), 1.f);
     // both branches are a handful of instructions: evaluate both and select (no divergent branch).  For y in
-    // [0.0031308, 1] the exponent lies in [-3.5, 0]: ex2.approx needs none of exp2f's range handling.
-    const float pw = __fsub_rn(__fmul_rn(1.055f, ex2_approx(__fmul_rn((float)(5.0 / 12.0), __log2f(fmaxf(y, 0.0031308f))))), 0.055f);
+    // [0.0031308, 1] the argument is a normal number and the exponent lies in [-3.5, 0]: lg2.approx / ex2.approx need
+    // none of log2f's / exp2f's range handling.
+    const float pw = __fmaf_rn(1.055f, ex2_approx(__fmul_rn((float)(5.0 / 12.0), lg2_approx(fmaxf(y, 0.0031308f)))), -0.055f);
     const float ln = __fmul_rn(y, 12.92f);
     return y >= 0.0031308f ? pw : ln;
 }

@@ -213,15 +213,22 @@ constexpr int PXF_IT = 3;          // row segments whose accumulator loads are i
 // 40-41), known only then — the pass returns at once unless that changes a bound, else it rewrites the stack.
 template <bool EXACT24, int POST = 0>
 __global__ void __launch_bounds__(PXF_THREADS)
-refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const uint32_t *__restrict__ accB,
+refocus_px_finalize_kernel(unsigned long long *accRG, uint32_t *accB,
                            const unsigned long long *__restrict__ edgeRG, const uint32_t *__restrict__ edgeB,
                            PxCtl ctl, float *__restrict__ out, int M, int S, int T, int Tp, int n0, int nsl,
-                           pcb_minmax_t *mm, const double *__restrict__ lohi = nullptr) {
+                           pcb_minmax_t *mm, const double *__restrict__ lohi = nullptr, int leave_zero = 0) {
     double lo = 0.0, inv = 1.0;
     bool scale = false;
+    // leave_zero (PCB_REFOCUS_LEAVE_ZEROED): the LAST pass that reads an accumulator word stores zero behind it, so the
+    // next exposure starts from a clean accumulator without a memset.  POST 0: this pass.  POST 1: this pass, unless the
+    // upper bound is exactly 0 - only then can the fix-up pass need the sums again (a lower bound of 0 implies a data
+    // minimum of 0: the values are non-negative and slice 0 belongs to the stack), and then the fix-up pass zeroes (when
+    // it does not run either, every sum is 0 already).
+    bool zero_acc = leave_zero != 0;
     if (POST) {
         lo = lohi[0];
         double hi = lohi[1];
+        if (POST == 1) zero_acc = zero_acc && hi != 0.0;
         if (POST == 2) {
             const double dmin = (double)key_to_float(mm->kmin), dmax = (double)key_to_float(mm->kmax);
             if (!((lo == 0.0 && dmin != 0.0) || (hi == 0.0 && dmax != 0.0))) return;
@@ -231,24 +238,24 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
         scale = (hi != lo) && (hi != 0.0);
         inv = scale ? 1.0 / (hi - lo) : 1.0;
     }
-    __shared__ int s_rows[16];     // edge-table row index (n*M + j)*2 + side of every clamped contribution
+    __shared__ int s_rows[16];     // edge-table row offset ((n*M + j)*2 + side) * Tp of every clamped contribution
     __shared__ int s_cnt;
     __shared__ float s_tile[PXF_THREADS * 3];
     DivByConst divM;
     divM.init((float)M);
     float mn = INFINITY, mx = -INFINITY;
-    // one CTA per (slice, row) for POST 0 / 1; the fix-up pass runs a small grid that strides over the rows, so that
-    // the launch that usually has nothing to do costs microseconds
-    const int row_step = POST == 2 ? (int)gridDim.x : S * nsl;       // POST 0 / 1: exactly one row per CTA
-    for (int row = blockIdx.x; row < S * nsl; row += row_step) {
-    const int sl = POST == 2 ? row / S : (int)blockIdx.y;
-    const int y = POST == 2 ? row - sl * S : (int)blockIdx.x, n = n0 + sl;
+    // a CTA walks a few (slice, row) pairs (grid-strided), so that the prologue above and the block reduction below are
+    // paid once per CTA, not once per row; the fix-up pass runs a small grid: the launch that usually has nothing to do
+    // costs microseconds
+    for (int row = blockIdx.x; row < S * nsl; row += (int)gridDim.x) {
+    const int sl = row / S;
+    const int y = row - sl * S, n = n0 + sl;
     if (threadIdx.x < 32) {                    // M <= 16: one lane per view-row, compacted with a ballot
         const int j = threadIdx.x;
         const int ys = y + ctl.a[sl] * (M / 2 - j);
         const bool clamped = j < M && ((ctl.row_active >> j) & 1u) && (ys < 0 || ys > S - 1);
         const unsigned m = __ballot_sync(0xffffffffu, clamped);
-        if (clamped) s_rows[__popc(m & ((1u << j) - 1u))] = (n * M + j) * 2 + (ys < 0 ? 0 : 1);
+        if (clamped) s_rows[__popc(m & ((1u << j) - 1u))] = ((n * M + j) * 2 + (ys < 0 ? 0 : 1)) * Tp;
         if (j == 0) s_cnt = __popc(m);
     }
     __syncthreads();
@@ -273,8 +280,8 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
             const int x = xb + threadIdx.x;
             if (x < T) {
                 for (int c = 0; c < cnt; ++c) {
-                    rg[k] += __ldg(edgeRG + (size_t)s_rows[c] * Tp + x);
-                    b[k] += __ldg(edgeB + (size_t)s_rows[c] * Tp + x);
+                    rg[k] += __ldg(edgeRG + s_rows[c] + x);
+                    b[k] += __ldg(edgeB + s_rows[c] + x);
                 }
                 const uint32_t v[3] = {(uint32_t)rg[k], (uint32_t)(rg[k] >> 32), b[k]};
 #pragma unroll
@@ -296,10 +303,27 @@ refocus_px_finalize_kernel(const unsigned long long *__restrict__ accRG, const u
             }
             __syncwarp();
         }
+        // every thread zeroes the words it read itself (no other thread reads them), and only now that its loads have
+        // long been answered: a store that meets the pending fill of its own line in L2 is slow (zeroing right behind
+        // each load made the pass 7x slower)
+        if (zero_acc) {
+#pragma unroll
+            for (int k = 0; k < PXF_IT; ++k) {
+                const int x = xb0 + k * PXF_THREADS + threadIdx.x;
+                if (x < T) { accRG[arow + x] = 0ull; accB[arow + x] = 0u; }
+            }
+        }
     }
-    if (POST == 2) __syncthreads();            // s_rows / s_cnt are rewritten by the next row
+    __syncthreads();                           // s_rows / s_cnt are rewritten by the next row
     }
     if (POST != 2 && mm != nullptr) block_minmax_commit(mn, mx, mm);
+}
+
+constexpr int PXF_ROWS_PER_CTA = 4;
+// a few rows per CTA once there are enough rows to fill the GPU several times over (a single slice stays one row per CTA)
+static dim3 finalize_grid(int rows) {
+    const int per = rows >= 16 * PXF_ROWS_PER_CTA * sm_count() ? PXF_ROWS_PER_CTA : 1;
+    return dim3((rows + per - 1) / per, 1);
 }
 
 struct PxPlan {
@@ -368,6 +392,7 @@ static PxPlan plan_refocus_px(int M, int S, int T, int N, int max_abs_a, int max
     pl.clamp = shift > T;
     pl.exact24 = (long long)n_active_total * 65535LL < (1LL << 24);
     if ((long long)N * S * pl.a.Tp >= (1LL << 31)) return pl;          // 32-bit accumulator offsets
+    if ((long long)N * M * 2 * pl.a.Tp >= (1LL << 31)) return pl;      // ... and edge-table offsets
     pl.accRG_bytes = (size_t)N * S * pl.a.Tp * 8;
     pl.accB_bytes = (size_t)N * S * pl.a.Tp * 4;
     pl.edgeRG_bytes = (size_t)N * M * 2 * pl.a.Tp * 8;
@@ -427,7 +452,7 @@ static int launch_refocus_px(const PxPlan &pl, const uint16_t *vp, const int32_t
         a.nsl = nloc;
         const int rc = launch_px_threads(pl, a, ctl, st);
         if (rc) return rc;
-        dim3 fgrid(a.S, nloc);
+        const dim3 fgrid = finalize_grid(a.S * nloc);
         if (pl.exact24)
             refocus_px_finalize_kernel<true><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, ctl, out,
                                                                           a.M, a.S, a.T, a.Tp, n0, nloc, mm);

@@ -407,22 +407,24 @@ struct PxpFusedPost {
 
 template <int POST>
 static int launch_pxp_finalize(const PxpPlan &pl, const PxpArgs &a, const PxCtl &fctl, float *out, int n0, int nloc,
-                               pcb_minmax_t *mm, const double *lohi, cudaStream_t st) {
-    dim3 fgrid(a.S, nloc);
+                               pcb_minmax_t *mm, const double *lohi, int leave_zero, cudaStream_t st) {
+    dim3 fgrid = finalize_grid(a.S * nloc);
     if (POST == 2) fgrid = dim3(min(a.S * nloc, 8 * sm_count()), 1);     // usually returns at once: keep the launch small
     if (pl.exact24)
         refocus_px_finalize_kernel<true, POST><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, fctl, out,
-                                                                            a.M, a.S, a.T, a.Tp, n0, nloc, mm, lohi);
+                                                                            a.M, a.S, a.T, a.Tp, n0, nloc, mm, lohi,
+                                                                            leave_zero);
     else
         refocus_px_finalize_kernel<false, POST><<<fgrid, PXF_THREADS, 0, st>>>(a.accRG, a.accB, a.edgeRG, a.edgeB, fctl,
-                                                                             out, a.M, a.S, a.T, a.Tp, n0, nloc, mm, lohi);
+                                                                             out, a.M, a.S, a.T, a.Tp, n0, nloc, mm, lohi,
+                                                                             leave_zero);
     PCB_LAUNCH_OK();
     return PCB_OK;
 }
 
 static int launch_refocus_pxp(const PxPlan &px, const PxpPlan &pl, const uint16_t *vp, const int32_t *a_list_host,
                               const uint8_t *view_zeroed_host, void *scratch, float *out, pcb_minmax_t *mm,
-                              cudaStream_t st, const PxpFusedPost *post = nullptr) {
+                              cudaStream_t st, const PxpFusedPost *post = nullptr, int scratch_flags = 0) {
     PxpArgs a = pl.a;
     char *sp = reinterpret_cast<char *>(scratch);
     a.vp = vp;
@@ -431,7 +433,12 @@ static int launch_refocus_pxp(const PxPlan &px, const PxpPlan &pl, const uint16_
     a.edgeRG = reinterpret_cast<unsigned long long *>(sp + px.accRG_bytes + px.accB_bytes);
     a.edgeB = reinterpret_cast<uint32_t *>(sp + px.accRG_bytes + px.accB_bytes + px.edgeRG_bytes);
     PCB_REQUIRE(a.S <= 65535, "S <= 65535");
-    PCB_CUDA(cudaMemsetAsync(sp, 0, px.accRG_bytes + px.accB_bytes, st));
+    // PCB_REFOCUS_SCRATCH_ZEROED: the caller vouches that the accumulators hold zeros (a previous call with
+    // PCB_REFOCUS_LEAVE_ZEROED on the same scratch and stream order); PCB_REFOCUS_LEAVE_ZEROED: the pass that reads an
+    // accumulator word last stores zero behind it (refocus_px_finalize_kernel)
+    if (!(scratch_flags & PCB_REFOCUS_SCRATCH_ZEROED))
+        PCB_CUDA(cudaMemsetAsync(sp, 0, px.accRG_bytes + px.accB_bytes, st));
+    const int leave = (scratch_flags & PCB_REFOCUS_LEAVE_ZEROED) ? 1 : 0;
     PxpCtl ctl = pl.ctl;
     PxCtl fctl;                                            // finalize shares refocus_px.cuh's pass
     memset(&fctl, 0, sizeof(fctl));
@@ -445,7 +452,7 @@ static int launch_refocus_pxp(const PxPlan &px, const PxpPlan &pl, const uint16_
     for (int pass = 0; pass < (post ? 3 : 1); ++pass) {
         if (pass == 1) {                                   // bounds from the linear slice 0
             for (int k = 0; k < RR_MAX_SLICES; ++k) fctl.a[k] = k == 0 ? a_list_host[0] : 0;
-            int rc = launch_pxp_finalize<0>(pl, a, fctl, post->ref_slice, 0, 1, nullptr, nullptr, st);
+            int rc = launch_pxp_finalize<0>(pl, a, fctl, post->ref_slice, 0, 1, nullptr, nullptr, 0, st);
             if (rc) return rc;
             rc = run_contrast_bounds(post->ref_slice, (int64_t)a.S * a.T, post->q_lo, post->q_hi, post->lohi,
                                      post->pscratch, st);
@@ -464,11 +471,11 @@ static int launch_refocus_pxp(const PxPlan &px, const PxpPlan &pl, const uint16_
                 else
                     rc = pl.ppt == 1 ? launch_pxp_variant<1024, 1>(pl, a, ctl, st) : launch_pxp_variant<1024, 2>(pl, a, ctl, st);
                 if (g_kev[1]) cudaEventRecord(g_kev[1], st);
-                if (rc == PCB_OK && !post) rc = launch_pxp_finalize<0>(pl, a, fctl, out, n0, nloc, mm, nullptr, st);
+                if (rc == PCB_OK && !post) rc = launch_pxp_finalize<0>(pl, a, fctl, out, n0, nloc, mm, nullptr, leave, st);
             } else if (pass == 1) {
-                rc = launch_pxp_finalize<1>(pl, a, fctl, out, n0, nloc, mm, post->lohi, st);
+                rc = launch_pxp_finalize<1>(pl, a, fctl, out, n0, nloc, mm, post->lohi, leave, st);
             } else {
-                rc = launch_pxp_finalize<2>(pl, a, fctl, out, n0, nloc, mm, post->lohi, st);
+                rc = launch_pxp_finalize<2>(pl, a, fctl, out, n0, nloc, mm, post->lohi, leave, st);
             }
             if (rc) return rc;
         }

@@ -215,6 +215,7 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
             if (use_tile) {
                 for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
                     const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RPK_RSTR + (d.rowoff[rr] & ~3));
+#pragma unroll 4
                     for (int m = lane; m < nw; m += 32) {
                         const uint32_t v = wsrc[m];
                         pmn = __vminu2(pmn, v);
@@ -244,6 +245,7 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
             for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
                 const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RPK_RSTR + (d.rowoff[rr] & ~3));
                 float2 *dst = reinterpret_cast<float2 *>(tile + rr * RPK_TS);
+#pragma unroll 4
                 for (int m = lane; m < nw; m += 32) {
                     const uint32_t v = wsrc[m];
                     dst[m] = make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7610)) - 8388608.0f,

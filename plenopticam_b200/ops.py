@@ -5,6 +5,8 @@ torch stream and does not synchronise.  There is no CPU fallback: without a CUDA
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -324,14 +326,34 @@ class RefocusPlan(object):
         self.fused = None            # None: not tried yet; True / False: pcb_refocus_int_srgb applies / does not
         self.ref_slice = None
 
+    # The accumulators in `scratch` must be zero when the kernel starts.  The aligned entry points can hand them back
+    # zeroed (the finalize pass stores zero behind every word it reads) and skip their memset the next time; the state
+    # travels with the scratch TENSOR, because plans of one geometry share it (LightFieldPipeline).
+    SCRATCH_ZEROED, LEAVE_ZEROED = 1, 2
+
+    def _take_scratch(self, keep_clean):
+        """Flags for the next launch; the scratch counts as dirty until `_scratch_left_clean` says otherwise (an
+        exception in between leaves it dirty: the next launch zeroes it itself)."""
+        was_clean = bool(getattr(self.scratch, "_pcb_acc_zero", False))
+        self.scratch._pcb_acc_zero = False
+        if not keep_clean or os.environ.get("PCB_REFOCUS_MEMSET") == "1":      # A/B knob: always memset
+            return 0
+        return self.LEAVE_ZEROED | (self.SCRATCH_ZEROED if was_clean else 0)
+
+    def _scratch_left_clean(self):
+        self.scratch._pcb_acc_zero = True
+
     def launch(self, vp, out, mm=None):
         M, S, T, Cn = self.shape
         mmp = _ptr(mm) if mm is not None else C.c_void_p(0)
         if self.Ma is not None:
+            flags = self._take_scratch(True)
             nat.check(nat.lib().pcb_refocus_int_aligned(_ptr(vp), self.dtype, self.Ma, M, S, T, Cn, self.a_ptr, self.N,
                                                         self.z_ptr, _ptr(self.scratch), self.scratch.numel(), _ptr(out),
-                                                        mmp, _stream()))
+                                                        mmp, flags, _stream()))
+            self._scratch_left_clean()
             return out
+        self._take_scratch(False)
         nat.check(nat.lib().pcb_refocus_int(_ptr(vp), self.dtype, M, S, T, Cn, self.a_ptr, self.N, self.z_ptr,
                                             _ptr(self.scratch), self.scratch.numel(), _ptr(out), mmp, _stream()))
         return out
@@ -347,11 +369,14 @@ def _refocus_plan_launch_srgb(self, vp, out, mm, lohi, pscratch, q_lo=0.005, q_h
         self.ref_slice = torch.empty((S, T, Cn), dtype=torch.float32, device=self.scratch.device)
     try:
         if self.Ma is not None:
+            flags = self._take_scratch(True)
             nat.check(nat.lib().pcb_refocus_int_srgb_aligned(_ptr(vp), self.dtype, self.Ma, M, S, T, Cn, self.a_ptr,
                                                              self.N, self.z_ptr, _ptr(self.scratch), self.scratch.numel(),
                                                              q_lo, q_hi, _ptr(self.ref_slice), _ptr(lohi), _ptr(pscratch),
-                                                             _ptr(out), _ptr(mm), _stream()))
+                                                             _ptr(out), _ptr(mm), flags, _stream()))
+            self._scratch_left_clean()
         else:
+            self._take_scratch(False)
             nat.check(nat.lib().pcb_refocus_int_srgb(_ptr(vp), self.dtype, M, S, T, Cn, self.a_ptr, self.N, self.z_ptr,
                                                      _ptr(self.scratch), self.scratch.numel(), q_lo, q_hi,
                                                      _ptr(self.ref_slice), _ptr(lohi), _ptr(pscratch), _ptr(out),

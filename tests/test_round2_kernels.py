@@ -105,3 +105,79 @@ def test_minmax_pass_with_tile_skipping_is_exact(cuda, pat):
             finally:
                 os.environ.pop("PCB_RESAMPLE_NOSKIP", None)
         assert res[0] == res[1] == ops.minmax_values(mm32) == (float(al32.min()), float(al32.max()))
+
+
+def _srgb_from_aligned(plan, al, pscratch):
+    import torch
+    from plenopticam_b200 import ops
+    M, S, T, Cn = plan.shape
+    out = torch.empty((plan.N, S, T, Cn), dtype=torch.float32, device=al.device)
+    mm = ops.new_minmax()
+    lohi = torch.empty(2, dtype=torch.float64, device=al.device)
+    assert plan.launch_srgb(al, out, mm, lohi, pscratch) is True
+    return out, ops.minmax_values(mm), lohi.cpu().numpy().copy()
+
+
+def test_accumulators_come_back_zeroed_across_a_sequence_of_exposures(cuda):
+    """A plan that serves a SEQUENCE of exposures skips the accumulator memset from the second call on (the finalize pass
+    stores zero behind every word it reads, PCB_REFOCUS_LEAVE_ZEROED / _SCRATCH_ZEROED): every stack must equal the one a
+    fresh plan gives, for the linear and the fused sRGB form, incl. the degenerate exposures whose upper contrast bound
+    is exactly 0 (then the fix-up pass re-reads the sums: the zeroing moves there) and an all-zero exposure."""
+    import torch
+    from plenopticam_b200 import _native as nat, ops
+    Ma, M, S, T = 9, 7, 40, 52
+    a_list = list(range(-4, 5))
+    rng = np.random.default_rng(11)
+    dense = [rng.integers(0, 65536, size=(S * Ma, T * Ma, 3), dtype=np.uint16) for _ in range(3)]
+    spike = np.zeros_like(dense[0])                       # one bright sample: 99.9 % of slice 0 is zero, the stack is not
+    spike[(S // 2) * Ma + Ma // 2, (T // 2) * Ma + Ma // 2, 1] = 60000
+    dark = (dense[1] >> 12).astype(np.uint16)             # lower bound 0 (many zero samples), upper bound > 0
+    zero = np.zeros_like(dense[0])
+    seq = [dense[0], spike, dense[1], zero, dark, spike, spike, dense[2], zero, zero, dense[0]]
+    pscratch = torch.empty(int(nat.lib().pcb_percentile_scratch_bytes()), dtype=torch.uint8, device=cuda)
+
+    def plan():
+        return ops.RefocusPlan((M, M, S, T, 3), torch.uint16, a_list, None, cuda, aligned_pitch=Ma)
+
+    shared = plan()
+    flags_seen = []
+    for k, host in enumerate(seq):
+        al = ops.to_device(host)
+        was_clean = bool(getattr(shared.scratch, "_pcb_acc_zero", False))
+        flags_seen.append(was_clean)
+        if k % 3 == 2:                                     # linear form
+            got = ops.refocus_int_from_aligned(al, Ma, a_list, M=M, plan=shared)
+            ref = ops.refocus_int_from_aligned(al, Ma, a_list, M=M, plan=plan())
+            assert torch.equal(got, ref), k
+        else:                                              # fused colour management
+            got, mm, lohi = _srgb_from_aligned(shared, al, pscratch)
+            ref, mm_ref, lohi_ref = _srgb_from_aligned(plan(), al, pscratch)
+            assert torch.equal(got, ref), k
+            assert mm == mm_ref and np.array_equal(lohi, lohi_ref), k
+            # ... and the separate kernels on the explicit gather (no flags anywhere on that route)
+            lin = ops.refocus_int(ops.viewpoints(al, Ma, M), a_list)
+            assert torch.equal(got, ops.refocuser_postprocess(lin)), k
+        torch.cuda.synchronize()
+        acc_bytes = len(a_list) * S * ((T + 3) // 4 * 4) * 12
+        assert int(shared.scratch[:acc_bytes].count_nonzero()) == 0, k     # what the next call relies on
+    assert flags_seen[0] is False and all(flags_seen[1:])
+
+
+def test_a_launch_without_flags_marks_the_shared_scratch_dirty(cuda):
+    """Plans of one geometry share the accumulators (LightFieldPipeline): the 4-D form leaves them dirty, so the aligned
+    form that follows must zero them itself."""
+    import torch
+    from plenopticam_b200 import ops
+    Ma, M, S, T = 7, 7, 12, 20
+    a_list = list(range(-3, 4))
+    al = _aligned(cuda, Ma, S, T, 5)
+    p_al = ops.RefocusPlan((M, M, S, T, 3), torch.uint16, a_list, None, cuda, aligned_pitch=Ma)
+    p_vp = ops.RefocusPlan((M, M, S, T, 3), torch.uint16, a_list, None, cuda)
+    p_vp.scratch = p_al.scratch
+    ref = ops.refocus_int_from_aligned(al, Ma, a_list, plan=p_al)
+    assert p_al.scratch._pcb_acc_zero is True
+    vp = ops.viewpoints(al, Ma)
+    assert torch.equal(ops.refocus_int(vp, a_list, plan=p_vp), ref)
+    assert p_al.scratch._pcb_acc_zero is False
+    assert torch.equal(ops.refocus_int_from_aligned(al, Ma, a_list, plan=p_al), ref)
+    assert torch.equal(ops.refocus_int_from_aligned(al, Ma, a_list, plan=p_al), ref)
