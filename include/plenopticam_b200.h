@@ -25,7 +25,7 @@ extern "C" {
 
 /* ABI revision: bumped whenever an entry point is added or its arguments change.  pcb_version() returns the value the
  * library was built with; a binding refuses a library of another revision (plenopticam_b200/_native.py). */
-#define PCB_ABI_VERSION 201
+#define PCB_ABI_VERSION 202
 
 #define PCB_OK               0
 #define PCB_ERR_INVALID      1   /* bad argument (null pointer, non-positive size, unsupported dtype)  */

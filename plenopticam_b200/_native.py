@@ -64,7 +64,7 @@ def _sources():
 
 #: ABI the binding below was written against; `pcb_version()` of the loaded library must return it.  Bump together
 #: with PCB_ABI_VERSION in include/plenopticam_b200.h whenever an entry point is added or its arguments change.
-ABI_VERSION = 201
+ABI_VERSION = 202
 
 STAMP_PATH = LIB_PATH + ".srchash"
 

@@ -15,6 +15,7 @@
 // prologue.  Tiles whose aligned bulk copies would leave the caller's buffer, whose box does not fit the tile, or rows
 // that are not 4-byte phase-aligned take the direct global path inside rc_columns, exactly like the one-tile kernel.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 #include "resample_col.cuh"
 #include "refocus_pxp.cuh"        // mbarrier / bulk-copy helpers
@@ -31,10 +32,10 @@ constexpr int RPK_TS = PCB_RPK_TS;                   // float tile row stride (a
 constexpr int RPK_CONS = PCB_RPK_CONS;               // consumer threads
 constexpr int RPK_THREADS = RPK_CONS + 32;           // + one producer warp
 constexpr int RPK_RSTR = ((RPK_TS * 2 + 32 + 15) / 16) * 16;      // bytes per raw row in a ring slot
-constexpr int RPK_SLOT = RC_ROWS * RPK_RSTR;         // bytes per ring slot
+constexpr int RPK_SLOT = (RC_ROWS * RPK_RSTR + 127) / 128 * 128;      // bytes per ring slot (tensor copies land 128-byte aligned)
 
 struct RpkDesc {                  // what the producer hands over per tile
-    int ly, k0, kn, xa, nsrc;
+    int ly, k0, kn, xa, nsrc;     // ly < 0: no more tiles
     int ymin, xmin, R, Wt;
     int use_tile;                 // 1: raw rows are in the ring slot; 0: rc_columns reads global memory directly
     int ninv;
@@ -44,14 +45,96 @@ struct RpkDesc {                  // what the producer hands over per tile
 };
 
 __device__ __forceinline__ void rpk_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RPK_CONS) : "memory"); }
+__device__ __forceinline__ void tma_tensor2d_g2s(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- the tables of one tile, per lane of ONE warp (used by the producer warp and by the tile-bounds kernel) ----------
+struct RpkPending { pcb_hexcol_t h; pcb_lens_t Ls; int xa_est; };      // loads in flight: first / last hex column, lens window
+
+__device__ __forceinline__ RpkPending rpk_request(const ResampleArgs &p, int t, int ntx, int lane) {
+    RpkPending q;
+    q.h.x0 = q.h.x1 = 0; q.h.w = 0.f; q.h.reserved = 0;
+    const int ly = t / ntx, k0 = (t - ly * ntx) * RPK_KT;
+    const int kn = min(RPK_KT, p.Xs - k0);
+    const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((ly + p.hex_odd) & 1) * p.Xs : nullptr;
+    q.xa_est = k0;
+    if (hc) {
+        q.xa_est = max((int)floorf((float)k0 * (float)p.LX / (float)max(p.Xs - 1, 1)) - 1, 0);
+        if (lane < 2) q.h = hc[lane == 0 ? k0 : k0 + kn - 1];
+    }
+    q.Ls = p.lens[ly * p.LX + min(q.xa_est + lane, p.LX - 1)];
+    return q;
+}
+
+struct RpkBox {
+    int ly, k0, kn, xa, nsrc;
+    int ymin, xmin, R, Wt;
+    bool use_tile, mine;          // mine: this lane holds source lens xa + lane in L
+    unsigned inv;                 // ballot of the invalid source lenses
+    size_t a0;                    // lane < R: 16-byte aligned start of the bulk copy of box row `lane`
+    uint32_t nbytes;              // ... and its length (the aligned superset of the row, + one sample of slack)
+    pcb_lens_t L;
+};
+
+// (as in resample_col_kernel) source lens range, bounding box of the raw samples, and whether the box can travel by bulk
+// copies: 16-byte aligned supersets of every row inside the caller's buffer, 4-byte phase-aligned rows
+__device__ __forceinline__ RpkBox rpk_box(const ResampleArgs &p, int M, int t, int ntx, int lane, const RpkPending &cur,
+                                          size_t raw_lo, size_t raw_hi) {
+    RpkBox b;
+    b.ly = t / ntx; b.k0 = (t - b.ly * ntx) * RPK_KT;
+    b.kn = min(RPK_KT, p.Xs - b.k0);
+    int xa = b.k0, xb = b.k0 + b.kn - 1;
+    if (p.hexcol) {
+        xa = __shfl_sync(0xffffffffu, cur.h.x0, 0);
+        const int bx0 = __shfl_sync(0xffffffffu, cur.h.x0, 1), bx1 = __shfl_sync(0xffffffffu, cur.h.x1, 1);
+        const float bw = __shfl_sync(0xffffffffu, cur.h.w, 1);
+        xb = bw == 0.f ? bx0 : bx1;
+    }
+    b.xa = xa;
+    b.nsrc = xb - xa + 1;
+    const int from = xa + lane - cur.xa_est;
+    b.L.oy = __shfl_sync(0xffffffffu, cur.Ls.oy, from & 31);
+    b.L.ox = __shfl_sync(0xffffffffu, cur.Ls.ox, from & 31);
+    b.L.wy = __shfl_sync(0xffffffffu, cur.Ls.wy, from & 31);
+    b.L.wx = __shfl_sync(0xffffffffu, cur.Ls.wx, from & 31);
+    b.mine = lane < b.nsrc && b.nsrc <= RC_MAX_SRC;
+    if (b.mine && (from < 0 || from > 31 || cur.xa_est + from > p.LX - 1)) b.L = p.lens[b.ly * p.LX + xa + lane];
+    const bool valid = b.mine && b.L.oy != PCB_LENS_INVALID;
+    int b0 = valid ? b.L.oy : INT32_MAX, b1 = valid ? b.L.oy : INT32_MIN;
+    int b2 = valid ? b.L.ox : INT32_MAX, b3 = valid ? b.L.ox : INT32_MIN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        b0 = min(b0, __shfl_xor_sync(0xffffffffu, b0, o)); b1 = max(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+        b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o)); b3 = max(b3, __shfl_xor_sync(0xffffffffu, b3, o));
+    }
+    b.inv = __ballot_sync(0xffffffffu, b.mine && !valid);
+    b.ymin = b0; b.xmin = b2;
+    b.R = b1 - b.ymin + M + 1; b.Wt = (b3 - b.xmin + M + 1) * 3;
+    const bool any_valid = b1 != INT32_MIN;
+    bool use_tile = b.nsrc <= RC_MAX_SRC && any_valid && b.R <= RC_ROWS && b.Wt + 2 <= RPK_TS &&
+                    (raw_lo & 3) == 0 && ((p.W * 3) & 1) == 0;
+    b.a0 = 0; b.nbytes = 0;
+    if (use_tile && lane < b.R) {
+        const size_t A = raw_lo + (((size_t)(b.ymin + lane)) * p.W + b.xmin) * 6;
+        b.a0 = A & ~(size_t)15;
+        b.nbytes = (uint32_t)(((A + (size_t)b.Wt * 2 + 2 + 15) & ~(size_t)15) - b.a0);
+    }
+    const bool row_ok = !(use_tile && lane < b.R) ||
+                        (b.a0 >= raw_lo && b.a0 + b.nbytes <= raw_hi && b.nbytes <= (uint32_t)RPK_RSTR);
+    b.use_tile = use_tile && __all_sync(0xffffffffu, row_ok);
+    return b;
 }
 
 template <int MODE, int MT>
 __global__ void __launch_bounds__(RPK_THREADS, 2)
 resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__restrict__ out_u16, pcb_minmax_t *mm_rw,
-                     const pcb_minmax_t *mm_ro, int ntx, int ntiles) {
+                     const pcb_minmax_t *mm_ro, int ntx, int ntiles, const __grid_constant__ CUtensorMap tmap, int use2d) {
     extern __shared__ __align__(128) unsigned char dsm[];
     float *tile = reinterpret_cast<float *>(dsm);                                  // [RC_ROWS][RPK_TS]
     unsigned char *ring = dsm + (size_t)RC_ROWS * RPK_TS * sizeof(float);           // 2 slots of RPK_SLOT bytes
@@ -76,103 +159,33 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
 
     if (warp == RPK_CONS / 32) {
         // ================================================= producer =================================================
-        // The table loads of tile t + stride are issued before tile t is processed (register-carried), so their latency
-        // runs under the wait for a free slot instead of in front of every tile's bulk copies.
-        struct Pending { pcb_hexcol_t h; pcb_lens_t Ls; uint32_t kmn, kmx; int xa_est; };
-        auto request = [&](int t) {
-            Pending q;
-            q.h.x0 = q.h.x1 = 0; q.h.w = 0.f; q.h.reserved = 0;
-            q.kmn = q.kmx = 0u;
-            const int ly = t / ntx, k0 = (t - ly * ntx) * RPK_KT;
-            const int kn = min(RPK_KT, p.Xs - k0);
-            const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((ly + p.hex_odd) & 1) * p.Xs : nullptr;
-            q.xa_est = k0;
-            if (hc) {
-                q.xa_est = max((int)floorf((float)k0 * (float)p.LX / (float)max(p.Xs - 1, 1)) - 1, 0);
-                if (lane < 2) q.h = hc[lane == 0 ? k0 : k0 + kn - 1];
-            }
-            q.Ls = p.lens[ly * p.LX + min(q.xa_est + lane, p.LX - 1)];
-            if (may_skip && lane == 0) {
-                q.kmn = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmin);
-                q.kmx = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax);
-            }
-            return q;
-        };
-        int it = 0;
-        Pending nxt = request(blockIdx.x);
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        int it = 0;                        // descriptors handed over so far
+        // hand one tile (or the end marker, b == nullptr) to the consumers through the next ring slot
+        auto hand_over = [&](const RpkBox *b, float g_mn, float g_mx) {
             const int slot = it & 1;
-            const int ly = t / ntx, k0 = (t - ly * ntx) * RPK_KT;
-            const int kn = min(RPK_KT, p.Xs - k0);
-            const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((ly + p.hex_odd) & 1) * p.Xs : nullptr;
-            const Pending cur = nxt;
-            if (t + (int)gridDim.x < ntiles) nxt = request(t + gridDim.x);
-            // ---- tables (as in resample_col_kernel)
-            float g_mn = __int_as_float(0x7fffffff), g_mx = __int_as_float(0x7fffffff);   // NaN: "unknown" (always commit)
-            int xa = k0, xb = k0 + kn - 1;
-            const int xa_est = cur.xa_est;
-            const pcb_hexcol_t h = cur.h;
-            const pcb_lens_t Ls = cur.Ls;
-            if (may_skip) {
-                g_mn = key_to_float(__shfl_sync(0xffffffffu, cur.kmn, 0));
-                g_mx = key_to_float(__shfl_sync(0xffffffffu, cur.kmx, 0));
-            }
-            if (hc) {
-                xa = __shfl_sync(0xffffffffu, h.x0, 0);
-                const int bx0 = __shfl_sync(0xffffffffu, h.x0, 1), bx1 = __shfl_sync(0xffffffffu, h.x1, 1);
-                const float bw = __shfl_sync(0xffffffffu, h.w, 1);
-                xb = bw == 0.f ? bx0 : bx1;
-            }
-            const int nsrc = xb - xa + 1;
-            const int from = xa + lane - xa_est;
-            pcb_lens_t L;
-            L.oy = __shfl_sync(0xffffffffu, Ls.oy, from & 31);
-            L.ox = __shfl_sync(0xffffffffu, Ls.ox, from & 31);
-            L.wy = __shfl_sync(0xffffffffu, Ls.wy, from & 31);
-            L.wx = __shfl_sync(0xffffffffu, Ls.wx, from & 31);
-            const bool mine = lane < nsrc && nsrc <= RC_MAX_SRC;
-            if (mine && (from < 0 || from > 31 || xa_est + from > p.LX - 1)) L = p.lens[ly * p.LX + xa + lane];
-            const bool valid = mine && L.oy != PCB_LENS_INVALID;
-            int b0 = valid ? L.oy : INT32_MAX, b1 = valid ? L.oy : INT32_MIN;
-            int b2 = valid ? L.ox : INT32_MAX, b3 = valid ? L.ox : INT32_MIN;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                b0 = min(b0, __shfl_xor_sync(0xffffffffu, b0, o)); b1 = max(b1, __shfl_xor_sync(0xffffffffu, b1, o));
-                b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o)); b3 = max(b3, __shfl_xor_sync(0xffffffffu, b3, o));
-            }
-            const unsigned inv = __ballot_sync(0xffffffffu, mine && !valid);
-            const int ymin = b0, xmin = b2;
-            const int R = b1 - ymin + M + 1, Wt = (b3 - xmin + M + 1) * 3;
-            const bool any_valid = b1 != INT32_MIN;
-            bool use_tile = nsrc <= RC_MAX_SRC && any_valid && R <= RC_ROWS && Wt + 2 <= RPK_TS &&
-                            (raw_lo & 3) == 0 && ((p.W * 3) & 1) == 0;
-            // ---- bulk copies: the 16-byte aligned superset of every row of the box; all of it must lie inside the image
-            size_t a0 = 0;
-            uint32_t nbytes = 0;
-            if (use_tile && lane < R) {
-                const size_t A = raw_lo + (((size_t)(ymin + lane)) * p.W + xmin) * 6;
-                a0 = A & ~(size_t)15;
-                nbytes = (uint32_t)(((A + (size_t)Wt * 2 + 2 + 15) & ~(size_t)15) - a0);      // + one sample of slack
-            }
-            const bool row_ok = !(use_tile && lane < R) || (a0 >= raw_lo && a0 + nbytes <= raw_hi && nbytes <= (uint32_t)RPK_RSTR);
-            use_tile = use_tile && __all_sync(0xffffffffu, row_ok);
-            uint32_t total = use_tile && lane < R ? nbytes : 0u;
+            const bool use_tile = b != nullptr && b->use_tile;
+            uint32_t total = use_tile && lane < b->R ? b->nbytes : 0u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            // ---- the slot (ring rows AND descriptor) is free once the consumers are through with the tile before last
+            if (use_tile && use2d) total = (uint32_t)(RC_ROWS * RPK_RSTR);         // the box of the tensor map, whole
+            // the slot (ring rows AND descriptor) is free once the consumers are through with the tile before last
             if (it >= 2) mbar_wait(&s_empty[slot], ((it >> 1) - 1) & 1);
             RpkDesc &d = s_desc[slot];
-            if (mine) d.lens[lane] = L;
-            if (use_tile && lane < R) {
-                const size_t A = raw_lo + (((size_t)(ymin + lane)) * p.W + xmin) * 6;
-                d.rowoff[lane] = (int)(A - a0);
-            }
-            if (lane == 0) {
-                d.ly = ly; d.k0 = k0; d.kn = kn; d.xa = xa; d.nsrc = nsrc;
-                d.ymin = ymin; d.xmin = xmin; d.R = R; d.Wt = Wt;
-                d.use_tile = use_tile ? 1 : 0;
-                d.ninv = __popc(inv);
-                d.g_mn = g_mn; d.g_mx = g_mx;
+            if (b != nullptr) {
+                if (b->mine) d.lens[lane] = b->L;
+                if (use_tile && lane < b->R) {
+                    const size_t A = raw_lo + (((size_t)(b->ymin + lane)) * p.W + b->xmin) * 6;
+                    d.rowoff[lane] = (int)(A - b->a0);
+                }
+                if (lane == 0) {
+                    d.ly = b->ly; d.k0 = b->k0; d.kn = b->kn; d.xa = b->xa; d.nsrc = b->nsrc;
+                    d.ymin = b->ymin; d.xmin = b->xmin; d.R = b->R; d.Wt = b->Wt;
+                    d.use_tile = use_tile ? 1 : 0;
+                    d.ninv = __popc(b->inv);
+                    d.g_mn = g_mn; d.g_mx = g_mx;
+                }
+            } else if (lane == 0) {
+                d.ly = -1;
             }
             __syncwarp();
             if (lane == 0) {
@@ -180,10 +193,45 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
                 mbar_expect_tx(&s_full[slot], total);                           // (arrive: the descriptor stores precede it)
             }
             __syncwarp();
-            if (use_tile && lane < R)
-                tma_bulk_g2s(ring + (size_t)slot * RPK_SLOT + (size_t)lane * RPK_RSTR, reinterpret_cast<const void *>(a0),
-                             nbytes, &s_full[slot]);
+            if (use_tile && use2d) {
+                // ONE tensor copy of the whole box (19 rows x 1440 bytes, zero-filled outside the image): 19 row copies per
+                // tile cost the pipeline 40 % more time than one copy of the same bytes
+                if (lane == 0)
+                    tma_tensor2d_g2s(ring + (size_t)slot * RPK_SLOT, &tmap, (b->xmin * 6 & ~15) >> 3, b->ymin, &s_full[slot]);
+            } else
+            if (use_tile && lane < b->R)
+                tma_bulk_g2s(ring + (size_t)slot * RPK_SLOT + (size_t)lane * RPK_RSTR, reinterpret_cast<const void *>(b->a0),
+                             b->nbytes, &s_full[slot]);
+            ++it;
+        };
+        const float nanf_ = __int_as_float(0x7fffffff);       // bounds "unknown": the tile's own bounds are always committed
+        auto bounds = [&](uint32_t &kmn, uint32_t &kmx) {
+            kmn = kmx = 0u;
+            if (may_skip && lane == 0) {
+                kmn = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmin);
+                kmx = *reinterpret_cast<volatile uint32_t *>(&mm_rw->kmax);
+            }
+        };
+        {
+            // ---- static round-robin; the table loads of tile t + stride are issued before tile t is handed over
+            // (register-carried), so their latency runs under the wait for a free slot
+            RpkPending nxt = rpk_request(p, blockIdx.x, ntx, lane);
+            uint32_t nkmn, nkmx;
+            bounds(nkmn, nkmx);
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const RpkPending cur = nxt;
+                const uint32_t kmn = nkmn, kmx = nkmx;
+                if (t + (int)gridDim.x < ntiles) { nxt = rpk_request(p, t + gridDim.x, ntx, lane); bounds(nkmn, nkmx); }
+                float g_mn = nanf_, g_mx = nanf_;
+                if (may_skip) {
+                    g_mn = key_to_float(__shfl_sync(0xffffffffu, kmn, 0));
+                    g_mx = key_to_float(__shfl_sync(0xffffffffu, kmx, 0));
+                }
+                const RpkBox b = rpk_box(p, M, t, ntx, lane, cur, raw_lo, raw_hi);
+                hand_over(&b, g_mn, g_mx);
+            }
         }
+        hand_over(nullptr, 0.f, 0.f);
         return;
     }
 
@@ -192,11 +240,11 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
     out.f32 = out_f32; out.u16 = out_u16;
     out.qz.init(0.f, 0.f);
     if (MODE == RS_U16) out.qz.init(key_to_float(mm_ro->kmin), key_to_float(mm_ro->kmax));
-    int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (int it = 0;; ++it) {
         const int slot = it & 1;
         mbar_wait(&s_full[slot], (it >> 1) & 1);
         const RpkDesc &d = s_desc[slot];
+        if (d.ly < 0) break;
         const bool use_tile = d.use_tile != 0;
         const int R = d.R, Wt = d.Wt;
         int shift = 0;
@@ -291,6 +339,34 @@ static bool resample_pipe_applies(const ResampleArgs &a, int raw_dtype) {
     return raw_dtype == PCB_U16 && a.C == 3 && a.M + 2 <= RC_ROWS && a.M >= 1;
 }
 
+// The raw exposure as a 2-D tensor of 8-byte elements (rows of W*6 bytes), box = one ring slot.  Needs a 16-byte aligned
+// base and row pitch; cuTensorMapEncodeTiled comes from the driver at run time (no link dependency on libcuda).
+static bool rpk_make_tensor_map(const ResampleArgs &a, CUtensorMap *map) {
+    const char *e = getenv("PCB_RESAMPLE_ROWCOPIES");
+    if (e && atoi(e)) return false;
+    const size_t row_bytes = (size_t)a.W * 6;
+    if ((reinterpret_cast<size_t>(a.raw) & 15) != 0 || (row_bytes & 15) != 0) return false;
+    typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = []() -> encode_t {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<encode_t>(fn);
+    }();
+    if (!encode) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes / 8), (cuuint64_t)a.H};
+    const cuuint64_t gstr[1] = {(cuuint64_t)row_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)(RPK_RSTR / 8), (cuuint32_t)RC_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void *>(a.raw), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int MODE>
 static int launch_resample_pipe(const ResampleArgs &a_in, float *out_f32, uint16_t *out_u16, pcb_minmax_t *mm_rw,
                                 const pcb_minmax_t *mm_ro, cudaStream_t st) {
@@ -300,12 +376,15 @@ static int launch_resample_pipe(const ResampleArgs &a_in, float *out_f32, uint16
     const int ntx = (a.Xs + RPK_KT - 1) / RPK_KT;
     const int ntiles = ntx * a.LY;
     const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const int use2d = rpk_make_tensor_map(a, &tmap) ? 1 : 0;
     if (a.M == 15) {
         PCB_CUDA(cudaFuncSetAttribute(resample_pipe_kernel<MODE, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        resample_pipe_kernel<MODE, 15><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles);
+        resample_pipe_kernel<MODE, 15><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles, tmap, use2d);
     } else {
         PCB_CUDA(cudaFuncSetAttribute(resample_pipe_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        resample_pipe_kernel<MODE, 0><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles);
+        resample_pipe_kernel<MODE, 0><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles, tmap, use2d);
     }
     PCB_LAUNCH_OK();
     return PCB_OK;

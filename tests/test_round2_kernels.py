@@ -78,33 +78,63 @@ def test_pipeline_gather_fused_equals_explicit_gather(cuda):
         assert torch.equal(o, outs[0])
 
 
-@pytest.mark.parametrize("pat", ["hex", "rec"])
-def test_minmax_pass_with_tile_skipping_is_exact(cuda, pat):
-    """The bounds of the skipping min/max pass == those of the pass that interpolates every tile == the min / max of the
-    float32 aligned image; with smooth data most tiles are skipped, with a saturated image none can be."""
+@pytest.mark.parametrize("pat,pad_w", [("hex", True), ("rec", True), ("hex", False)])
+def test_minmax_pass_with_tile_skipping_is_exact(cuda, pat, pad_w):
+    """The forms of the min/max pass - every tile interpolated; tiles that cannot move the bounds dropped after a scan of
+    their raw samples, the box fetched by one tensor copy (needs a 16-byte row pitch) or by one bulk copy per row - give
+    the bounds of the float32 image, bit for bit; so does the quantised image of the second pass."""
     import torch
     from plenopticam_b200 import ops
     from plenopticam_b200.lfp_aligner import build_tables
     from plenopticam_b200.misc import synth
     cent = synth.synth_centroids(40, 90, 14.25, pat, jitter=0.15, origin=(9.5, 9.5), seed=8)
     H, W = int(cent[:, 0].max() + 11), int(cent[:, 1].max() + 11)
+    W = (W + 7) // 8 * 8 if pad_w else W // 8 * 8 + 3        # row pitch a multiple of 16 bytes (tensor copies) or not
     tabs = ops.LensTables(build_tables(cent, (H, W, 3), 15, pat))
     raws = [synth.synth_raw(H, W, 3, seed=9), np.full((H, W, 3), 65535, dtype=np.uint16)]
     raws.append(raws[0].copy())
     raws[2][7, 11] = 0                               # a single black sample inside the very first tile
     raws[2][H // 2, W // 2] = 65535
+    raws.append(np.zeros((H, W, 3), dtype=np.uint16))
+    raws.append((raws[0] >> 9).astype(np.uint16))    # few distinct values: many ties with the running bounds
     for raw in raws:
         dev = ops.to_device(raw)
         al32, mm32 = ops.resample_f32(dev, tabs, want_minmax=True)
-        res = []
-        for noskip in ("0", "1"):
-            os.environ["PCB_RESAMPLE_NOSKIP"] = noskip
+        res, imgs = [], []
+        for env in ({"PCB_RESAMPLE_NOSKIP": "1"}, {"PCB_RESAMPLE_ROWCOPIES": "1"}, {}):
+            os.environ.update(env)
             try:
-                _, mm = ops.resample_u16(dev, tabs)
+                al16, mm = ops.resample_u16(dev, tabs)
                 res.append(ops.minmax_values(mm))
+                imgs.append(al16)
             finally:
-                os.environ.pop("PCB_RESAMPLE_NOSKIP", None)
-        assert res[0] == res[1] == ops.minmax_values(mm32) == (float(al32.min()), float(al32.max()))
+                for k in env:
+                    os.environ.pop(k, None)
+        assert all(r == res[0] for r in res), res
+        assert res[0] == ops.minmax_values(mm32) == (float(al32.min()), float(al32.max()))
+        assert all(torch.equal(i, imgs[0]) for i in imgs)
+        assert torch.equal(imgs[0], ops.quantize_u16(al32, mm32))
+
+
+def test_resampler_many_launches_on_two_streams(cuda):
+    """Every launch carries its own tensor map (a kernel parameter): many launches in flight on two streams."""
+    import torch
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_aligner import build_tables
+    from plenopticam_b200.misc import synth
+    cent = synth.synth_centroids(24, 50, 14.25, "hex", jitter=0.15, origin=(9.5, 9.5), seed=3)
+    H, W = int(cent[:, 0].max() + 11), (int(cent[:, 1].max() + 11) + 7) // 8 * 8
+    tabs = ops.LensTables(build_tables(cent, (H, W, 3), 15, "hex"))
+    devs = [ops.to_device(synth.synth_raw(H, W, 3, seed=k)) for k in (2, 3)]
+    refs = [ops.resample_u16(d, tabs)[0] for d in devs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=cuda), torch.cuda.Stream(device=cuda)]
+    outs = []
+    for k in range(60):
+        with torch.cuda.stream(streams[k & 1]):
+            outs.append(ops.resample_u16(devs[k & 1], tabs)[0])
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, refs[k & 1]) for k, o in enumerate(outs))
 
 
 def _srgb_from_aligned(plan, al, pscratch):
