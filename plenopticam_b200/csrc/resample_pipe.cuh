@@ -5,8 +5,9 @@
 // Here a CTA walks many tiles and a dedicated PRODUCER warp runs one tile ahead of the CONSUMER warps:
 //
 //   producer : tile tables (hex-column entries + lens window, one global-memory latency), the tile's bounding box, then
-//              one cp.async.bulk per raw row of the box (TMA unit, no registers, completion on an mbarrier) into a
-//              uint16 ring of two slots; it also snapshots the running global bounds for the min/max pass' skip test;
+//              ONE 2-D tensor copy of the box (cp.async.bulk.tensor.2d; or one cp.async.bulk per raw row when the base or
+//              the row pitch is not 16-byte aligned) - TMA unit, no registers, completion on an mbarrier - into a uint16
+//              ring of two slots; it also snapshots the running global bounds for the min/max pass' skip test;
 //   consumers: wait for the slot, convert it to the float32 tile (shared -> shared, the same magic-number conversion as
 //              before), and run the column loop of resample_col.cuh (rc_columns, unchanged arithmetic: identical bits).
 //
