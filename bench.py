@@ -601,6 +601,7 @@ def main():
     dom = max(stage_names, key=lambda nm: stage_ms[nm])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stage_gbs[dom], "peak": peak, "unit": "GB/s",
                 "frac": stage_gbs[dom] / peak, "traffic": None, "peak_source": peak_src,
+                "peak_nominal": 8000.0, "frac_nominal": stage_gbs[dom] / 8000.0,
                 "algorithmic_bytes_per_launch": abytes[dom], "ms_per_launch": stage_ms[dom],
                 "whole_step": {"algorithmic_bytes": sum(abytes[nm] for nm in stage_names),
                                "achieved": sum(abytes[nm] for nm in stage_names) / (elapsed_ms / K * 1e-3) / 1e9,
