@@ -39,6 +39,43 @@ def test_library_exports_every_declared_symbol():
         assert L.pcb_key_to_float(int(key)) == np.float32(f)
 
 
+def _c_kind(decl):
+    """'p' pointer, 'q' int64, 'd' double, 'f' float, 'u' uint32, 'i' int - of one C parameter / return declaration."""
+    if "*" in decl or "[" in decl:                     # an array parameter is a pointer
+        return "p"
+    for key, kind in (("int64_t", "q"), ("double", "d"), ("float", "f"), ("uint32_t", "u"), ("int", "i")):
+        if re.search(r"\b%s\b" % key, decl):
+            return kind
+    raise AssertionError("unclassified C declaration: %r" % decl)
+
+
+def _ctypes_kind(t):
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(t, (ctypes._Pointer, ctypes.Structure, ctypes.Array)):
+        return "p"
+    return {ctypes.c_int64: "q", ctypes.c_double: "d", ctypes.c_float: "f", ctypes.c_uint32: "u", ctypes.c_int: "i"}[t]
+
+
+def test_binding_signatures_match_the_header_prototypes():
+    """Every entry point: the ctypes argument list of the binding has the number and the kinds (pointer / int / int64 /
+    double / float) of the parameters the header declares, and the same kind of result - a stale binding would pass
+    wrong words to the library without any error."""
+    from plenopticam_b200 import _native
+    txt = open(os.path.join(ROOT, "include", "plenopticam_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"^\s*#.*$", "", txt, flags=re.M)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(pcb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S)
+    seen = {}
+    for ret, name, args in protos:
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        seen[name] = (_c_kind(ret + " x"), [_c_kind(a) for a in params])
+    assert set(seen) == set(_native._SIGNATURES)
+    for name, (res, argtypes) in _native._SIGNATURES.items():
+        want_res, want_args = seen[name]
+        assert _ctypes_kind(res) == want_res, name
+        assert [_ctypes_kind(t) for t in argtypes] == want_args, (name, want_args)
+
+
 def test_argument_validation_without_gpu():
     """Bad arguments are rejected before any CUDA call is made."""
     from plenopticam_b200 import _native
