@@ -49,9 +49,13 @@ class LfpShiftAndSum(LfpViewpoints):
             # the alternates taken when only the aligned image is given (lfp_shiftandsum.py:62-68; `pragma: no cover`
             # upstream, never reached from LfpRefocuser: SURVEY §8a row a11)
             if self.cfg.params[self.cfg.opt_refi]:
+                # the reference's own method cannot run: its shape line (:232) makes m the whole shape tuple for a colour
+                # image (TypeError at :241) and it indexes a third axis of a monochrome one (IndexError at :258) -
+                # tests/test_reference_patch.py::test_reference_scratch_upsample_alternate_cannot_run - so there is no
+                # output to reproduce
                 raise NotImplementedError('refo_from_scratch_upsample (lfp_shiftandsum.py:223-304: linear ramps between '
-                                          'neighbouring micro-image pixels) is not offered; pass vp_img_arr for the '
-                                          'refinement path')
+                                          'neighbouring micro-image pixels) fails in the reference itself (TypeError / '
+                                          'IndexError) and is not offered; pass vp_img_arr for the refinement path')
             if self.refo_from_scratch() is False:
                 return False
         return True

@@ -78,3 +78,24 @@ def test_unmodified_reference_aligner_with_patched_stages_vs_its_own_golden(cuda
         # the centroid table was de-rotated in cfg (lfp_aligner/top_level.py:70) and the image still spans the range
         assert aligned.min() == 0 and aligned.max() == 65535
         assert not np.allclose(np.asarray(cfg.calibs[cfg.mic_list])[:, :2], g["centroids"][:, :2])
+
+
+@needs_ref
+@pytest.mark.parametrize("ndim", [3, 2])
+def test_reference_scratch_upsample_alternate_cannot_run(ndim):
+    """SURVEY 8 row a11': `LfpShiftAndSum.refo_from_scratch_upsample` (lfp_shiftandsum.py:223-304, `pragma: no cover`, the
+    alternate main() takes for an aligned image with opt_refi on) has no output to be equal to: its shape line
+    (`m, n, P = shape if len(shape) == 3 else shape[0], shape[1], 1`, :232) binds the whole shape tuple to m for a colour
+    image (TypeError at :241) and indexes a third axis of a monochrome one (IndexError at :258).  The drop-in class raises
+    NotImplementedError for it (test_cabi_and_host.py::test_unsupported_paths_fail_loudly)."""
+    ref_shim.load_reference()
+    from plenopticam.lfp_refocuser.lfp_shiftandsum import LfpShiftAndSum
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 65536, size=(15, 20, 3) if ndim == 3 else (15, 20), dtype=np.uint16)
+    with tempfile.TemporaryDirectory() as tmp, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cfg, sta = ref_shim.make_cfg_sta(tmp, [[0, 0, 0, 0]], 'rec', 5, ran_refo=(-1, 2))
+        cfg.params[cfg.opt_refi] = True
+        obj = LfpShiftAndSum(lfp_img_align=img, cfg=cfg, sta=sta)
+        with pytest.raises(TypeError if ndim == 3 else IndexError):
+            obj.main()
