@@ -148,13 +148,14 @@ def _srgb_from_aligned(plan, al, pscratch):
     return out, ops.minmax_values(mm), lohi.cpu().numpy().copy()
 
 
-def test_accumulators_come_back_zeroed_across_a_sequence_of_exposures(cuda):
+def test_accumulators_come_back_zeroed_across_a_sequence_of_exposures(cuda, monkeypatch):
     """A plan that serves a SEQUENCE of exposures skips the accumulator memset from the second call on (the finalize pass
     stores zero behind every word it reads, PCB_REFOCUS_LEAVE_ZEROED / _SCRATCH_ZEROED): every stack must equal the one a
     fresh plan gives, for the linear and the fused sRGB form, incl. the degenerate exposures whose upper contrast bound
     is exactly 0 (then the fix-up pass re-reads the sums: the zeroing moves there) and an all-zero exposure."""
     import torch
     from plenopticam_b200 import _native as nat, ops
+    monkeypatch.delenv("PCB_REFOCUS_MEMSET", raising=False)          # the A/B knob that forces the memset form
     Ma, M, S, T = 9, 7, 40, 52
     a_list = list(range(-4, 5))
     rng = np.random.default_rng(11)
