@@ -36,7 +36,9 @@ static inline int grid_for(int64_t n, int per_block) {
 template <int MODE>
 static int dispatch_resample(const ResampleArgs &a, int raw_dtype, float *out_f32, uint16_t *out_u16,
                              pcb_minmax_t *mm_rw, const pcb_minmax_t *mm_ro, cudaStream_t st) {
-    if (resample_pipe_applies(a, raw_dtype)) return launch_resample_pipe<MODE>(a, out_f32, out_u16, mm_rw, mm_ro, st);
+    if (resample_pipe_applies(a, raw_dtype))
+        return raw_dtype == PCB_F32 ? launch_resample_pipe<MODE, float>(a, out_f32, out_u16, mm_rw, mm_ro, st)
+                                    : launch_resample_pipe<MODE, uint16_t>(a, out_f32, out_u16, mm_rw, mm_ro, st);
     if (resample_col_applies(a, raw_dtype)) return launch_resample_col<MODE>(a, out_f32, out_u16, mm_rw, mm_ro, st);
     return launch_resample<MODE>(a, raw_dtype, out_f32, out_u16, mm_rw, mm_ro, st);
 }

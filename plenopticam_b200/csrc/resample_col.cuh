@@ -104,13 +104,14 @@ __device__ __forceinline__ void rc_emit(const ResampleOut<MODE> &out, size_t o, 
 
 // The output columns of one tile: thread `tid` of `nthreads` walks columns tid, tid + nthreads, ... down the patch rows.
 // Shared by the one-tile-per-CTA kernel below and the persistent pipelined kernel of resample_pipe.cuh.
-template <int MODE, int MT, int TS = RC_TS>
+// TRAW: element type of the raw exposure (the direct global path of a tile that was not staged reads it).
+template <int MODE, int MT, int TS = RC_TS, typename TRAW = uint16_t>
 __device__ __forceinline__ void rc_columns(const ResampleArgs &p, const ResampleOut<MODE> &out, const float *tile, int shift,
                                            const pcb_lens_t *s_lens, int xa, bool lens_in_smem, bool use_tile, int ymin,
                                            int xmin, int ly, int k0, int kn, const pcb_hexcol_t *hc, int tid, int nthreads,
                                            float &mn, float &mx) {
     const int M = MT ? MT : p.M;
-    const uint16_t *raw = reinterpret_cast<const uint16_t *>(p.raw);
+    const TRAW *raw = reinterpret_cast<const TRAW *>(p.raw);
     const int ncols_tile = kn * M * 3;
     for (int lc = tid; lc < ncols_tile; lc += nthreads) {
         const int px = lc / 3;
@@ -170,8 +171,8 @@ __device__ __forceinline__ void rc_columns(const ResampleArgs &p, const Resample
             }
         } else {
             const size_t stride = (size_t)p.W * 3;
-            const uint16_t *g0 = raw + ((size_t)(ok0 ? L0.oy : 0) * p.W + (ok0 ? L0.ox : 0) + us) * 3 + ch;
-            const uint16_t *g1 = ok1 ? raw + ((size_t)L1.oy * p.W + L1.ox + us) * 3 + ch : g0;
+            const TRAW *g0 = raw + ((size_t)(ok0 ? L0.oy : 0) * p.W + (ok0 ? L0.ox : 0) + us) * 3 + ch;
+            const TRAW *g1 = ok1 ? raw + ((size_t)L1.oy * p.W + L1.ox + us) * 3 + ch : g0;
             float pa0 = (float)__ldg(g0), pb0 = (float)__ldg(g0 + 3), pa1 = (float)__ldg(g1), pb1 = (float)__ldg(g1 + 3);
             for (int r = 1; r <= M; ++r) {
                 g0 += stride; g1 += stride;

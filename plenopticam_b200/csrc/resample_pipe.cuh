@@ -35,6 +35,20 @@ constexpr int RPK_THREADS = RPK_CONS + 32;           // + one producer warp
 constexpr int RPK_RSTR = ((RPK_TS * 2 + 32 + 15) / 16) * 16;      // bytes per raw row in a ring slot
 constexpr int RPK_SLOT = (RC_ROWS * RPK_RSTR + 127) / 128 * 128;      // bytes per ring slot (tensor copies land 128-byte aligned)
 
+// Per raw element type.  uint16: the slot is converted into a float tile before the column loop.  float32 (what
+// LfpAligner hands on after de-vignetting or rotation): the slot IS the tile - no float tile, no conversion pass; the
+// column loop reads the staged rows in place, which needs every row of the box at the same 16-byte phase (row pitch a
+// multiple of 16 bytes, i.e. W % 4 == 0).
+template <typename T> struct RpkRaw;
+template <> struct RpkRaw<uint16_t> {
+    static constexpr int ES = 2, RSTR = RPK_RSTR, SLOT = RPK_SLOT;
+    static constexpr bool INPLACE = false;
+};
+template <> struct RpkRaw<float> {
+    static constexpr int ES = 4, RSTR = ((RPK_TS * 4 + 32 + 15) / 16) * 16, SLOT = (RC_ROWS * RSTR + 127) / 128 * 128;
+    static constexpr bool INPLACE = true;
+};
+
 struct RpkDesc {                  // what the producer hands over per tile
     int ly, k0, kn, xa, nsrc;     // ly < 0: no more tiles
     int ymin, xmin, R, Wt;
@@ -85,8 +99,10 @@ struct RpkBox {
 
 // (as in resample_col_kernel) source lens range, bounding box of the raw samples, and whether the box can travel by bulk
 // copies: 16-byte aligned supersets of every row inside the caller's buffer, 4-byte phase-aligned rows
+template <typename TRAW = uint16_t>
 __device__ __forceinline__ RpkBox rpk_box(const ResampleArgs &p, int M, int t, int ntx, int lane, const RpkPending &cur,
                                           size_t raw_lo, size_t raw_hi) {
+    constexpr int ES = RpkRaw<TRAW>::ES;
     RpkBox b;
     b.ly = t / ntx; b.k0 = (t - b.ly * ntx) * RPK_KT;
     b.kn = min(RPK_KT, p.Xs - b.k0);
@@ -118,36 +134,37 @@ __device__ __forceinline__ RpkBox rpk_box(const ResampleArgs &p, int M, int t, i
     b.ymin = b0; b.xmin = b2;
     b.R = b1 - b.ymin + M + 1; b.Wt = (b3 - b.xmin + M + 1) * 3;
     const bool any_valid = b1 != INT32_MIN;
-    bool use_tile = b.nsrc <= RC_MAX_SRC && any_valid && b.R <= RC_ROWS && b.Wt + 2 <= RPK_TS &&
-                    (raw_lo & 3) == 0 && ((p.W * 3) & 1) == 0;
+    bool use_tile = b.nsrc <= RC_MAX_SRC && any_valid && b.R <= RC_ROWS && b.Wt + (ES == 2 ? 2 : 4) <= RPK_TS &&
+                    (raw_lo & 3) == 0 && (ES == 2 ? ((p.W * 3) & 1) == 0 : (p.W & 3) == 0);
     b.a0 = 0; b.nbytes = 0;
     if (use_tile && lane < b.R) {
-        const size_t A = raw_lo + (((size_t)(b.ymin + lane)) * p.W + b.xmin) * 6;
+        const size_t A = raw_lo + (((size_t)(b.ymin + lane)) * p.W + b.xmin) * (3 * ES);
         b.a0 = A & ~(size_t)15;
-        b.nbytes = (uint32_t)(((A + (size_t)b.Wt * 2 + 2 + 15) & ~(size_t)15) - b.a0);
+        b.nbytes = (uint32_t)(((A + (size_t)b.Wt * ES + ES + 15) & ~(size_t)15) - b.a0);
     }
     const bool row_ok = !(use_tile && lane < b.R) ||
-                        (b.a0 >= raw_lo && b.a0 + b.nbytes <= raw_hi && b.nbytes <= (uint32_t)RPK_RSTR);
+                        (b.a0 >= raw_lo && b.a0 + b.nbytes <= raw_hi && b.nbytes <= (uint32_t)RpkRaw<TRAW>::RSTR);
     b.use_tile = use_tile && __all_sync(0xffffffffu, row_ok);
     return b;
 }
 
-template <int MODE, int MT>
+template <int MODE, int MT, typename TRAW = uint16_t>
 __global__ void __launch_bounds__(RPK_THREADS, 2)
 resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__restrict__ out_u16, pcb_minmax_t *mm_rw,
                      const pcb_minmax_t *mm_ro, int ntx, int ntiles, const __grid_constant__ CUtensorMap tmap, int use2d) {
+    using RR = RpkRaw<TRAW>;
+    constexpr int ES = RR::ES;
     extern __shared__ __align__(128) unsigned char dsm[];
-    float *tile = reinterpret_cast<float *>(dsm);                                  // [RC_ROWS][RPK_TS]
-    unsigned char *ring = dsm + (size_t)RC_ROWS * RPK_TS * sizeof(float);           // 2 slots of RPK_SLOT bytes
+    float *tile = reinterpret_cast<float *>(dsm);                                  // [RC_ROWS][RPK_TS] (uint16 only)
+    unsigned char *ring = dsm + (RR::INPLACE ? 0 : (size_t)RC_ROWS * RPK_TS * sizeof(float));    // 2 slots of RR::SLOT bytes
     __shared__ RpkDesc s_desc[2];
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
-    __shared__ int s_smm[2];
+    __shared__ uint32_t s_smm[2];          // min / max of the staged raw samples (uint16 values, or ordered keys of floats)
     __shared__ uint32_t s_tmm[2];          // ordered keys of the min / max of the tile being interpolated
     const int M = MT ? MT : p.M;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const uint16_t *raw = reinterpret_cast<const uint16_t *>(p.raw);
-    const size_t raw_lo = reinterpret_cast<size_t>(raw), raw_hi = raw_lo + (size_t)p.H * p.W * 6;
+    const size_t raw_lo = reinterpret_cast<size_t>(p.raw), raw_hi = raw_lo + (size_t)p.H * p.W * (3 * ES);
     const bool may_skip = MODE == RS_MINMAX && mm_rw != nullptr && p.skip;
 
     if (tid == 0) {
@@ -168,14 +185,14 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
             uint32_t total = use_tile && lane < b->R ? b->nbytes : 0u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            if (use_tile && use2d) total = (uint32_t)(RC_ROWS * RPK_RSTR);         // the box of the tensor map, whole
+            if (use_tile && use2d) total = (uint32_t)(RC_ROWS * RR::RSTR);         // the box of the tensor map, whole
             // the slot (ring rows AND descriptor) is free once the consumers are through with the tile before last
             if (it >= 2) mbar_wait(&s_empty[slot], ((it >> 1) - 1) & 1);
             RpkDesc &d = s_desc[slot];
             if (b != nullptr) {
                 if (b->mine) d.lens[lane] = b->L;
                 if (use_tile && lane < b->R) {
-                    const size_t A = raw_lo + (((size_t)(b->ymin + lane)) * p.W + b->xmin) * 6;
+                    const size_t A = raw_lo + (((size_t)(b->ymin + lane)) * p.W + b->xmin) * (3 * ES);
                     d.rowoff[lane] = (int)(A - b->a0);
                 }
                 if (lane == 0) {
@@ -198,10 +215,10 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
                 // ONE tensor copy of the whole box (19 rows x 1440 bytes, zero-filled outside the image): 19 row copies per
                 // tile cost the pipeline 40 % more time than one copy of the same bytes
                 if (lane == 0)
-                    tma_tensor2d_g2s(ring + (size_t)slot * RPK_SLOT, &tmap, (b->xmin * 6 & ~15) >> 3, b->ymin, &s_full[slot]);
+                    tma_tensor2d_g2s(ring + (size_t)slot * RR::SLOT, &tmap, (b->xmin * (3 * ES) & ~15) >> 3, b->ymin, &s_full[slot]);
             } else
             if (use_tile && lane < b->R)
-                tma_bulk_g2s(ring + (size_t)slot * RPK_SLOT + (size_t)lane * RPK_RSTR, reinterpret_cast<const void *>(b->a0),
+                tma_bulk_g2s(ring + (size_t)slot * RR::SLOT + (size_t)lane * RR::RSTR, reinterpret_cast<const void *>(b->a0),
                              b->nbytes, &s_full[slot]);
             ++it;
         };
@@ -228,7 +245,7 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
                     g_mn = key_to_float(__shfl_sync(0xffffffffu, kmn, 0));
                     g_mx = key_to_float(__shfl_sync(0xffffffffu, kmx, 0));
                 }
-                const RpkBox b = rpk_box(p, M, t, ntx, lane, cur, raw_lo, raw_hi);
+                const RpkBox b = rpk_box<TRAW>(p, M, t, ntx, lane, cur, raw_lo, raw_hi);
                 hand_over(&b, g_mn, g_mx);
             }
         }
@@ -249,30 +266,51 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
         const bool use_tile = d.use_tile != 0;
         const int R = d.R, Wt = d.Wt;
         int shift = 0;
-        const unsigned char *srow0 = ring + (size_t)slot * RPK_SLOT;
+        const unsigned char *srow0 = ring + (size_t)slot * RR::SLOT;
         int nw = 0;
         if (use_tile) {
-            shift = (d.rowoff[0] >> 1) & 1;                                     // same phase for every row (W * 3 even)
-            nw = (Wt + shift + 1) >> 1;             // words per row from the word that holds the first sample
+            if (RR::INPLACE) {
+                shift = d.rowoff[0] >> 2;                                       // samples from the start of the slot row
+                nw = (d.rowoff[0] + Wt * 4 + 15) >> 4;                          // 16-byte vectors per row (scan)
+            } else {
+                shift = (d.rowoff[0] >> 1) & 1;                                 // same phase for every row (W * 3 even)
+                nw = (Wt + shift + 1) >> 1;         // words per row from the word that holds the first sample
+            }
         }
         bool skip = false;
         if (may_skip) {
-            // min / max of the raw samples of the tile on the packed uint16 pairs (a word may hold one sample before /
-            // after the box: neighbours of the row, a superset is fine); most tiles end here
-            if (tid == 0) { s_smm[0] = 0xffff; s_smm[1] = 0; }
-            uint32_t pmn = 0xffffffffu, pmx = 0u;
-            if (use_tile) {
-                for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
-                    const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RPK_RSTR + (d.rowoff[rr] & ~3));
-#pragma unroll 4
-                    for (int m = lane; m < nw; m += 32) {
-                        const uint32_t v = wsrc[m];
-                        pmn = __vminu2(pmn, v);
-                        pmx = __vmaxu2(pmx, v);
+            // min / max of the raw samples of the tile (a word / vector may hold samples before or after the box:
+            // neighbours of the row, a superset is fine); most tiles end here
+            if (tid == 0) { s_smm[0] = 0xffffffffu; s_smm[1] = 0u; }
+            uint32_t lo, hi;
+            if (RR::INPLACE) {
+                float fmn = INFINITY, fmx = -INFINITY;
+                if (use_tile) {
+                    for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
+                        const float4 *vsrc = reinterpret_cast<const float4 *>(srow0 + (size_t)rr * RR::RSTR);
+                        for (int m = lane; m < nw; m += 32) {
+                            const float4 v = vsrc[m];
+                            fmn = fminf(fmn, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+                            fmx = fmaxf(fmx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+                        }
                     }
                 }
+                lo = float_to_key(fmn); hi = float_to_key(fmx);                 // order-preserving keys
+            } else {
+                uint32_t pmn = 0xffffffffu, pmx = 0u;
+                if (use_tile) {
+                    for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
+                        const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RR::RSTR + (d.rowoff[rr] & ~3));
+#pragma unroll 4
+                        for (int m = lane; m < nw; m += 32) {
+                            const uint32_t v = wsrc[m];
+                            pmn = __vminu2(pmn, v);
+                            pmx = __vmaxu2(pmx, v);
+                        }
+                    }
+                }
+                lo = min(pmn & 0xffffu, pmn >> 16); hi = max(pmx & 0xffffu, pmx >> 16);
             }
-            uint32_t lo = min(pmn & 0xffffu, pmn >> 16), hi = max(pmx & 0xffffu, pmx >> 16);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -280,19 +318,21 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
             }
             rpk_consumer_sync();             // s_smm reset visible
             if (lane == 0 && use_tile) {
-                atomicMin(&s_smm[0], (int)lo);
-                atomicMax(&s_smm[1], (int)hi);
+                atomicMin(&s_smm[0], lo);
+                atomicMax(&s_smm[1], hi);
             }
             rpk_consumer_sync();             // s_smm complete
             if (use_tile && d.ninv == 0) {
-                const float tmn = (float)s_smm[0], tmx = (float)s_smm[1];
-                skip = tmn * (1.f - RC_SKIP_EPS) > d.g_mn && tmx * (1.f + RC_SKIP_EPS) < d.g_mx;      // uniform over the CTA
+                const float tmn = RR::INPLACE ? key_to_float(s_smm[0]) : (float)s_smm[0];
+                const float tmx = RR::INPLACE ? key_to_float(s_smm[1]) : (float)s_smm[1];
+                // the margins scale with the magnitude, whatever the sign (float exposures may hold negative samples)
+                skip = tmn - fabsf(tmn) * RC_SKIP_EPS > d.g_mn && tmx + fabsf(tmx) * RC_SKIP_EPS < d.g_mx;     // uniform over the CTA
             }
         }
-        if (use_tile && !skip) {
+        if (!RR::INPLACE && use_tile && !skip) {
             // ring slot (uint16, any 2-byte phase) -> float tile: whole 32-bit words
             for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
-                const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RPK_RSTR + (d.rowoff[rr] & ~3));
+                const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(srow0 + (size_t)rr * RR::RSTR + (d.rowoff[rr] & ~3));
                 float2 *dst = reinterpret_cast<float2 *>(tile + rr * RPK_TS);
 #pragma unroll 4
                 for (int m = lane; m < nw; m += 32) {
@@ -302,12 +342,17 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
                 }
             }
         }
-        if (!skip) rpk_consumer_sync();      // tile complete (uniform: every consumer took the same decision)
+        if (!RR::INPLACE && !skip) rpk_consumer_sync();      // tile complete (uniform: every consumer took the same decision)
         if (!skip) {
             const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((d.ly + p.hex_odd) & 1) * p.Xs : nullptr;
             float mn = INFINITY, mx = -INFINITY;
-            rc_columns<MODE, MT, RPK_TS>(p, out, tile, shift, d.lens, d.xa, d.nsrc <= RC_MAX_SRC, use_tile, d.ymin, d.xmin, d.ly,
-                                 d.k0, d.kn, hc, tid, RPK_CONS, mn, mx);
+            if (RR::INPLACE)
+                rc_columns<MODE, MT, RR::RSTR / 4, TRAW>(p, out, reinterpret_cast<const float *>(srow0), shift, d.lens, d.xa,
+                                                         d.nsrc <= RC_MAX_SRC, use_tile, d.ymin, d.xmin, d.ly, d.k0, d.kn, hc,
+                                                         tid, RPK_CONS, mn, mx);
+            else
+                rc_columns<MODE, MT, RPK_TS, TRAW>(p, out, tile, shift, d.lens, d.xa, d.nsrc <= RC_MAX_SRC, use_tile, d.ymin,
+                                                   d.xmin, d.ly, d.k0, d.kn, hc, tid, RPK_CONS, mn, mx);
             if (MODE != RS_U16 && mm_rw != nullptr) {
                 // fold the tile's bounds in shared memory first: ONE pair of global atomics per tile (and only when the tile
                 // moves the bounds the producer saw) - every warp hitting the same two global words serialises in L2
@@ -337,6 +382,8 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
 static bool resample_pipe_applies(const ResampleArgs &a, int raw_dtype) {
     const char *e = getenv("PCB_RESAMPLE_KERNEL");
     if (e && (!strcmp(e, "tile") || !strcmp(e, "col"))) return false;
+    if (raw_dtype == PCB_F32)           // the slot is the tile: every row of a box at the same 16-byte phase
+        return a.C == 3 && a.M + 2 <= RC_ROWS && a.M >= 1 && (a.W & 3) == 0 && (reinterpret_cast<size_t>(a.raw) & 3) == 0;
     return raw_dtype == PCB_U16 && a.C == 3 && a.M + 2 <= RC_ROWS && a.M >= 1;
 }
 
@@ -368,24 +415,25 @@ static bool rpk_make_tensor_map(const ResampleArgs &a, CUtensorMap *map) {
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int MODE>
+template <int MODE, typename TRAW = uint16_t>
 static int launch_resample_pipe(const ResampleArgs &a_in, float *out_f32, uint16_t *out_u16, pcb_minmax_t *mm_rw,
                                 const pcb_minmax_t *mm_ro, cudaStream_t st) {
+    using RR = RpkRaw<TRAW>;
     ResampleArgs a = a_in;
     a.skip = (getenv("PCB_RESAMPLE_NOSKIP") && atoi(getenv("PCB_RESAMPLE_NOSKIP"))) ? 0 : 1;
-    const size_t smem = (size_t)RC_ROWS * RPK_TS * sizeof(float) + 2 * (size_t)RPK_SLOT;
+    const size_t smem = (RR::INPLACE ? 0 : (size_t)RC_ROWS * RPK_TS * sizeof(float)) + 2 * (size_t)RR::SLOT;
     const int ntx = (a.Xs + RPK_KT - 1) / RPK_KT;
     const int ntiles = ntx * a.LY;
     const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
     alignas(64) CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    const int use2d = rpk_make_tensor_map(a, &tmap) ? 1 : 0;
+    const int use2d = (RR::ES == 2 && rpk_make_tensor_map(a, &tmap)) ? 1 : 0;       // float rows exceed one tensor box
     if (a.M == 15) {
-        PCB_CUDA(cudaFuncSetAttribute(resample_pipe_kernel<MODE, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        resample_pipe_kernel<MODE, 15><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles, tmap, use2d);
+        PCB_CUDA(cudaFuncSetAttribute(resample_pipe_kernel<MODE, 15, TRAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resample_pipe_kernel<MODE, 15, TRAW><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles, tmap, use2d);
     } else {
-        PCB_CUDA(cudaFuncSetAttribute(resample_pipe_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        resample_pipe_kernel<MODE, 0><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles, tmap, use2d);
+        PCB_CUDA(cudaFuncSetAttribute(resample_pipe_kernel<MODE, 0, TRAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resample_pipe_kernel<MODE, 0, TRAW><<<grid, RPK_THREADS, smem, st>>>(a, out_f32, out_u16, mm_rw, mm_ro, ntx, ntiles, tmap, use2d);
     }
     PCB_LAUNCH_OK();
     return PCB_OK;

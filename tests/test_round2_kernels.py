@@ -212,3 +212,39 @@ def test_a_launch_without_flags_marks_the_shared_scratch_dirty(cuda):
     assert p_al.scratch._pcb_acc_zero is False
     assert torch.equal(ops.refocus_int_from_aligned(al, Ma, a_list, plan=p_al), ref)
     assert torch.equal(ops.refocus_int_from_aligned(al, Ma, a_list, plan=p_al), ref)
+
+
+@pytest.mark.parametrize("pat,W4,negative", [("hex", True, False), ("rec", True, False), ("hex", False, False),
+                                             ("hex", True, True)])
+def test_float32_exposures_through_the_pipelined_resampler(cuda, pat, W4, negative):
+    """float32 exposures (what LfpAligner hands on after de-vignetting or rotation) take the persistent kernel too when
+    the row pitch is a multiple of 16 bytes (W % 4 == 0: the ring slot is the tile, read in place), else the general
+    tiled kernel.  Same image as the uint16 exposure of the same values, the bounds of the min/max pass (with tile
+    skipping, also with negative samples) are those of the image, the quantised image is the quantised float image."""
+    import torch
+    from plenopticam_b200 import ops
+    from plenopticam_b200.lfp_aligner import build_tables
+    from plenopticam_b200.misc import synth
+    cent = synth.synth_centroids(40, 90, 14.25, pat, jitter=0.15, origin=(9.5, 9.5), seed=8)
+    H, W = int(cent[:, 0].max() + 11), int(cent[:, 1].max() + 11)
+    W = (W + 3) // 4 * 4 if W4 else W // 4 * 4 + 1
+    tabs = ops.LensTables(build_tables(cent, (H, W, 3), 15, pat))
+    raw16 = synth.synth_raw(H, W, 3, seed=9)
+    raw32 = raw16.astype(np.float32)
+    if negative:
+        raw32 = raw32 - 30000.0
+    d16, d32 = ops.to_device(raw16), ops.to_device(raw32)
+    al_ref = ops.resample_f32(d16, tabs)                              # uint16 exposure, persistent kernel (pinned elsewhere)
+    al32, mm32 = ops.resample_f32(d32, tabs, want_minmax=True)
+    off = 30000.0 if negative else 0.0
+    assert float((al32 + off - al_ref).abs().max()) <= (2e-6 * 65535 if not negative else 2e-2)
+    assert ops.minmax_values(mm32) == (float(al32.min()), float(al32.max()))
+    q, mm = ops.resample_u16(d32, tabs)
+    assert ops.minmax_values(mm) == ops.minmax_values(mm32)
+    assert torch.equal(q, ops.quantize_u16(al32, mm32))
+    os.environ["PCB_RESAMPLE_KERNEL"] = "tile"                       # the general kernel on the same exposure
+    try:
+        al_t, mm_t = ops.resample_f32(d32, tabs, want_minmax=True)
+    finally:
+        os.environ.pop("PCB_RESAMPLE_KERNEL", None)
+    assert float((al32 - al_t).abs().max()) <= 2e-6 * 65535
