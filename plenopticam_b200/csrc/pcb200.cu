@@ -36,9 +36,17 @@ static inline int grid_for(int64_t n, int per_block) {
 template <int MODE>
 static int dispatch_resample(const ResampleArgs &a, int raw_dtype, float *out_f32, uint16_t *out_u16,
                              pcb_minmax_t *mm_rw, const pcb_minmax_t *mm_ro, cudaStream_t st) {
-    if (resample_pipe_applies(a, raw_dtype))
-        return raw_dtype == PCB_F32 ? launch_resample_pipe<MODE, float>(a, out_f32, out_u16, mm_rw, mm_ro, st)
-                                    : launch_resample_pipe<MODE, uint16_t>(a, out_f32, out_u16, mm_rw, mm_ro, st);
+    if (resample_pipe_applies(a, raw_dtype)) {
+        if (raw_dtype == PCB_F32) return launch_resample_pipe<MODE, float>(a, out_f32, out_u16, mm_rw, mm_ro, st);
+        // the min/max pass interpolates a fraction of its tiles only: it reads the uint16 rows in place (conversion in the
+        // column loop) and spends the shared memory of the float tile on a ring of four slots (0.171 -> 0.160 ms); the passes
+        // that interpolate every tile keep the converted tile (in place they are slower: 0.302 -> 0.332 ms)
+        const char *e = getenv("PCB_RESAMPLE_INPLACE");
+        const bool inplace = e ? atoi(e) != 0 : MODE == RS_MINMAX;
+        if ((a.W & 7) == 0 && inplace)
+            return launch_resample_pipe<MODE, RpkU16InPlace>(a, out_f32, out_u16, mm_rw, mm_ro, st);
+        return launch_resample_pipe<MODE, uint16_t>(a, out_f32, out_u16, mm_rw, mm_ro, st);
+    }
     if (resample_col_applies(a, raw_dtype)) return launch_resample_col<MODE>(a, out_f32, out_u16, mm_rw, mm_ro, st);
     return launch_resample<MODE>(a, raw_dtype, out_f32, out_u16, mm_rw, mm_ro, st);
 }

@@ -104,9 +104,14 @@ __device__ __forceinline__ void rc_emit(const ResampleOut<MODE> &out, size_t o, 
 
 // The output columns of one tile: thread `tid` of `nthreads` walks columns tid, tid + nthreads, ... down the patch rows.
 // Shared by the one-tile-per-CTA kernel below and the persistent pipelined kernel of resample_pipe.cuh.
+// a staged sample as float: float32 tiles as they are, uint16 tiles (raw samples read in place) through the 2^23 trick
+__device__ __forceinline__ float rc_ld(const float *q) { return *q; }
+__device__ __forceinline__ float rc_ld(const uint16_t *q) { return u16_to_float_magic((uint32_t)*q); }
+
 // TRAW: element type of the raw exposure (the direct global path of a tile that was not staged reads it).
-template <int MODE, int MT, int TS = RC_TS, typename TRAW = uint16_t>
-__device__ __forceinline__ void rc_columns(const ResampleArgs &p, const ResampleOut<MODE> &out, const float *tile, int shift,
+// TE: element type of the staged tile (float32, or uint16_t = the raw samples as fetched, converted on load).
+template <int MODE, int MT, int TS = RC_TS, typename TRAW = uint16_t, typename TE = float>
+__device__ __forceinline__ void rc_columns(const ResampleArgs &p, const ResampleOut<MODE> &out, const TE *tile, int shift,
                                            const pcb_lens_t *s_lens, int xa, bool lens_in_smem, bool use_tile, int ymin,
                                            int xmin, int ly, int k0, int kn, const pcb_hexcol_t *hc, int tid, int nthreads,
                                            float &mn, float &mx) {
@@ -141,13 +146,13 @@ __device__ __forceinline__ void rc_columns(const ResampleArgs &p, const Resample
         const long long ostep = p.flip ? -(long long)p.ncols : (long long)p.ncols;
 
         if (use_tile) {
-            const float *t0 = tile + shift + (ok0 ? (L0.oy - ymin) * TS + (L0.ox - xmin + us) * 3 + ch : 0);
-            const float *t1 = ok1 ? tile + shift + (L1.oy - ymin) * TS + (L1.ox - xmin + us) * 3 + ch : t0;   // finite x 0
-            float pa0 = t0[0], pb0 = t0[3], pa1 = t1[0], pb1 = t1[3];
+            const TE *t0 = tile + shift + (ok0 ? (L0.oy - ymin) * TS + (L0.ox - xmin + us) * 3 + ch : 0);
+            const TE *t1 = ok1 ? tile + shift + (L1.oy - ymin) * TS + (L1.ox - xmin + us) * 3 + ch : t0;   // finite x 0
+            float pa0 = rc_ld(t0), pb0 = rc_ld(t0 + 3), pa1 = rc_ld(t1), pb1 = rc_ld(t1 + 3);
             if (MT) {
 #pragma unroll
                 for (int r = 1; r <= (MT ? MT : 1); ++r) {
-                    const float a0 = t0[r * TS], b0 = t0[r * TS + 3], a1 = t1[r * TS], b1 = t1[r * TS + 3];
+                    const float a0 = rc_ld(t0 + r * TS), b0 = rc_ld(t0 + r * TS + 3), a1 = rc_ld(t1 + r * TS), b1 = rc_ld(t1 + r * TS + 3);
                     float val = W000 * pa0;
                     val = fmaf(W001, pb0, val); val = fmaf(W010, a0, val); val = fmaf(W011, b0, val);
                     val = fmaf(W100, pa1, val); val = fmaf(W101, pb1, val); val = fmaf(W110, a1, val);
@@ -159,7 +164,7 @@ __device__ __forceinline__ void rc_columns(const ResampleArgs &p, const Resample
             } else {
                 for (int r = 1; r <= M; ++r) {
                     t0 += TS; t1 += TS;
-                    const float a0 = t0[0], b0 = t0[3], a1 = t1[0], b1 = t1[3];
+                    const float a0 = rc_ld(t0), b0 = rc_ld(t0 + 3), a1 = rc_ld(t1), b1 = rc_ld(t1 + 3);
                     float val = W000 * pa0;
                     val = fmaf(W001, pb0, val); val = fmaf(W010, a0, val); val = fmaf(W011, b0, val);
                     val = fmaf(W100, pa1, val); val = fmaf(W101, pb1, val); val = fmaf(W110, a1, val);

@@ -39,13 +39,21 @@ constexpr int RPK_SLOT = (RC_ROWS * RPK_RSTR + 127) / 128 * 128;      // bytes p
 // LfpAligner hands on after de-vignetting or rotation): the slot IS the tile - no float tile, no conversion pass; the
 // column loop reads the staged rows in place, which needs every row of the box at the same 16-byte phase (row pitch a
 // multiple of 16 bytes, i.e. W % 4 == 0).
+struct RpkU16InPlace {};          // tag: uint16 exposure whose rows share one 16-byte phase (W % 8 == 0), read in place
 template <typename T> struct RpkRaw;
 template <> struct RpkRaw<uint16_t> {
-    static constexpr int ES = 2, RSTR = RPK_RSTR, SLOT = RPK_SLOT;
+    typedef uint16_t elem;
+    static constexpr int ES = 2, RSTR = RPK_RSTR, SLOT = RPK_SLOT, NSLOT = 2;
     static constexpr bool INPLACE = false;
 };
+template <> struct RpkRaw<RpkU16InPlace> {
+    typedef uint16_t elem;
+    static constexpr int ES = 2, RSTR = RPK_RSTR, SLOT = RPK_SLOT, NSLOT = 4;
+    static constexpr bool INPLACE = true;
+};
 template <> struct RpkRaw<float> {
-    static constexpr int ES = 4, RSTR = ((RPK_TS * 4 + 32 + 15) / 16) * 16, SLOT = (RC_ROWS * RSTR + 127) / 128 * 128;
+    typedef float elem;
+    static constexpr int ES = 4, RSTR = ((RPK_TS * 4 + 32 + 15) / 16) * 16, SLOT = (RC_ROWS * RSTR + 127) / 128 * 128, NSLOT = 2;
     static constexpr bool INPLACE = true;
 };
 
@@ -135,7 +143,7 @@ __device__ __forceinline__ RpkBox rpk_box(const ResampleArgs &p, int M, int t, i
     b.R = b1 - b.ymin + M + 1; b.Wt = (b3 - b.xmin + M + 1) * 3;
     const bool any_valid = b1 != INT32_MIN;
     bool use_tile = b.nsrc <= RC_MAX_SRC && any_valid && b.R <= RC_ROWS && b.Wt + (ES == 2 ? 2 : 4) <= RPK_TS &&
-                    (raw_lo & 3) == 0 && (ES == 2 ? ((p.W * 3) & 1) == 0 : (p.W & 3) == 0);
+                    (raw_lo & 3) == 0 && ((p.W * 3 * ES) & (RpkRaw<TRAW>::INPLACE ? 15 : 3)) == 0;
     b.a0 = 0; b.nbytes = 0;
     if (use_tile && lane < b.R) {
         const size_t A = raw_lo + (((size_t)(b.ymin + lane)) * p.W + b.xmin) * (3 * ES);
@@ -153,12 +161,14 @@ __global__ void __launch_bounds__(RPK_THREADS, 2)
 resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__restrict__ out_u16, pcb_minmax_t *mm_rw,
                      const pcb_minmax_t *mm_ro, int ntx, int ntiles, const __grid_constant__ CUtensorMap tmap, int use2d) {
     using RR = RpkRaw<TRAW>;
+    typedef typename RR::elem TEL;
     constexpr int ES = RR::ES;
     extern __shared__ __align__(128) unsigned char dsm[];
     float *tile = reinterpret_cast<float *>(dsm);                                  // [RC_ROWS][RPK_TS] (uint16 only)
     unsigned char *ring = dsm + (RR::INPLACE ? 0 : (size_t)RC_ROWS * RPK_TS * sizeof(float));    // 2 slots of RR::SLOT bytes
-    __shared__ RpkDesc s_desc[2];
-    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    constexpr int NSLOT = RR::NSLOT;
+    __shared__ RpkDesc s_desc[NSLOT];
+    __shared__ __align__(8) uint64_t s_full[NSLOT], s_empty[NSLOT];
     __shared__ uint32_t s_smm[2];          // min / max of the staged raw samples (uint16 values, or ordered keys of floats)
     __shared__ uint32_t s_tmm[2];          // ordered keys of the min / max of the tile being interpolated
     const int M = MT ? MT : p.M;
@@ -169,8 +179,7 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
 
     if (tid == 0) {
         s_tmm[0] = 0xffffffffu; s_tmm[1] = 0u;
-        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-        mbar_init(&s_empty[0], RPK_CONS / 32); mbar_init(&s_empty[1], RPK_CONS / 32);
+        for (int k = 0; k < NSLOT; ++k) { mbar_init(&s_full[k], 1); mbar_init(&s_empty[k], RPK_CONS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -180,14 +189,14 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
         int it = 0;                        // descriptors handed over so far
         // hand one tile (or the end marker, b == nullptr) to the consumers through the next ring slot
         auto hand_over = [&](const RpkBox *b, float g_mn, float g_mx) {
-            const int slot = it & 1;
+            const int slot = it % NSLOT;
             const bool use_tile = b != nullptr && b->use_tile;
             uint32_t total = use_tile && lane < b->R ? b->nbytes : 0u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             if (use_tile && use2d) total = (uint32_t)(RC_ROWS * RR::RSTR);         // the box of the tensor map, whole
             // the slot (ring rows AND descriptor) is free once the consumers are through with the tile before last
-            if (it >= 2) mbar_wait(&s_empty[slot], ((it >> 1) - 1) & 1);
+            if (it >= NSLOT) mbar_wait(&s_empty[slot], ((it / NSLOT) - 1) & 1);
             RpkDesc &d = s_desc[slot];
             if (b != nullptr) {
                 if (b->mine) d.lens[lane] = b->L;
@@ -259,8 +268,8 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
     out.qz.init(0.f, 0.f);
     if (MODE == RS_U16) out.qz.init(key_to_float(mm_ro->kmin), key_to_float(mm_ro->kmax));
     for (int it = 0;; ++it) {
-        const int slot = it & 1;
-        mbar_wait(&s_full[slot], (it >> 1) & 1);
+        const int slot = it % NSLOT;
+        mbar_wait(&s_full[slot], (it / NSLOT) & 1);
         const RpkDesc &d = s_desc[slot];
         if (d.ly < 0) break;
         const bool use_tile = d.use_tile != 0;
@@ -270,8 +279,8 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
         int nw = 0;
         if (use_tile) {
             if (RR::INPLACE) {
-                shift = d.rowoff[0] >> 2;                                       // samples from the start of the slot row
-                nw = (d.rowoff[0] + Wt * 4 + 15) >> 4;                          // 16-byte vectors per row (scan)
+                shift = d.rowoff[0] / ES;                                       // samples from the start of the slot row
+                nw = (d.rowoff[0] + Wt * ES + 15) >> 4;                         // 16-byte vectors per row (scan)
             } else {
                 shift = (d.rowoff[0] >> 1) & 1;                                 // same phase for every row (W * 3 even)
                 nw = (Wt + shift + 1) >> 1;         // words per row from the word that holds the first sample
@@ -283,7 +292,20 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
             // neighbours of the row, a superset is fine); most tiles end here
             if (tid == 0) { s_smm[0] = 0xffffffffu; s_smm[1] = 0u; }
             uint32_t lo, hi;
-            if (RR::INPLACE) {
+            if (RR::INPLACE && ES == 2) {
+                uint32_t pmn = 0xffffffffu, pmx = 0u;
+                if (use_tile) {
+                    for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
+                        const uint4 *vsrc = reinterpret_cast<const uint4 *>(srow0 + (size_t)rr * RR::RSTR);
+                        for (int m = lane; m < nw; m += 32) {
+                            const uint4 v = vsrc[m];
+                            pmn = __vminu2(__vminu2(pmn, v.x), __vminu2(__vminu2(v.y, v.z), v.w));
+                            pmx = __vmaxu2(__vmaxu2(pmx, v.x), __vmaxu2(__vmaxu2(v.y, v.z), v.w));
+                        }
+                    }
+                }
+                lo = min(pmn & 0xffffu, pmn >> 16); hi = max(pmx & 0xffffu, pmx >> 16);
+            } else if (RR::INPLACE) {
                 float fmn = INFINITY, fmx = -INFINITY;
                 if (use_tile) {
                     for (int rr = warp; rr < R; rr += RPK_CONS / 32) {
@@ -323,8 +345,8 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
             }
             rpk_consumer_sync();             // s_smm complete
             if (use_tile && d.ninv == 0) {
-                const float tmn = RR::INPLACE ? key_to_float(s_smm[0]) : (float)s_smm[0];
-                const float tmx = RR::INPLACE ? key_to_float(s_smm[1]) : (float)s_smm[1];
+                const float tmn = ES == 4 ? key_to_float(s_smm[0]) : (float)s_smm[0];
+                const float tmx = ES == 4 ? key_to_float(s_smm[1]) : (float)s_smm[1];
                 // the margins scale with the magnitude, whatever the sign (float exposures may hold negative samples)
                 skip = tmn - fabsf(tmn) * RC_SKIP_EPS > d.g_mn && tmx + fabsf(tmx) * RC_SKIP_EPS < d.g_mx;     // uniform over the CTA
             }
@@ -347,12 +369,12 @@ resample_pipe_kernel(ResampleArgs p, float *__restrict__ out_f32, uint16_t *__re
             const pcb_hexcol_t *hc = p.hexcol ? p.hexcol + ((d.ly + p.hex_odd) & 1) * p.Xs : nullptr;
             float mn = INFINITY, mx = -INFINITY;
             if (RR::INPLACE)
-                rc_columns<MODE, MT, RR::RSTR / 4, TRAW>(p, out, reinterpret_cast<const float *>(srow0), shift, d.lens, d.xa,
-                                                         d.nsrc <= RC_MAX_SRC, use_tile, d.ymin, d.xmin, d.ly, d.k0, d.kn, hc,
-                                                         tid, RPK_CONS, mn, mx);
+                rc_columns<MODE, MT, RR::RSTR / ES, TEL, TEL>(p, out, reinterpret_cast<const TEL *>(srow0), shift, d.lens, d.xa,
+                                                              d.nsrc <= RC_MAX_SRC, use_tile, d.ymin, d.xmin, d.ly, d.k0, d.kn,
+                                                              hc, tid, RPK_CONS, mn, mx);
             else
-                rc_columns<MODE, MT, RPK_TS, TRAW>(p, out, tile, shift, d.lens, d.xa, d.nsrc <= RC_MAX_SRC, use_tile, d.ymin,
-                                                   d.xmin, d.ly, d.k0, d.kn, hc, tid, RPK_CONS, mn, mx);
+                rc_columns<MODE, MT, RPK_TS, TEL>(p, out, tile, shift, d.lens, d.xa, d.nsrc <= RC_MAX_SRC, use_tile, d.ymin,
+                                                  d.xmin, d.ly, d.k0, d.kn, hc, tid, RPK_CONS, mn, mx);
             if (MODE != RS_U16 && mm_rw != nullptr) {
                 // fold the tile's bounds in shared memory first: ONE pair of global atomics per tile (and only when the tile
                 // moves the bounds the producer saw) - every warp hitting the same two global words serialises in L2
@@ -421,7 +443,7 @@ static int launch_resample_pipe(const ResampleArgs &a_in, float *out_f32, uint16
     using RR = RpkRaw<TRAW>;
     ResampleArgs a = a_in;
     a.skip = (getenv("PCB_RESAMPLE_NOSKIP") && atoi(getenv("PCB_RESAMPLE_NOSKIP"))) ? 0 : 1;
-    const size_t smem = (RR::INPLACE ? 0 : (size_t)RC_ROWS * RPK_TS * sizeof(float)) + 2 * (size_t)RR::SLOT;
+    const size_t smem = (RR::INPLACE ? 0 : (size_t)RC_ROWS * RPK_TS * sizeof(float)) + (size_t)RR::NSLOT * RR::SLOT;
     const int ntx = (a.Xs + RPK_KT - 1) / RPK_KT;
     const int ntiles = ntx * a.LY;
     const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
