@@ -12,9 +12,16 @@
 //              before), and run the column loop of resample_col.cuh (rc_columns, unchanged arithmetic: identical bits).
 //
 // So the global-memory latency of tile t+1 is spent while tile t is interpolated, a dropped tile of the min/max pass costs
-// its conversion only (no CTA launch, no table / raw latency on the critical path), and there is no per-tile CTA
-// prologue.  Tiles whose aligned bulk copies would leave the caller's buffer, whose box does not fit the tile, or rows
-// that are not 4-byte phase-aligned take the direct global path inside rc_columns, exactly like the one-tile kernel.
+// its scan only (no CTA launch, no table / raw latency on the critical path), and there is no per-tile CTA prologue.
+// Tiles whose aligned bulk copies would leave the caller's buffer, whose box does not fit the tile, or rows that are not
+// 4-byte phase-aligned take the direct global path inside rc_columns, exactly like the one-tile kernel.
+//
+// Three forms of the slot (RpkRaw<>):
+//   uint16_t       the slot is converted into a float tile (two slots + tile, 108 KB) - the passes that interpolate every
+//                  tile (quantise, float output);
+//   RpkU16InPlace  no float tile: the column loop reads the uint16 rows in place (conversion on load) and the ring has four
+//                  slots - the min/max pass, which interpolates a fraction of its tiles (needs W % 8 == 0);
+//   float          float32 exposures (after de-vignetting / rotation): the slot IS the tile, read in place (W % 4 == 0).
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
