@@ -403,7 +403,7 @@ def main():
     if fuse_gather:
         abytes["refocus_int"] = abytes["refocus_int_from_aligned"]
     stage_gbs = {nm: abytes[nm] / (stage_ms[nm] * 1e-3) / 1e9 for nm in stage_names}
-    launches_per_step = 2 + 2 + (0 if fuse_gather else 1) + (5 if fuse_post else 2 + 2)
+    launches_per_step = 2 + 2 + (0 if fuse_gather else 1) + (6 if fuse_post else 3 + 2)      # incl. edge_cumsum_kernel
 
     extras = {}
     if not args.no_extras:

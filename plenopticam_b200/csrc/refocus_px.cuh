@@ -200,6 +200,52 @@ refocus_px_kernel(PxArgs p, PxCtl ctl) {
 #undef PCB_PX_NACT
 }
 
+// The edge tables, made cumulative over the view rows in the order "clamped first".  Output row y of slice a takes the
+// view rows whose source row y + a (c0 - j) leaves the image from the edge table; for one side (top / bottom) those rows
+// are always a prefix or a suffix of j (the source row is monotone in j), so with running sums along j stored in place
+// the finalize pass needs ONE table row per side instead of one per clamped view row (a chain of dependent L2 loads that
+// cost 30 % of that pass).  Rows without an unmasked view carry the sum on.  Integer sums: exact, same bits.
+__global__ void __launch_bounds__(256)
+edge_cumsum_kernel(unsigned long long *__restrict__ edgeRG, uint32_t *__restrict__ edgeB, PxCtl ctl, int M, int Tp, int n0) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int sl = blockIdx.y >> 1, side = blockIdx.y & 1;
+    const int a = ctl.a[sl];
+    if (x >= Tp || a == 0) return;                         // a == 0: no source row ever leaves the image
+    const int n = n0 + sl;
+    const bool desc = (a > 0) == (side == 0);              // top of a > 0 and bottom of a < 0 clamp the LARGE j first
+    // all loads first (a load behind a store to the same array would wait for it: M round trips instead of one)
+    unsigned long long vrg[16];
+    uint32_t vb[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int j = desc ? M - 1 - k : k;
+        vrg[k] = 0ull; vb[k] = 0u;
+        if (k < M && ((ctl.row_active >> j) & 1u)) {
+            const size_t e = (size_t)((n * M + j) * 2 + side) * Tp + x;
+            vrg[k] = edgeRG[e]; vb[k] = edgeB[e];
+        }
+    }
+    unsigned long long crg = 0ull;
+    uint32_t cb = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k < M) {
+            const int j = desc ? M - 1 - k : k;
+            const size_t e = (size_t)((n * M + j) * 2 + side) * Tp + x;
+            crg += vrg[k]; cb += vb[k];
+            edgeRG[e] = crg;
+            edgeB[e] = cb;
+        }
+    }
+}
+
+static int launch_edge_cumsum(unsigned long long *edgeRG, uint32_t *edgeB, const PxCtl &ctl, int M, int Tp, int n0, int nloc,
+                              cudaStream_t st) {
+    edge_cumsum_kernel<<<dim3((Tp + 255) / 256, nloc * 2), 256, 0, st>>>(edgeRG, edgeB, ctl, M, Tp, n0);
+    PCB_LAUNCH_OK();
+    return PCB_OK;
+}
+
 // out[n,y,x,:] = (acc[n,y,x] + sum_{j: source row clamped} edge[n,j,side,x]) / M ;  fused min/max.
 // The three floats of a pixel are transposed through shared memory (warp-locally) so that the row leaves in
 // 128-byte runs.
@@ -238,8 +284,6 @@ refocus_px_finalize_kernel(unsigned long long *accRG, uint32_t *accB,
         scale = (hi != lo) && (hi != 0.0);
         inv = scale ? 1.0 / (hi - lo) : 1.0;
     }
-    __shared__ int s_rows[16];     // edge-table row offset ((n*M + j)*2 + side) * Tp of every clamped contribution
-    __shared__ int s_cnt;
     __shared__ float s_tile[PXF_THREADS * 3];
     DivByConst divM;
     divM.init((float)M);
@@ -250,16 +294,18 @@ refocus_px_finalize_kernel(unsigned long long *accRG, uint32_t *accB,
     for (int row = blockIdx.x; row < S * nsl; row += (int)gridDim.x) {
     const int sl = row / S;
     const int y = row - sl * S, n = n0 + sl;
-    if (threadIdx.x < 32) {                    // M <= 16: one lane per view-row, compacted with a ballot
-        const int j = threadIdx.x;
-        const int ys = y + ctl.a[sl] * (M / 2 - j);
-        const bool clamped = j < M && ((ctl.row_active >> j) & 1u) && (ys < 0 || ys > S - 1);
-        const unsigned m = __ballot_sync(0xffffffffu, clamped);
-        if (clamped) s_rows[__popc(m & ((1u << j) - 1u))] = ((n * M + j) * 2 + (ys < 0 ? 0 : 1)) * Tp;
-        if (j == 0) s_cnt = __popc(m);
+    // the view rows whose source row leaves the image at the top / at the bottom are a prefix or a suffix of j: one row
+    // of the CUMULATIVE edge table (edge_cumsum_kernel) per side, that of the least clamped j.  Every warp works it out
+    // for itself (lane = view row), no shared memory, no barrier.
+    int offT = -1, offB = -1;
+    {
+        const int a = ctl.a[sl], lj = threadIdx.x & 31;
+        const int ys = y + a * (M / 2 - lj);
+        const unsigned mt = __ballot_sync(0xffffffffu, lj < M && ys < 0);
+        const unsigned mb = __ballot_sync(0xffffffffu, lj < M && ys > S - 1);
+        if (mt) offT = ((n * M + (a > 0 ? __ffs(mt) - 1 : 31 - __clz(mt))) * 2 + 0) * Tp;
+        if (mb) offB = ((n * M + (a > 0 ? 31 - __clz(mb) : __ffs(mb) - 1)) * 2 + 1) * Tp;
     }
-    __syncthreads();
-    const int cnt = s_cnt;
     const size_t arow = ((size_t)n * S + y) * Tp;
     float *orow = out + ((size_t)n * S + y) * (size_t)T * 3;
     // the accumulator words of PXF_IT row segments are requested up front (the kernel is bound by the latency of
@@ -273,16 +319,33 @@ refocus_px_finalize_kernel(unsigned long long *accRG, uint32_t *accB,
             rg[k] = 0ull; b[k] = 0u;
             if (x < T) { rg[k] = accRG[arow + x]; b[k] = accB[arow + x]; }
         }
+        // ... and so are the (at most two) edge-table rows: every load of the row is in flight before the first sum
+        unsigned long long et[PXF_IT], eb[PXF_IT];
+        uint32_t ft[PXF_IT], fb[PXF_IT];
+#pragma unroll
+        for (int k = 0; k < PXF_IT; ++k) { et[k] = eb[k] = 0ull; ft[k] = fb[k] = 0u; }
+        if (offT >= 0) {
+#pragma unroll
+            for (int k = 0; k < PXF_IT; ++k) {
+                const int x = xb0 + k * PXF_THREADS + threadIdx.x;
+                if (x < T) { et[k] = __ldg(edgeRG + offT + x); ft[k] = __ldg(edgeB + offT + x); }
+            }
+        }
+        if (offB >= 0) {
+#pragma unroll
+            for (int k = 0; k < PXF_IT; ++k) {
+                const int x = xb0 + k * PXF_THREADS + threadIdx.x;
+                if (x < T) { eb[k] = __ldg(edgeRG + offB + x); fb[k] = __ldg(edgeB + offB + x); }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PXF_IT; ++k) { rg[k] += et[k] + eb[k]; b[k] += ft[k] + fb[k]; }
 #pragma unroll
         for (int k = 0; k < PXF_IT; ++k) {
             const int xb = xb0 + k * PXF_THREADS;
             if (xb >= T) break;
             const int x = xb + threadIdx.x;
             if (x < T) {
-                for (int c = 0; c < cnt; ++c) {
-                    rg[k] += __ldg(edgeRG + s_rows[c] + x);
-                    b[k] += __ldg(edgeB + s_rows[c] + x);
-                }
                 const uint32_t v[3] = {(uint32_t)rg[k], (uint32_t)(rg[k] >> 32), b[k]};
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
@@ -314,7 +377,6 @@ refocus_px_finalize_kernel(unsigned long long *accRG, uint32_t *accB,
             }
         }
     }
-    __syncthreads();                           // s_rows / s_cnt are rewritten by the next row
     }
     if (POST != 2 && mm != nullptr) block_minmax_commit(mn, mx, mm);
 }
@@ -450,7 +512,9 @@ static int launch_refocus_px(const PxPlan &pl, const uint16_t *vp, const int32_t
         for (int k = 0; k < RR_MAX_SLICES; ++k) ctl.a[k] = k < nloc ? a_list_host[n0 + k] : 0;
         a.n0 = n0;
         a.nsl = nloc;
-        const int rc = launch_px_threads(pl, a, ctl, st);
+        int rc = launch_px_threads(pl, a, ctl, st);
+        if (rc) return rc;
+        rc = launch_edge_cumsum(a.edgeRG, a.edgeB, ctl, a.M, a.Tp, n0, nloc, st);
         if (rc) return rc;
         const dim3 fgrid = finalize_grid(a.S * nloc);
         if (pl.exact24)

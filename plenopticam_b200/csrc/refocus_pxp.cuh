@@ -471,6 +471,7 @@ static int launch_refocus_pxp(const PxPlan &px, const PxpPlan &pl, const uint16_
                 else
                     rc = pl.ppt == 1 ? launch_pxp_variant<1024, 1>(pl, a, ctl, st) : launch_pxp_variant<1024, 2>(pl, a, ctl, st);
                 if (g_kev[1]) cudaEventRecord(g_kev[1], st);
+                if (rc == PCB_OK) rc = launch_edge_cumsum(a.edgeRG, a.edgeB, fctl, a.M, a.Tp, n0, nloc, st);
                 if (rc == PCB_OK && !post) rc = launch_pxp_finalize<0>(pl, a, fctl, out, n0, nloc, mm, nullptr, leave, st);
             } else if (pass == 1) {
                 rc = launch_pxp_finalize<1>(pl, a, fctl, out, n0, nloc, mm, post->lohi, leave, st);
