@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--no-fuse-gather", action="store_true",
                     help="separate viewpoints kernel + refocus from the 4-D array instead of reading the aligned image")
     ap.add_argument("--no-config1", action="store_true", help="reference arm: skip the one-off configs[0] run")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch the kernels of a step one by one on the stream instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -243,7 +245,11 @@ def workload_config(w, args):
                       "array is materialised on request: see unfused / aligned_lfs_per_s)" if fuse_g
                       else "separate viewpoints kernel",
             "post": "separate contrast kernels" if getattr(args, "no_fuse_post", False)
-                    else "contrast + sRGB fused into the refocus epilogue"}
+                    else "contrast + sRGB fused into the refocus epilogue",
+            "launch": "kernels launched one by one on the stream" if getattr(args, "no_graph", False) or not fuse_g
+                      or getattr(args, "no_fuse_post", False)
+                      else "the launches of a step replayed as one CUDA graph per ring buffer "
+                           "(LightFieldPipeline.capture); stage_ms from a second pass with stream launches and events"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -391,13 +397,34 @@ def main():
         step, stage_names = make_step(False, fuse_post)
     for i in range(W_):
         step(ring[i % 3])
+    use_graph = fuse_gather and fuse_post and not args.no_graph
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    elapsed_ms, events = timed(step, len(stage_names) + 1, K, 0)
-    clocks = sampler.stop() if rank == 0 else None
+    if use_graph:
+        # the same launches (LightFieldPipeline.run_device == `step`), captured once per ring buffer and replayed
+        caps = [pipe.capture(r, out=pipe.post) for r in ring]
+        for i in range(max(W_, 3)):
+            caps[i % 3].replay()
+        if rank == 0:
+            sampler.start()
+        t_b, t_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_b.record(stream)
+        for i in range(K):
+            caps[i % 3].replay()
+        t_e.record(stream)
+        barrier()
+        elapsed_ms = _maxed(torch, dist, world, device, t_b.elapsed_time(t_e))
+        clocks = sampler.stop() if rank == 0 else None
+        _, events = timed(step, len(stage_names) + 1, min(K, 50), 2)          # per-stage times: stream launches + events
+        K_ev = min(K, 50)
+    else:
+        if rank == 0:
+            sampler.start()
+        elapsed_ms, events = timed(step, len(stage_names) + 1, K, 0)
+        clocks = sampler.stop() if rank == 0 else None
+        K_ev = K
     value = world * K * n_slices / (elapsed_ms * 1e-3)
-    stage_ms = {nm: float(np.mean([events[i][k].elapsed_time(events[i][k + 1]) for i in range(K)]))
+    stage_ms = {nm: float(np.mean([events[i][k].elapsed_time(events[i][k + 1]) for i in range(K_ev)]))
                 for k, nm in enumerate(stage_names)}
     abytes = pipe.algorithmic_bytes()
     if fuse_gather:

@@ -180,6 +180,12 @@ class LightFieldPipeline(object):
             return out
         return self.stack
 
+    @_on_own_device
+    def capture(self, raw, out=None):
+        """The launches of `run_device(raw, out)` as a CUDA graph bound to these two tensors (see CapturedExposure): for a
+        stream of exposures of one camera that arrive in the same device buffer(s)."""
+        return CapturedExposure(self, raw, out)
+
     # -- host-buffer entry point -----------------------------------------------------------------------------
     @_on_own_device
     def _staging(self):
@@ -227,6 +233,45 @@ class LightFieldPipeline(object):
             "refocus_int_from_aligned": b_vp_active + self.N * b_sl,
             "post": 2 * self.N * b_sl + 2 * 4 * b_sl,
         }
+
+
+class CapturedExposure(object):
+    """`LightFieldPipeline.run_device(raw, out)` captured once as a CUDA graph and replayed: the ten kernels of an exposure
+    are then launched by one call, and the gaps between them shrink (1.606 -> 1.593 ms per Illum exposure).  The graph is
+    bound to the `raw` tensor (copy or generate the next exposure into it) and to the result tensor `self.out`.
+
+        step = pipe.capture(raw_dev)
+        ...fill raw_dev...; stack = step.replay()      # enqueues on the current stream, returns `step.out`
+
+    The refocus scratch comes back zeroed from every replay and the captured launches rely on that (no memset inside
+    the graph); if another launch dirtied it in between, replay() zeroes it first."""
+
+    def __init__(self, pipe, raw, out=None):
+        self.pipe, self.raw = pipe, raw
+        with torch.cuda.device(pipe.device):
+            self.out = out if out is not None else torch.empty_like(pipe.post if pipe.postprocess else pipe.stack)
+            cur = torch.cuda.current_stream(pipe.device)
+            side = torch.cuda.Stream(device=pipe.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):                        # settles the plans (fused forms, scratch state) before the capture
+                    pipe.run_device(raw, out=self.out)
+                side.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side):
+                    res = pipe.run_device(raw, out=self.out)
+                assert res is self.out
+            cur.wait_stream(side)
+        self._scratch = pipe.refocus_plan.scratch
+
+    def replay(self):
+        with torch.cuda.device(self.pipe.device):
+            if not getattr(self._scratch, "_pcb_acc_zero", False):
+                self._scratch.zero_()
+            self._scratch._pcb_acc_zero = False
+            self.graph.replay()
+            self._scratch._pcb_acc_zero = True
+        return self.out
 
 
 class ExposureStream(object):

@@ -248,3 +248,28 @@ def test_float32_exposures_through_the_pipelined_resampler(cuda, pat, W4, negati
     finally:
         os.environ.pop("PCB_RESAMPLE_KERNEL", None)
     assert float((al32 - al_t).abs().max()) <= 2e-6 * 65535
+
+
+def test_captured_exposure_replays_like_the_stream_launches(cuda):
+    """LightFieldPipeline.capture: the launches of one exposure as a CUDA graph; replays on new contents of the bound raw
+    tensor equal run_device, also after a launch that left the shared refocus scratch dirty."""
+    import torch
+    from plenopticam_b200 import ops
+    from plenopticam_b200.misc import synth
+    from plenopticam_b200.pipeline import LightFieldPipeline
+    w = synth.illum_workload(9, small=True)
+    cent = synth.illum_centroids(w)
+    raws = [ops.to_device(synth.synth_raw(w["H"], w["W"], 3, seed=s)) for s in (4, 5, 6)]
+    pipe = LightFieldPipeline(cent, tuple(raws[0].shape), np.uint16, w["M"], w["pat"], ran_refo=w["ran_refo"])
+    refs = [pipe.run_device(r).clone() for r in raws]
+    buf = raws[0].clone()
+    step = pipe.capture(buf)
+    for k in (1, 2, 0, 2):
+        buf.copy_(raws[k])
+        assert torch.equal(step.replay(), refs[k]), k
+    pipe.viewpoints()
+    pipe.refocus()                                       # the 4-D form: leaves the shared accumulators dirty
+    assert pipe.refocus_plan.scratch._pcb_acc_zero is False
+    buf.copy_(raws[1])
+    assert torch.equal(step.replay(), refs[1])
+    assert torch.equal(pipe.run_device(raws[2]), refs[2])              # and stream launches after a replay
